@@ -1,0 +1,47 @@
+"""Convert the reference's own golden fixtures for the assembly path into small .npz files.
+
+Run HERE (the build container), where /root/reference exists; the GPU box only sees the .npz files.
+Sources (fixtures 1,2,3,5,7) -- Python-2 pickles holding only numpy arrays and
+scalars, loaded with encoding='latin1':
+
+  1,2  sucemfem/ProblemConfigurations/tests/LHS_matrix.npy, RHS_vector.pickle
+       (test: sucemfem/ProblemConfigurations/tests/test_EMDrivenProblem.py:64-82)
+  3    sucemfem/Sources/tests/fillament_source_test_data.pickle
+       (test: sucemfem/Sources/tests/test_fillament_source.py:62-69)
+  5    sucemfem/PostProcessing/tests/data/power_flux_reference_dofs_...pickle
+       (generator: sucemfem/PostProcessing/tests/data/power_flux_generate_dofs.py:44-92)
+  7    sucemfem/PostProcessing/tests/data/reference_dofs-2-0.149896229-0.0499654096667.pickle
+       (generator: sucemfem/PostProcessing/tests/data/ntff_generate_dofs.py:40-85)
+"""
+import os
+import pickle
+
+import numpy as np
+
+REF = '/root/reference/sucemfem/'
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def load(p):
+    with open(REF + p, 'rb') as f:
+        return pickle.load(f, encoding='latin1')
+
+
+def main():
+    lhs = np.load(REF + 'ProblemConfigurations/tests/LHS_matrix.npy')
+    rhs = load('ProblemConfigurations/tests/RHS_vector.pickle')
+    np.savez_compressed(os.path.join(HERE, 'driven_order1_inscribedtet.npz'), LHS=lhs, RHS=np.asarray(rhs),
+                        frequency=1e8, source_coord=np.zeros(3), source_value=np.array([2, -1, 3.]))
+    d = load('Sources/tests/fillament_source_test_data.pickle')
+    np.savez_compressed(os.path.join(HERE, 'fillament_source_order2.npz'), **{k: np.asarray(v) for k, v in d.items()})
+    d = load('PostProcessing/tests/data/power_flux_reference_dofs_f-1000000000.000000_o-2_s-0.074948_'
+             'l-0.100000_h-0.166667.pickle')
+    np.savez_compressed(os.path.join(HERE, 'driven_order2_unitcube3.npz'), x=d['x'], freq=d['freq'],
+                        order=d['order'], source_endpoints=d['source_endpoints'], I=d['I'],
+                        known_answer_variational_flux=np.complex128(26.9015957282 - 7.85747240242e-08j))
+    d = load('PostProcessing/tests/data/reference_dofs-2-0.149896229-0.0499654096667.pickle')
+    np.savez_compressed(os.path.join(HERE, 'driven_order2_unitcube5.npz'), **{k: np.asarray(v) for k, v in d.items()})
+
+
+if __name__ == '__main__':
+    main()
