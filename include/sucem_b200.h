@@ -1,0 +1,139 @@
+/*
+ * sucem_b200.h -- C ABI of libsucem_b200.so: B200-native N1curl (Nedelec 1st kind, order 1-2) assembly
+ * of the curl-curl stiffness S, mass M(=T) and first-order-ABC boundary matrix S_0 with PEC row
+ * elimination, on tetrahedra and triangles.
+ *
+ * The reference (cemagg/sucem-fem) has NO FFI of its own for this path: it reaches DOLFIN through its
+ * SWIG Python module at exactly two call sites,
+ *     dolfin.assemble(form, tensor=mat)                 sucemfem/SystemMatrices.py:54
+ *     self.boundary_conditions.apply_essential(mat)     sucemfem/SystemMatrices.py:55
+ * plus dolfin.FunctionSpace(mesh, family, order)        sucemfem/ProblemConfigurations/EMProblem.py:100-105
+ * Each entry point below names the reference interface (file:line, relative to /root/reference) whose
+ * work it replaces.  INTEGRATION.md shows the ctypes binding a maintainer adds on the reference side.
+ *
+ * Conventions
+ *   - every function returns 0 on success, non-zero on failure; sfem_last_error() returns a
+ *     thread-local message for the last failing call on the calling thread.
+ *   - handles are opaque, created and destroyed by the library; a handle is bound to the CUDA device
+ *     that was current at creation.  No global mutable state; calls on different handles are re-entrant.
+ *   - all bulk arrays are caller-owned DEVICE pointers (e.g. torch tensors' data_ptr()); the library
+ *     never frees them and they must outlive the handle that was created from them.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = default stream).  Calls are asynchronous with
+ *     respect to the host unless stated; creation calls synchronise the stream before returning because
+ *     they return sizes.
+ */
+#ifndef SUCEM_B200_H
+#define SUCEM_B200_H
+
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#define SFEM_API __attribute__((visibility("default")))
+#else
+#define SFEM_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct sfem_mesh_s* sfem_mesh_t;
+typedef struct sfem_space_s* sfem_space_t;
+typedef struct sfem_pattern_s* sfem_pattern_t;
+
+/* forms: which bilinear form a value array is assembled for */
+enum {
+  SFEM_FORM_MASS = 0,      /* eps_r*inner(v,u)*dx              sucemfem/Forms.py:71-77            */
+  SFEM_FORM_STIFFNESS = 1, /* dot(curl(v),curl(u))/mu_r*dx     sucemfem/Forms.py:79-85            */
+  SFEM_FORM_ABC = 2        /* inner(cross(n,v),cross(n,u))*ds  sucemfem/BoundaryConditions/ABC.py:56-57 */
+};
+
+/* kernel variants for the S/M value kernels */
+enum {
+  SFEM_KERNEL_AUTO = 0,    /* fastest available for the space                                    */
+  SFEM_KERNEL_GENERIC = 1, /* row-owner gather with full reference tensors (any dim/order)       */
+  SFEM_KERNEL_CANONICAL = 2/* canonical-frame straight-line kernels (tets)                       */
+};
+
+SFEM_API const char* sfem_last_error(void);
+/* "sucem_b200 <version> sm_100a" */
+SFEM_API const char* sfem_version(void);
+
+/* ---- mesh: replaces dolfin.Mesh / UnitCube / UnitSquare as inputs of the path -------------------
+ * (examples/resonant_cavity/driver.py:34, sucemfem/Utilities/MeshGenerators.py:32-36).
+ * gdim = 2 (triangles) or 3 (tetrahedra). d_coords: double [n_vertices][gdim]; d_cells: int32
+ * [n_cells][gdim+1], each cell's vertex ids ascending (UFC order; checked, error otherwise). */
+SFEM_API int sfem_mesh_create(int gdim, int64_t n_vertices, const double* d_coords, int64_t n_cells,
+                     const int32_t* d_cells, void* stream, sfem_mesh_t* out);
+SFEM_API int sfem_mesh_destroy(sfem_mesh_t mesh);
+
+/* Fill a structured UnitCube(nx,ny,nz) / UnitSquare(nx,ny) mesh on the device (DOLFIN 1.0 layout,
+ * SURVEY 8.1-M): d_coords double [(nx+1)(ny+1)(nz+1)][3], d_cells int32 [6 nx ny nz][4] (nz = 0: the
+ * 2-D right-diagonal square, [2 nx ny][3]).  Coordinates are scale*(i/n) + shift per axis. */
+SFEM_API int sfem_fill_unit_mesh(int nx, int ny, int nz, const double* scale3, const double* shift3,
+                        double* d_coords, int32_t* d_cells, void* stream);
+
+/* ---- function space + dof map: replaces dolfin.FunctionSpace(mesh, "Nedelec 1st kind H(curl)", order)
+ * (sucemfem/ProblemConfigurations/EMProblem.py:36,100-105): numbers edges (and faces) by first
+ * appearance, builds the cell->entity tables and the entity->cell incidence lists (sort/scan kernels). */
+SFEM_API int sfem_space_create(sfem_mesh_t mesh, int order, void* stream, sfem_space_t* out);
+SFEM_API int sfem_space_destroy(sfem_space_t space);
+/* global_dimension() (EMProblem.py:44-47), #edges, #faces (0 in 2-D), dofs per cell */
+SFEM_API int sfem_space_info(sfem_space_t space, int64_t* ndof, int64_t* n_edges, int64_t* n_faces, int* ndof_cell);
+/* dofmap.tabulate_dofs for every cell (sucemfem/Sources/point_source.py:81): int32 [n_cells][ndof_cell] */
+SFEM_API int sfem_space_cell_dofs(sfem_space_t space, int32_t* d_out, void* stream);
+/* cell->edge int32 [n_cells][6|3] and (3-D) cell->face int32 [n_cells][4] tables (either may be NULL) */
+SFEM_API int sfem_space_cell_entities(sfem_space_t space, int32_t* d_cell_edges, int32_t* d_cell_faces, void* stream);
+/* number of facets (faces in 3-D, edges in 2-D) = size of a facet MeshFunction */
+SFEM_API int sfem_space_num_facets(sfem_space_t space, int64_t* n_facets);
+
+/* DomainBoundary().mark(mesh_function, value) (sucemfem/BoundaryConditions/essential.py:93-97):
+ * d_markers uint32 [n_facets]; facets with exactly one incident cell are set to `value`, others untouched. */
+SFEM_API int sfem_mark_exterior_facets(sfem_space_t space, uint32_t* d_markers, uint32_t value, void* stream);
+/* dofs constrained by DirichletBC(V, zero, mesh_function, region) (essential.py:77-80): sets
+ * d_row_flags[dof] = 1 (uint8 [ndof], not cleared first) for every dof in the closure of a facet whose
+ * marker == region. */
+SFEM_API int sfem_pec_row_flags(sfem_space_t space, const uint32_t* d_markers, uint32_t region, uint8_t* d_row_flags,
+                       void* stream);
+
+/* Materials: coef[c] = value_of_region[region[c]] (sucemfem/Materials.py:135-146).  d_regions uint32
+ * [n_cells]; region_ids/values host arrays of length n_regions.  On an unknown region returns non-zero
+ * and stores that region number in *bad_region (caller raises ValueError like Materials.py:147-148). */
+SFEM_API int sfem_expand_material(int64_t n_cells, const uint32_t* d_regions, int n_regions, const uint32_t* region_ids,
+                         const double* values, double* d_out, uint32_t* bad_region, void* stream);
+
+/* ---- sparsity pattern: replaces DOLFIN's SparsityPatternBuilder + tensor init inside dolfin.assemble
+ * (sucemfem/SystemMatrices.py:54).  Rows are owned by DOF-entity: the pattern covers the rows of the
+ * entities [ent_lo, ent_hi) of the combined entity numbering (edges, then faces / cell interiors), i.e.
+ * dof rows [order*ent_lo, order*ent_hi).  ent_lo = 0, ent_hi = -1 means all rows.  Multi-GPU: each rank
+ * builds the block it owns; assembly of a block needs no communication. */
+SFEM_API int sfem_pattern_create(sfem_space_t space, int64_t ent_lo, int64_t ent_hi, void* stream, sfem_pattern_t* out);
+SFEM_API int sfem_pattern_destroy(sfem_pattern_t pat);
+SFEM_API int sfem_pattern_info(sfem_pattern_t pat, int64_t* row_begin, int64_t* n_rows, int64_t* nnz);
+/* CSR arrays as returned by A.data() (sucemfem/Utilities/Converters.py:37): d_rowptr int64 [n_rows+1]
+ * (offsets into this block), d_cols int32 [nnz] global column ids ascending within a row. */
+SFEM_API int sfem_pattern_export(sfem_pattern_t pat, int64_t* d_rowptr, int32_t* d_cols, void* stream);
+/* Split [0, n_entities) into nparts contiguous entity ranges of (nearly) equal nnz; host int64 [nparts+1]. */
+SFEM_API int sfem_partition_rows(sfem_space_t space, int nparts, int64_t* ent_bounds, void* stream);
+
+/* ---- values: replaces dolfin.assemble(form, tensor=mat) + apply_essential(mat)
+ * (sucemfem/SystemMatrices.py:54-55).  d_coef: per-cell double [n_cells] (eps_r for MASS, mu_r for
+ * STIFFNESS; NULL = 1.0; ignored for ABC).  d_pec_row_flags: uint8 [ndof] or NULL; flagged rows are
+ * written as unit rows (row-only ident, pattern kept).  d_values: double [nnz of the pattern block].
+ * For ABC, d_facet_mask uint8 [n_facets] or NULL selects the facets to integrate over (NULL = all
+ * exterior facets, what ABC.py:32-33 does). */
+SFEM_API int sfem_assemble(sfem_pattern_t pat, int form, const double* d_coef, const uint8_t* d_facet_mask,
+                  const uint8_t* d_pec_row_flags, double* d_values, int kernel, void* stream);
+/* Fused S and M(=T) in one pass over the rows (the benchmarked hot path). */
+SFEM_API int sfem_assemble_ST(sfem_pattern_t pat, const double* d_eps_r, const double* d_mu_r,
+                     const uint8_t* d_pec_row_flags, double* d_S, double* d_T, int kernel, void* stream);
+
+/* DirichletBC.apply(A) -> GenericMatrix::ident (sucemfem/BoundaryConditions/essential.py:77-81, called from
+ * sucemfem/BoundaryConditions/container.py:39-42) as a separate step on already assembled values:
+ * flagged rows of the block become unit rows, pattern kept, columns untouched. */
+SFEM_API int sfem_apply_ident(sfem_pattern_t pat, const uint8_t* d_row_flags, double* d_values, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SUCEM_B200_H */

@@ -1,0 +1,430 @@
+// C ABI of libsucem_b200.so (declared in include/sucem_b200.h) and the small device helpers that sit
+// either side of the assembly kernels: structured mesh fill, exterior-facet marking, PEC row flags,
+// material expansion, row partitioning.
+#include <cub/cub.cuh>
+
+#include <vector>
+
+#include "sfem_internal.h"
+
+namespace sfem {
+static thread_local std::string g_last_error;
+void set_error(const std::string& msg) { g_last_error = msg; }
+
+namespace {
+inline unsigned grid_for(int64_t n, int bs = 256) { return (unsigned)((n + bs - 1) / bs); }
+
+struct DeviceGuard {
+  int prev = -1;
+  explicit DeviceGuard(int dev) {
+    cudaGetDevice(&prev);
+    if (prev != dev) cudaSetDevice(dev);
+  }
+  ~DeviceGuard() {
+    int cur = -1;
+    cudaGetDevice(&cur);
+    if (cur != prev && prev >= 0) cudaSetDevice(prev);
+  }
+};
+
+// UnitCube / UnitSquare of DOLFIN 1.0: vertex id = ix + (nx+1) iy + (nx+1)(ny+1) iz; cube
+// (ix,iy,iz), x fastest, emits six tets in a fixed order, each vertex-sorted.
+__global__ void k_fill_coords(int nx, int ny, int nz, double sx, double sy, double sz, double tx, double ty,
+                              double tz, double* __restrict__ coords, int64_t V) {
+  int64_t v = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (v >= V) return;
+  int64_t ix = v % (nx + 1), iy = (v / (nx + 1)) % (ny + 1), iz = v / ((int64_t)(nx + 1) * (ny + 1));
+  if (nz > 0) {
+    coords[v * 3 + 0] = ((double)ix / (double)nx) * sx + tx;
+    coords[v * 3 + 1] = ((double)iy / (double)ny) * sy + ty;
+    coords[v * 3 + 2] = ((double)iz / (double)nz) * sz + tz;
+  } else {
+    coords[v * 2 + 0] = ((double)ix / (double)nx) * sx + tx;
+    coords[v * 2 + 1] = ((double)iy / (double)ny) * sy + ty;
+  }
+}
+
+__device__ __forceinline__ void sort4(int32_t* v) {
+#define SFEM_CSWAP(a, b) { int32_t lo = min(v[a], v[b]), hi = max(v[a], v[b]); v[a] = lo; v[b] = hi; }
+  SFEM_CSWAP(0, 1) SFEM_CSWAP(2, 3) SFEM_CSWAP(0, 2) SFEM_CSWAP(1, 3) SFEM_CSWAP(1, 2)
+#undef SFEM_CSWAP
+}
+
+__global__ void k_fill_cells3(int nx, int ny, int nz, int32_t* __restrict__ cells, int64_t ncube) {
+  int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (q >= ncube) return;
+  int64_t ix = q % nx, iy = (q / nx) % ny, iz = q / ((int64_t)nx * ny);
+  const int32_t sx = 1, sy = nx + 1, sz = (nx + 1) * (ny + 1);
+  const int32_t v0 = (int32_t)(ix + sy * iy + (int64_t)sz * iz);
+  const int32_t cv[8] = {v0, v0 + sx, v0 + sy, v0 + sy + sx, v0 + sz, v0 + sz + sx, v0 + sz + sy, v0 + sz + sy + sx};
+  const int t[6][4] = {{0, 1, 3, 7}, {0, 1, 7, 5}, {0, 5, 7, 4}, {0, 3, 2, 7}, {0, 6, 4, 7}, {0, 2, 6, 7}};
+  for (int k = 0; k < 6; ++k) {
+    int32_t v[4] = {cv[t[k][0]], cv[t[k][1]], cv[t[k][2]], cv[t[k][3]]};
+    sort4(v);
+    *reinterpret_cast<int4*>(cells + (q * 6 + k) * 4) = make_int4(v[0], v[1], v[2], v[3]);
+  }
+}
+
+__global__ void k_fill_cells2(int nx, int ny, int32_t* __restrict__ cells, int64_t nsq) {
+  int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (q >= nsq) return;
+  int64_t ix = q % nx, iy = q / nx;
+  const int32_t v0 = (int32_t)(ix + (int64_t)(nx + 1) * iy), v1 = v0 + 1, v2 = v0 + nx + 1, v3 = v2 + 1;
+  int32_t* o = cells + q * 6;
+  o[0] = v0; o[1] = v1; o[2] = v3;   // right diagonal: (v0,v1,v3), (v0,v2,v3) -- already ascending
+  o[3] = v0; o[4] = v2; o[5] = v3;
+}
+
+__global__ void k_mark_exterior(const uint8_t* __restrict__ ncells, uint32_t* __restrict__ markers, uint32_t value,
+                                int64_t n) {
+  int64_t f = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (f < n && ncells[f] == 1) markers[f] = value;
+}
+
+// closure dofs of marked facets: tet face -> its 3 edges (q dofs each) + q(q-1) face dofs; triangle edge -> q dofs
+__global__ void k_pec_flags(const uint32_t* __restrict__ markers, uint32_t region, int dim, int q, int64_t E,
+                            const int32_t* __restrict__ first_cell, const uint8_t* __restrict__ first_loc,
+                            const int32_t* __restrict__ cell_edges, uint8_t* __restrict__ flags, int64_t n) {
+  int64_t f = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (f >= n || markers[f] != region) return;
+  if (dim == 2) {
+    for (int k = 0; k < q; ++k) flags[q * f + k] = 1;
+    return;
+  }
+  const int64_t c = first_cell[f];
+  const int lf = first_loc[f];
+  for (int j = 0; j < 3; ++j) {
+    const int64_t e = cell_edges[c * 6 + tet_face_edge(lf, j)];
+    for (int k = 0; k < q; ++k) flags[q * e + k] = 1;
+  }
+  if (q == 2) {
+    flags[2 * (E + f)] = 1;
+    flags[2 * (E + f) + 1] = 1;
+  }
+}
+
+__global__ void k_expand_material(const uint32_t* __restrict__ regions, int nreg, const uint32_t* __restrict__ ids,
+                                  const double* __restrict__ vals, double* __restrict__ out, int64_t C,
+                                  unsigned long long* __restrict__ bad) {
+  int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const uint32_t r = regions[c];
+  for (int i = 0; i < nreg; ++i)
+    if (ids[i] == r) {
+      out[c] = vals[i];
+      return;
+    }
+  atomicMin(bad, ((unsigned long long)c << 32) | r);  // first offending cell wins, like the reference's loop
+}
+
+__global__ void k_cell_dofs(SpaceView sv, int q, int64_t C, int32_t* __restrict__ out) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  const int nd = q * sv.n_ent_cell;
+  if (i >= C * nd) return;
+  int64_t c = i / nd;
+  int j = (int)(i - c * nd), u = j / q, k = j - u * q;
+  out[i] = q * sv.ent(c, u) + k;
+}
+
+// weight of an entity row for partitioning = its number of (entity-level) incidences * entities per cell
+// (an upper bound proportional to the row's nnz); prefix sums are searched on the host.
+__global__ void k_find_bounds(const int64_t* __restrict__ inc_ptr, int64_t n, int nparts, int64_t* __restrict__ out) {
+  int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p > nparts) return;
+  const int64_t total = inc_ptr[n] - inc_ptr[0];
+  const int64_t target = inc_ptr[0] + (int64_t)((__int128)total * p / nparts);
+  int64_t lo = 0, hi = n;
+  while (lo < hi) {
+    int64_t mid = (lo + hi) >> 1;
+    if (inc_ptr[mid] < target) lo = mid + 1; else hi = mid;
+  }
+  out[p] = p == nparts ? n : lo;
+}
+
+// row-only ident on assembled values: one warp per row entity
+__global__ void k_ident(const int64_t* __restrict__ ent_rowptr, const int32_t* __restrict__ ent_cols, int q,
+                        int64_t ent_lo, int64_t n_rows, const uint8_t* __restrict__ flags,
+                        double* __restrict__ vals) {
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t r = blockIdx.x * (int64_t)(blockDim.x >> 5) + w;
+  if (r >= n_rows) return;
+  const int64_t g = ent_lo + r;
+  const int64_t a = ent_rowptr[r];
+  const int len = (int)(ent_rowptr[r + 1] - a);
+  for (int k = 0; k < q; ++k) {
+    if (!flags[q * g + k]) continue;
+    const int64_t rs = (int64_t)q * q * a + (int64_t)k * q * len;
+    for (int idx = lane; idx < q * len; idx += 32) {
+      int s = idx / q, kp = idx - s * q;
+      vals[rs + idx] = (ent_cols[a + s] == g && kp == k) ? 1.0 : 0.0;
+    }
+  }
+}
+
+}  // namespace
+}  // namespace sfem
+
+using namespace sfem;
+
+extern "C" {
+
+const char* sfem_last_error(void) { return g_last_error.c_str(); }
+const char* sfem_version(void) { return "sucem_b200 0.1 sm_100a"; }
+
+int sfem_mesh_create(int gdim, int64_t n_vertices, const double* d_coords, int64_t n_cells,
+                     const int32_t* d_cells, void* stream, sfem_mesh_t* out) {
+  (void)stream;
+  SFEM_CHECK(out != nullptr, "out is NULL");
+  SFEM_CHECK(gdim == 2 || gdim == 3, "gdim must be 2 or 3");
+  SFEM_CHECK(n_vertices > 0 && n_cells > 0 && d_coords && d_cells, "empty mesh or NULL arrays");
+  SFEM_CHECK(n_vertices < (int64_t)2147483647, "too many vertices for int32 connectivity");
+  auto* m = new sfem_mesh_s();
+  SFEM_CUDA(cudaGetDevice(&m->device));
+  m->gdim = gdim;
+  m->nv = gdim + 1;
+  m->V = n_vertices;
+  m->C = n_cells;
+  m->coords = d_coords;
+  m->cells = d_cells;
+  *out = m;
+  return 0;
+}
+
+int sfem_mesh_destroy(sfem_mesh_t mesh) {
+  delete mesh;
+  return 0;
+}
+
+int sfem_fill_unit_mesh(int nx, int ny, int nz, const double* scale3, const double* shift3, double* d_coords,
+                        int32_t* d_cells, void* stream) {
+  SFEM_CHECK(nx > 0 && ny > 0 && nz >= 0 && d_coords && d_cells, "bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  const double s[3] = {scale3 ? scale3[0] : 1.0, scale3 ? scale3[1] : 1.0, scale3 ? scale3[2] : 1.0};
+  const double t[3] = {shift3 ? shift3[0] : 0.0, shift3 ? shift3[1] : 0.0, shift3 ? shift3[2] : 0.0};
+  const int64_t V = (int64_t)(nx + 1) * (ny + 1) * (nz + 1);
+  SFEM_CHECK(V < (int64_t)2147483647, "too many vertices for int32 connectivity");
+  k_fill_coords<<<grid_for(V), 256, 0, st>>>(nx, ny, nz, s[0], s[1], s[2], t[0], t[1], t[2], d_coords, V);
+  if (nz > 0) {
+    const int64_t nc = (int64_t)nx * ny * nz;
+    k_fill_cells3<<<grid_for(nc), 256, 0, st>>>(nx, ny, nz, d_cells, nc);
+  } else {
+    const int64_t nc = (int64_t)nx * ny;
+    k_fill_cells2<<<grid_for(nc), 256, 0, st>>>(nx, ny, d_cells, nc);
+  }
+  SFEM_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int sfem_space_create(sfem_mesh_t mesh, int order, void* stream, sfem_space_t* out) {
+  SFEM_CHECK(mesh && out, "NULL argument");
+  SFEM_CHECK(order == 1 || order == 2, "only N1curl order 1 and 2 are supported");
+  DeviceGuard dg(mesh->device);
+  auto* sp = new sfem_space_s();
+  sp->mesh = mesh;
+  sp->device = mesh->device;
+  sp->order = order;
+  int rc = build_numbering(sp, (cudaStream_t)stream);
+  if (rc != 0) {
+    sfem_space_destroy(sp);
+    return rc;
+  }
+  *out = sp;
+  return 0;
+}
+
+int sfem_space_destroy(sfem_space_t sp) {
+  if (!sp) return 0;
+  DeviceGuard dg(sp->device);
+  cudaFree(sp->cell_edges);
+  cudaFree(sp->cell_faces);
+  cudaFree(sp->inc_ptr);
+  cudaFree(sp->inc_cell);
+  cudaFree(sp->inc_loc);
+  cudaFree(sp->facet_ncells);
+  cudaFree(sp->facet_first_cell);
+  cudaFree(sp->facet_first_loc);
+  cudaFree(sp->cell_extmask);
+  delete sp;
+  return 0;
+}
+
+int sfem_space_info(sfem_space_t sp, int64_t* ndof, int64_t* n_edges, int64_t* n_faces, int* ndof_cell) {
+  SFEM_CHECK(sp, "NULL space");
+  if (ndof) *ndof = sp->ndof;
+  if (n_edges) *n_edges = sp->E;
+  if (n_faces) *n_faces = sp->F;
+  if (ndof_cell) *ndof_cell = sp->ndof_cell;
+  return 0;
+}
+
+int sfem_space_num_facets(sfem_space_t sp, int64_t* n_facets) {
+  SFEM_CHECK(sp && n_facets, "NULL argument");
+  *n_facets = sp->n_facets;
+  return 0;
+}
+
+int sfem_space_cell_dofs(sfem_space_t sp, int32_t* d_out, void* stream) {
+  SFEM_CHECK(sp && d_out, "NULL argument");
+  SFEM_CHECK(sp->ndof < (int64_t)2147483647, "dof ids exceed int32");
+  DeviceGuard dg(sp->mesh->device);
+  const int64_t n = sp->mesh->C * sp->ndof_cell;
+  k_cell_dofs<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>(make_view(sp), sp->order, sp->mesh->C, d_out);
+  SFEM_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int sfem_space_cell_entities(sfem_space_t sp, int32_t* d_cell_edges, int32_t* d_cell_faces, void* stream) {
+  SFEM_CHECK(sp, "NULL space");
+  DeviceGuard dg(sp->mesh->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (d_cell_edges)
+    SFEM_CUDA(cudaMemcpyAsync(d_cell_edges, sp->cell_edges, sp->mesh->C * sp->ne_loc * 4, cudaMemcpyDeviceToDevice, st));
+  if (d_cell_faces) {
+    SFEM_CHECK(sp->cell_faces, "no faces in 2-D");
+    SFEM_CUDA(cudaMemcpyAsync(d_cell_faces, sp->cell_faces, sp->mesh->C * 16, cudaMemcpyDeviceToDevice, st));
+  }
+  return 0;
+}
+
+int sfem_mark_exterior_facets(sfem_space_t sp, uint32_t* d_markers, uint32_t value, void* stream) {
+  SFEM_CHECK(sp && d_markers, "NULL argument");
+  DeviceGuard dg(sp->mesh->device);
+  k_mark_exterior<<<grid_for(sp->n_facets), 256, 0, (cudaStream_t)stream>>>(sp->facet_ncells, d_markers, value,
+                                                                             sp->n_facets);
+  SFEM_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int sfem_pec_row_flags(sfem_space_t sp, const uint32_t* d_markers, uint32_t region, uint8_t* d_row_flags,
+                       void* stream) {
+  SFEM_CHECK(sp && d_markers && d_row_flags, "NULL argument");
+  DeviceGuard dg(sp->mesh->device);
+  k_pec_flags<<<grid_for(sp->n_facets), 256, 0, (cudaStream_t)stream>>>(
+      d_markers, region, sp->mesh->gdim, sp->order, sp->E, sp->facet_first_cell, sp->facet_first_loc,
+      sp->cell_edges, d_row_flags, sp->n_facets);
+  SFEM_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int sfem_expand_material(int64_t n_cells, const uint32_t* d_regions, int n_regions, const uint32_t* region_ids,
+                         const double* values, double* d_out, uint32_t* bad_region, void* stream) {
+  SFEM_CHECK(d_regions && region_ids && values && d_out && n_regions > 0, "bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  uint32_t* d_ids = nullptr;
+  double* d_vals = nullptr;
+  unsigned long long* d_bad = nullptr;
+  SFEM_CUDA(cudaMalloc(&d_ids, n_regions * 4));
+  SFEM_CUDA(cudaMalloc(&d_vals, n_regions * 8));
+  SFEM_CUDA(cudaMalloc(&d_bad, 8));
+  SFEM_CUDA(cudaMemcpyAsync(d_ids, region_ids, n_regions * 4, cudaMemcpyHostToDevice, st));
+  SFEM_CUDA(cudaMemcpyAsync(d_vals, values, n_regions * 8, cudaMemcpyHostToDevice, st));
+  SFEM_CUDA(cudaMemsetAsync(d_bad, 0xff, 8, st));
+  k_expand_material<<<grid_for(n_cells), 256, 0, st>>>(d_regions, n_regions, d_ids, d_vals, d_out, n_cells, d_bad);
+  unsigned long long h_bad = 0;
+  SFEM_CUDA(cudaMemcpyAsync(&h_bad, d_bad, 8, cudaMemcpyDeviceToHost, st));
+  SFEM_CUDA(cudaStreamSynchronize(st));
+  cudaFree(d_ids);
+  cudaFree(d_vals);
+  cudaFree(d_bad);
+  if (h_bad != ~0ull) {
+    if (bad_region) *bad_region = (uint32_t)(h_bad & 0xffffffffu);
+    set_error("Material number " + std::to_string((uint32_t)(h_bad & 0xffffffffu)) + " not found");
+    return 4;
+  }
+  return 0;
+}
+
+int sfem_pattern_create(sfem_space_t sp, int64_t ent_lo, int64_t ent_hi, void* stream, sfem_pattern_t* out) {
+  SFEM_CHECK(sp && out, "NULL argument");
+  if (ent_hi < 0) ent_hi = sp->n_ent;
+  SFEM_CHECK(0 <= ent_lo && ent_lo <= ent_hi && ent_hi <= sp->n_ent, "entity range out of bounds");
+  DeviceGuard dg(sp->mesh->device);
+  auto* pat = new sfem_pattern_s();
+  pat->space = sp;
+  pat->device = sp->device;
+  pat->ent_lo = ent_lo;
+  pat->ent_hi = ent_hi;
+  pat->n_rows_ent = ent_hi - ent_lo;
+  int rc = build_pattern(pat, (cudaStream_t)stream);
+  if (rc != 0) {
+    sfem_pattern_destroy(pat);
+    return rc;
+  }
+  *out = pat;
+  return 0;
+}
+
+int sfem_pattern_destroy(sfem_pattern_t pat) {
+  if (!pat) return 0;
+  DeviceGuard dg(pat->device);
+  cudaFree(pat->ent_rowptr);
+  cudaFree(pat->ent_cols);
+  cudaFree(pat->pos);
+  delete pat;
+  return 0;
+}
+
+int sfem_pattern_info(sfem_pattern_t pat, int64_t* row_begin, int64_t* n_rows, int64_t* nnz) {
+  SFEM_CHECK(pat, "NULL pattern");
+  const int q = pat->space->order;
+  if (row_begin) *row_begin = q * pat->ent_lo;
+  if (n_rows) *n_rows = q * pat->n_rows_ent;
+  if (nnz) *nnz = (int64_t)q * q * pat->nnz_ent;
+  return 0;
+}
+
+int sfem_pattern_export(sfem_pattern_t pat, int64_t* d_rowptr, int32_t* d_cols, void* stream) {
+  SFEM_CHECK(pat && d_rowptr, "NULL argument");
+  SFEM_CHECK(pat->space->ndof < (int64_t)2147483647, "column ids exceed int32");
+  DeviceGuard dg(pat->space->mesh->device);
+  return export_pattern(pat, d_rowptr, d_cols, (cudaStream_t)stream);
+}
+
+int sfem_partition_rows(sfem_space_t sp, int nparts, int64_t* ent_bounds, void* stream) {
+  SFEM_CHECK(sp && ent_bounds && nparts > 0, "bad arguments");
+  DeviceGuard dg(sp->mesh->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  int64_t* d_out = nullptr;
+  SFEM_CUDA(cudaMalloc(&d_out, (nparts + 1) * 8));
+  k_find_bounds<<<grid_for(nparts + 1, 64), 64, 0, st>>>(sp->inc_ptr, sp->n_ent, nparts, d_out);
+  SFEM_CUDA(cudaMemcpyAsync(ent_bounds, d_out, (nparts + 1) * 8, cudaMemcpyDeviceToHost, st));
+  SFEM_CUDA(cudaStreamSynchronize(st));
+  cudaFree(d_out);
+  ent_bounds[0] = 0;
+  return 0;
+}
+
+int sfem_apply_ident(sfem_pattern_t pat, const uint8_t* d_row_flags, double* d_values, void* stream) {
+  SFEM_CHECK(pat && d_row_flags && d_values, "NULL argument");
+  DeviceGuard dg(pat->space->mesh->device);
+  if (pat->n_rows_ent == 0) return 0;
+  k_ident<<<(unsigned)((pat->n_rows_ent + 7) / 8), 256, 0, (cudaStream_t)stream>>>(
+      pat->ent_rowptr, pat->ent_cols, pat->space->order, pat->ent_lo, pat->n_rows_ent, d_row_flags, d_values);
+  SFEM_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int sfem_assemble(sfem_pattern_t pat, int form, const double* d_coef, const uint8_t* d_facet_mask,
+                  const uint8_t* d_pec_row_flags, double* d_values, int kernel, void* stream) {
+  SFEM_CHECK(pat && d_values, "NULL argument");
+  SFEM_CHECK(form == SFEM_FORM_MASS || form == SFEM_FORM_STIFFNESS || form == SFEM_FORM_ABC, "unknown form");
+  SFEM_CHECK(kernel != SFEM_KERNEL_CANONICAL, "the canonical kernels assemble S and M together: use sfem_assemble_ST");
+  DeviceGuard dg(pat->space->mesh->device);
+  const double* eps = form == SFEM_FORM_MASS ? d_coef : nullptr;
+  const double* mu = form == SFEM_FORM_STIFFNESS ? d_coef : nullptr;
+  return assemble_generic(pat, form, eps, mu, d_facet_mask, d_pec_row_flags, d_values, nullptr, (cudaStream_t)stream);
+}
+
+int sfem_assemble_ST(sfem_pattern_t pat, const double* d_eps_r, const double* d_mu_r,
+                     const uint8_t* d_pec_row_flags, double* d_S, double* d_T, int kernel, void* stream) {
+  SFEM_CHECK(pat && d_S && d_T, "NULL argument");
+  DeviceGuard dg(pat->space->mesh->device);
+  if (kernel == SFEM_KERNEL_AUTO) kernel = canonical_supported(pat) ? SFEM_KERNEL_CANONICAL : SFEM_KERNEL_GENERIC;
+  if (kernel == SFEM_KERNEL_CANONICAL) {
+    SFEM_CHECK(canonical_supported(pat), "canonical kernels support tetrahedra of order 1 and 2 only");
+    return assemble_canonical_ST(pat, d_eps_r, d_mu_r, d_pec_row_flags, d_S, d_T, (cudaStream_t)stream);
+  }
+  return assemble_generic(pat, 3, d_eps_r, d_mu_r, nullptr, d_pec_row_flags, d_S, d_T, (cudaStream_t)stream);
+}
+
+}  // extern "C"

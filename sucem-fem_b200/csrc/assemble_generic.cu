@@ -1,0 +1,321 @@
+// K3 (generic variant): row-owner gather of the S / M(=T) / S_0 values into the precomputed CSR slots.
+// Replaces the cell loop of dolfin.assemble (ufc tabulate_tensor + GenericMatrix::add) and
+// DirichletBC.apply -> ident called from /root/reference/sucemfem/SystemMatrices.py:54-55 for the forms of
+// /root/reference/sucemfem/Forms.py:76,84 and /root/reference/sucemfem/BoundaryConditions/ABC.py:57.
+//
+// One warp owns one row entity (an edge or a face / cell interior: its q rows share a pattern).  Lanes own
+// output columns; for each owned column the lane walks the entity's incident cells in ascending order
+// (DOLFIN's summation order), finds the cell-local column through the slot table and contracts the cell's
+// geometry factors with the full pre-integrated reference tensor.  Every CSR value is written exactly once,
+// coalesced, without atomics: results are bit-reproducible.  Works for any dim/order and any local position;
+// it is the cross-check for the canonical-frame kernels in assemble_canonical.cu.
+#include "sfem_internal.h"
+
+#define SFEM_TABLE static __device__ const
+#include "generated/n1curl_tables.inc"
+
+namespace sfem {
+namespace {
+
+template <int DIM, int ORDER>
+struct Elem;
+template <>
+struct Elem<3, 1> {
+  static constexpr int N = 6, NP = 6;
+  __device__ static const double* mass(int i, int j) { return kMassTet1[i][j]; }
+  __device__ static const double* curl(int i, int j) { return kCurlTet1[i][j]; }
+  __device__ static const double* facet(int f, int i, int j) { return kFacetTet1[f][i][j]; }
+};
+template <>
+struct Elem<3, 2> {
+  static constexpr int N = 20, NP = 6;
+  __device__ static const double* mass(int i, int j) { return kMassTet2[i][j]; }
+  __device__ static const double* curl(int i, int j) { return kCurlTet2[i][j]; }
+  __device__ static const double* facet(int f, int i, int j) { return kFacetTet2[f][i][j]; }
+};
+template <>
+struct Elem<2, 1> {
+  static constexpr int N = 3, NP = 3;
+  __device__ static const double* mass(int i, int j) { return kMassTri1[i][j]; }
+  __device__ static const double* curl(int i, int j) { return &kCurlTri1[i][j]; }
+  __device__ static const double* facet(int f, int i, int j) { return kFacetTri1[f][i][j]; }
+};
+template <>
+struct Elem<2, 2> {
+  static constexpr int N = 8, NP = 3;
+  __device__ static const double* mass(int i, int j) { return kMassTri2[i][j]; }
+  __device__ static const double* curl(int i, int j) { return &kCurlTri2[i][j]; }
+  __device__ static const double* facet(int f, int i, int j) { return kFacetTri2[f][i][j]; }
+};
+
+// Per-cell geometry factors, symmetric index order (00,11,22,01,02,12) / (00,11,01):
+//   gT = |detJ| eps_r (J^-1 J^-T)       gS = (J^T J) / (|detJ| mu_r)   (2-D: scalar 1/(|detJ| mu_r))
+// x = x_v0 + J X, columns of J = x_vi - x_v0, detJ may be negative.
+template <int DIM>
+__device__ __forceinline__ void cell_geometry(const double* __restrict__ coords, const int32_t* __restrict__ cell,
+                                              double eps, double mu, double* gT, double* gS, double* Jinv_out) {
+  double x[DIM + 1][DIM];
+#pragma unroll
+  for (int v = 0; v <= DIM; ++v)
+#pragma unroll
+    for (int d = 0; d < DIM; ++d) x[v][d] = coords[(int64_t)cell[v] * DIM + d];
+  double J[DIM][DIM];  // J[d][a] = x_{a+1}[d] - x_0[d]
+#pragma unroll
+  for (int d = 0; d < DIM; ++d)
+#pragma unroll
+    for (int a = 0; a < DIM; ++a) J[d][a] = x[a + 1][d] - x[0][d];
+  double Ji[DIM][DIM];  // inverse: Ji[a][d]
+  double det;
+  if (DIM == 3) {
+    double c00 = J[1][1] * J[2][2] - J[1][2] * J[2][1];
+    double c01 = J[1][2] * J[2][0] - J[1][0] * J[2][2];
+    double c02 = J[1][0] * J[2][1] - J[1][1] * J[2][0];
+    det = J[0][0] * c00 + J[0][1] * c01 + J[0][2] * c02;
+    double id = 1.0 / det;
+    Ji[0][0] = c00 * id;
+    Ji[1][0] = c01 * id;
+    Ji[2][0] = c02 * id;
+    Ji[0][1] = (J[0][2] * J[2][1] - J[0][1] * J[2][2]) * id;
+    Ji[1][1] = (J[0][0] * J[2][2] - J[0][2] * J[2][0]) * id;
+    Ji[2][1] = (J[0][1] * J[2][0] - J[0][0] * J[2][1]) * id;
+    Ji[0][2] = (J[0][1] * J[1][2] - J[0][2] * J[1][1]) * id;
+    Ji[1][2] = (J[0][2] * J[1][0] - J[0][0] * J[1][2]) * id;
+    Ji[2][2] = (J[0][0] * J[1][1] - J[0][1] * J[1][0]) * id;
+  } else {
+    det = J[0][0] * J[1][1] - J[0][1] * J[1][0];
+    double id = 1.0 / det;
+    Ji[0][0] = J[1][1] * id;
+    Ji[0][1] = -J[0][1] * id;
+    Ji[1][0] = -J[1][0] * id;
+    Ji[1][1] = J[0][0] * id;
+  }
+  const double ad = fabs(det);
+  const int pa[6] = {0, 1, 2, 0, 0, 1}, pb[6] = {0, 1, 2, 1, 2, 2};
+  const int qa[3] = {0, 1, 0}, qb[3] = {0, 1, 1};
+  constexpr int NP = DIM == 3 ? 6 : 3;
+#pragma unroll
+  for (int p = 0; p < NP; ++p) {
+    const int a = DIM == 3 ? pa[p] : qa[p], b = DIM == 3 ? pb[p] : qb[p];
+    double gi = 0, gg = 0;
+#pragma unroll
+    for (int d = 0; d < DIM; ++d) {
+      gi += Ji[a][d] * Ji[b][d];
+      gg += J[d][a] * J[d][b];
+    }
+    if (gT) gT[p] = gi * ad * eps;
+    if (gS && DIM == 3) gS[p] = gg / (ad * mu);
+  }
+  if (gS && DIM == 2) gS[0] = 1.0 / (ad * mu);
+  if (Jinv_out)
+#pragma unroll
+    for (int a = 0; a < DIM; ++a)
+#pragma unroll
+      for (int d = 0; d < DIM; ++d) Jinv_out[a * DIM + d] = Ji[a][d];
+}
+
+template <int DIM>
+__global__ void k_cell_geometry(const double* __restrict__ coords, const int32_t* __restrict__ cells,
+                                const double* __restrict__ eps, const double* __restrict__ mu, int64_t C,
+                                double* __restrict__ geo) {
+  int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double gT[6], gS[6];
+  cell_geometry<DIM>(coords, cells + c * (DIM + 1), eps ? eps[c] : 1.0, mu ? mu[c] : 1.0, gT, gS, nullptr);
+  constexpr int NP = DIM == 3 ? 6 : 3;
+#pragma unroll
+  for (int p = 0; p < NP; ++p) geo[c * 12 + p] = gT[p];
+#pragma unroll
+  for (int p = 0; p < (DIM == 3 ? 6 : 1); ++p) geo[c * 12 + 6 + p] = gS[p];
+}
+
+// ABC facet factors for local facet lf of a cell: K_ab = meas * (dim-1)! * ((J^-1 J^-T)_ab - nu_a nu_b),
+// nu = J^-1 n  (so that sum_ab K_ab Bhat^{ab}_ij = int_f (n x phi_i).(n x phi_j) ds).
+template <int DIM>
+__device__ void facet_geometry(const double* __restrict__ coords, const int32_t* __restrict__ cell, int lf,
+                               double* K) {
+  double gT[6], Ji[DIM * DIM];
+  cell_geometry<DIM>(coords, cell, 1.0, 1.0, gT, nullptr, Ji);
+  // undo the |detJ| factor folded into gT: recompute Ginv from Ji
+  double n[DIM], meas;
+  if (DIM == 3) {
+    const double* p0 = coords + (int64_t)cell[tet_face_vertex(lf, 0)] * 3;
+    const double* p1 = coords + (int64_t)cell[tet_face_vertex(lf, 1)] * 3;
+    const double* p2 = coords + (int64_t)cell[tet_face_vertex(lf, 2)] * 3;
+    double u[3] = {p1[0] - p0[0], p1[1] - p0[1], p1[2] - p0[2]};
+    double v[3] = {p2[0] - p0[0], p2[1] - p0[1], p2[2] - p0[2]};
+    n[0] = u[1] * v[2] - u[2] * v[1];
+    n[1] = u[2] * v[0] - u[0] * v[2];
+    n[2 % DIM] = u[0] * v[1] - u[1] * v[0];
+    meas = sqrt(n[0] * n[0] + n[1] * n[1] + n[2 % DIM] * n[2 % DIM]);
+  } else {
+    const double* p0 = coords + (int64_t)cell[tri_edge_vertex(lf, 0)] * 2;
+    const double* p1 = coords + (int64_t)cell[tri_edge_vertex(lf, 1)] * 2;
+    double t[2] = {p1[0] - p0[0], p1[1] - p0[1]};
+    n[0] = t[1];
+    n[1] = -t[0];
+    meas = sqrt(n[0] * n[0] + n[1] * n[1]);
+  }
+  double nu[DIM];
+#pragma unroll
+  for (int a = 0; a < DIM; ++a) {
+    double s = 0;
+#pragma unroll
+    for (int d = 0; d < DIM; ++d) s += Ji[a * DIM + d] * n[d];
+    nu[a] = s / meas;
+  }
+  const int pa[6] = {0, 1, 2, 0, 0, 1}, pb[6] = {0, 1, 2, 1, 2, 2};
+  const int qa[3] = {0, 1, 0}, qb[3] = {0, 1, 1};
+  constexpr int NP = DIM == 3 ? 6 : 3;
+#pragma unroll
+  for (int p = 0; p < NP; ++p) {
+    const int a = DIM == 3 ? pa[p] : qa[p], b = DIM == 3 ? pb[p] : qb[p];
+    double gi = 0;
+#pragma unroll
+    for (int d = 0; d < DIM; ++d) gi += Ji[a * DIM + d] * Ji[b * DIM + d];
+    K[p] = (gi - nu[a] * nu[b]) * meas;
+  }
+}
+
+struct PatView {
+  const int64_t* inc_ptr;
+  const int32_t* inc_cell;
+  const uint8_t* inc_loc;
+  const int64_t* ent_rowptr;
+  const int32_t* ent_cols;
+  const uint16_t* pos;
+  int64_t ent_lo, n_rows, inc_base;
+  int nec;
+};
+
+constexpr int kWarps = 8;
+
+// FORM: 0 = M only, 1 = S only, 3 = S and M fused, 2 = ABC
+template <int DIM, int ORDER, int FORM>
+__global__ void __launch_bounds__(kWarps * 32)
+k_values_generic(PatView pv, const double* __restrict__ geo, const double* __restrict__ coords,
+                 const int32_t* __restrict__ cells, const int32_t* __restrict__ cell_facets,
+                 const uint8_t* __restrict__ cell_extmask, const uint8_t* __restrict__ facet_mask,
+                 const uint8_t* __restrict__ pec, double* __restrict__ outA, double* __restrict__ outB) {
+  using El = Elem<DIM, ORDER>;
+  constexpr int Q = ORDER, NP = El::NP, NFAC = DIM + 1;
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t r = blockIdx.x * (int64_t)kWarps + w;
+  if (r >= pv.n_rows) return;
+  const int64_t g = pv.ent_lo + r;
+  const int64_t a = pv.ent_rowptr[r];
+  const int len = (int)(pv.ent_rowptr[r + 1] - a);
+  const int64_t i0 = pv.inc_ptr[g], i1 = pv.inc_ptr[g + 1];
+  for (int k = 0; k < Q; ++k) {
+    const int64_t rs = (int64_t)Q * Q * a + (int64_t)k * Q * len;
+    const bool pecrow = pec && pec[Q * g + k];
+    for (int idx = lane; idx < Q * len; idx += 32) {
+      const int s = idx / Q, kp = idx - s * Q;
+      double accA = 0.0, accB = 0.0;
+      if (pecrow) {
+        accA = accB = (pv.ent_cols[a + s] == g && kp == k) ? 1.0 : 0.0;
+      } else {
+        for (int64_t i = i0; i < i1; ++i) {
+          const uint16_t* ps = pv.pos + (i - pv.inc_base) * pv.nec;
+          int u = -1;
+          for (int uu = 0; uu < pv.nec; ++uu)
+            if (ps[uu] == s) u = uu;
+          if (u < 0) continue;
+          const int64_t c = pv.inc_cell[i];
+          const int li = pv.inc_loc[i] * Q + k, lj = u * Q + kp;
+          if (FORM == 2) {
+            unsigned m = cell_extmask[c];
+            if (!m) continue;
+            for (int lf = 0; lf < NFAC; ++lf) {
+              if (!((m >> lf) & 1)) continue;
+              if (facet_mask && !facet_mask[cell_facets[c * NFAC + lf]]) continue;
+              double K[6];
+              facet_geometry<DIM>(coords, cells + c * (DIM + 1), lf, K);
+              const double* B = El::facet(lf, li, lj);
+#pragma unroll
+              for (int p = 0; p < NP; ++p) accA += K[p] * B[p];
+            }
+          } else {
+            const double* gc = geo + c * 12;
+            if (FORM == 0 || FORM == 3) {
+              const double* Mh = El::mass(li, lj);
+              double t = 0;
+#pragma unroll
+              for (int p = 0; p < NP; ++p) t += gc[p] * Mh[p];
+              if (FORM == 3) accB += t; else accA += t;
+            }
+            if (FORM == 1 || FORM == 3) {
+              const double* Ch = El::curl(li, lj);
+              double t = 0;
+              if (DIM == 3) {
+#pragma unroll
+                for (int p = 0; p < 6; ++p) t += gc[6 + p] * Ch[p];
+              } else {
+                t = gc[6] * Ch[0];
+              }
+              accA += t;
+            }
+          }
+        }
+      }
+      outA[rs + idx] = accA;
+      if (FORM == 3) outB[rs + idx] = accB;
+    }
+  }
+}
+
+template <int DIM, int ORDER>
+int launch_generic(const sfem_pattern_s* pat, int form, const double* coef_a, const double* coef_b,
+                   const uint8_t* facet_mask, const uint8_t* pec, double* out_a, double* out_b,
+                   cudaStream_t st) {
+  const sfem_space_s* sp = pat->space;
+  const sfem_mesh_s* m = sp->mesh;
+  PatView pv{sp->inc_ptr, sp->inc_cell, sp->inc_loc, pat->ent_rowptr, pat->ent_cols, pat->pos,
+             pat->ent_lo, pat->n_rows_ent, pat->inc_base, sp->n_ent_cell};
+  if (pat->n_rows_ent == 0) return 0;
+  const unsigned grid = (unsigned)((pat->n_rows_ent + kWarps - 1) / kWarps);
+  const int32_t* cell_facets = DIM == 3 ? sp->cell_faces : sp->cell_edges;
+  double* geo = nullptr;
+  if (form != SFEM_FORM_ABC) {
+    SFEM_CUDA(cudaMallocAsync((void**)&geo, m->C * 12 * sizeof(double), st));
+    // coef_a = eps_r (mass), coef_b = mu_r (stiffness)
+    k_cell_geometry<DIM><<<(unsigned)((m->C + 255) / 256), 256, 0, st>>>(m->coords, m->cells, coef_a, coef_b, m->C, geo);
+  }
+  switch (form) {
+    case SFEM_FORM_MASS:
+      k_values_generic<DIM, ORDER, 0><<<grid, kWarps * 32, 0, st>>>(pv, geo, m->coords, m->cells, cell_facets,
+                                                                   sp->cell_extmask, facet_mask, pec, out_a, nullptr);
+      break;
+    case SFEM_FORM_STIFFNESS:
+      k_values_generic<DIM, ORDER, 1><<<grid, kWarps * 32, 0, st>>>(pv, geo, m->coords, m->cells, cell_facets,
+                                                                   sp->cell_extmask, facet_mask, pec, out_a, nullptr);
+      break;
+    case SFEM_FORM_ABC:
+      k_values_generic<DIM, ORDER, 2><<<grid, kWarps * 32, 0, st>>>(pv, geo, m->coords, m->cells, cell_facets,
+                                                                   sp->cell_extmask, facet_mask, pec, out_a, nullptr);
+      break;
+    default:  // 3: fused S (out_a) and M (out_b)
+      k_values_generic<DIM, ORDER, 3><<<grid, kWarps * 32, 0, st>>>(pv, geo, m->coords, m->cells, cell_facets,
+                                                                   sp->cell_extmask, facet_mask, pec, out_a, out_b);
+  }
+  SFEM_CUDA(cudaGetLastError());
+  if (geo) SFEM_CUDA(cudaFreeAsync(geo, st));
+  return 0;
+}
+
+}  // namespace
+
+// form: SFEM_FORM_MASS (coef_a = eps_r), SFEM_FORM_STIFFNESS (coef_b = mu_r), SFEM_FORM_ABC, or 3 = fused
+// S -> out_a, M -> out_b with coef_a = eps_r, coef_b = mu_r.
+int assemble_generic(const sfem_pattern_s* pat, int form, const double* coef_a, const double* coef_b,
+                     const uint8_t* facet_mask, const uint8_t* pec, double* out_a, double* out_b,
+                     cudaStream_t st) {
+  const int dim = pat->space->mesh->gdim, order = pat->space->order;
+  if (dim == 3 && order == 1) return launch_generic<3, 1>(pat, form, coef_a, coef_b, facet_mask, pec, out_a, out_b, st);
+  if (dim == 3 && order == 2) return launch_generic<3, 2>(pat, form, coef_a, coef_b, facet_mask, pec, out_a, out_b, st);
+  if (dim == 2 && order == 1) return launch_generic<2, 1>(pat, form, coef_a, coef_b, facet_mask, pec, out_a, out_b, st);
+  if (dim == 2 && order == 2) return launch_generic<2, 2>(pat, form, coef_a, coef_b, facet_mask, pec, out_a, out_b, st);
+  set_error("unsupported (dim, order)");
+  return 2;
+}
+
+}  // namespace sfem

@@ -1,0 +1,186 @@
+// K2: CSR sparsity pattern on the device.  Replaces DOLFIN's SparsityPatternBuilder + tensor init that run
+// inside dolfin.assemble (/root/reference/sucemfem/SystemMatrices.py:54).  Contract: row i
+// holds the sorted-ascending union of the cell-dof sets of all cells containing dof i, zeros included.
+//
+// Because dof = q*entity + k, the dof-level pattern is the q x q block expansion of an
+// ENTITY-level pattern; only that one is built and stored (nnz/q^2 column ids):
+//   one warp per row entity: gather the entities of its incident cells, rank-sort + unique in shared
+//   memory, count -> scan (int64) -> fill; the same pass records pos[incidence][u] = slot of the cell's
+//   u-th entity in the row (the "precomputed CSR value slots" the value kernels scatter into).
+#include <cub/cub.cuh>
+
+#include "sfem_internal.h"
+
+namespace sfem {
+namespace {
+
+constexpr int kWarpsPerBlock = 4;
+constexpr int kCap = 1024;  // candidates per row entity (valence * entities per cell)
+
+template <bool FILL>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+k_pattern(SpaceView sv, const int64_t* __restrict__ inc_ptr, const int32_t* __restrict__ inc_cell,
+          int64_t ent_lo, int64_t n_rows, int64_t inc_base, int32_t* __restrict__ row_len,
+          const int64_t* __restrict__ ent_rowptr, int32_t* __restrict__ ent_cols, uint16_t* __restrict__ pos,
+          int* __restrict__ overflow) {
+  __shared__ int32_t s_cand[kWarpsPerBlock][kCap];
+  __shared__ int32_t s_sorted[kWarpsPerBlock][kCap];
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t r = blockIdx.x * (int64_t)kWarpsPerBlock + w;
+  if (r >= n_rows) return;
+  const int64_t g = ent_lo + r;
+  const int64_t i0 = inc_ptr[g], i1 = inc_ptr[g + 1];
+  const int nec = sv.n_ent_cell;
+  const int L = (int)(i1 - i0) * nec;
+  if (L > kCap) {
+    if (lane == 0) *overflow = 1;
+    return;
+  }
+  int32_t* cand = s_cand[w];
+  int32_t* sorted = s_sorted[w];
+  for (int idx = lane; idx < L; idx += 32) {
+    int i = idx / nec, u = idx - i * nec;
+    cand[idx] = sv.ent(inc_cell[i0 + i], u);
+  }
+  __syncwarp();
+  // rank sort (stable): sorted[rank] = x
+  for (int idx = lane; idx < L; idx += 32) {
+    int32_t x = cand[idx];
+    int rk = 0;
+    for (int j = 0; j < L; ++j) {
+      int32_t y = cand[j];
+      rk += (y < x) || (y == x && j < idx);
+    }
+    sorted[rk] = x;
+  }
+  __syncwarp();
+  // unique-compact in place into cand[0..nu)
+  int nu = 0;
+  for (int base = 0; base < L; base += 32) {
+    int idx = base + lane;
+    bool keep = idx < L && (idx == 0 || sorted[idx] != sorted[idx - 1]);
+    unsigned m = __ballot_sync(0xffffffffu, keep);
+    if (keep) cand[nu + __popc(m & ((1u << lane) - 1))] = sorted[idx];
+    nu += __popc(m);
+  }
+  __syncwarp();
+  if (!FILL) {
+    if (lane == 0) row_len[r] = nu;
+    return;
+  }
+  const int64_t rp = ent_rowptr[r];
+  for (int k = lane; k < nu; k += 32) ent_cols[rp + k] = cand[k];
+  // slot of every (incidence, local entity) in the unique list
+  for (int idx = lane; idx < L; idx += 32) {
+    int i = idx / nec, u = idx - i * nec;
+    int32_t x = sv.ent(inc_cell[i0 + i], u);
+    int lo = 0, hi = nu - 1;
+    while (lo < hi) {
+      int mid = (lo + hi) >> 1;
+      if (cand[mid] < x) lo = mid + 1; else hi = mid;
+    }
+    pos[(i0 - inc_base + i) * nec + u] = (uint16_t)lo;
+  }
+}
+
+__global__ void k_len_to_i64(const int32_t* __restrict__ len, int64_t* __restrict__ out, int64_t n) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i <= n) out[i] = i < n ? len[i] : 0;
+}
+
+// dof-level CSR from the entity-level one: dof row q*g+k; columns q*h+k'
+__global__ void k_export(const int64_t* __restrict__ ent_rowptr, const int32_t* __restrict__ ent_cols, int q,
+                         int64_t n_rows_ent, int64_t* __restrict__ rowptr, int32_t* __restrict__ cols) {
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t r = blockIdx.x * (int64_t)(blockDim.x >> 5) + w;
+  if (r > n_rows_ent) return;
+  if (r == n_rows_ent) {
+    if (lane == 0) rowptr[q * r] = (int64_t)q * q * ent_rowptr[r];
+    return;
+  }
+  const int64_t a = ent_rowptr[r];
+  const int len = (int)(ent_rowptr[r + 1] - a);
+  for (int k = 0; k < q; ++k) {
+    const int64_t rs = (int64_t)q * q * a + (int64_t)k * q * len;
+    if (lane == 0) rowptr[q * r + k] = rs;
+    if (cols)
+      for (int idx = lane; idx < q * len; idx += 32) {
+        int s = idx / q, kp = idx - s * q;
+        cols[rs + idx] = q * ent_cols[a + s] + kp;
+      }
+  }
+}
+
+inline unsigned grid_for(int64_t n, int bs = 256) { return (unsigned)((n + bs - 1) / bs); }
+
+}  // namespace
+
+int build_pattern(sfem_pattern_s* pat, cudaStream_t st) {
+  const sfem_space_s* sp = pat->space;
+  const int64_t n = pat->n_rows_ent;
+  SpaceView sv = make_view(sp);
+  int64_t bounds[2];
+  SFEM_CUDA(cudaMemcpyAsync(&bounds[0], sp->inc_ptr + pat->ent_lo, 8, cudaMemcpyDeviceToHost, st));
+  SFEM_CUDA(cudaMemcpyAsync(&bounds[1], sp->inc_ptr + pat->ent_hi, 8, cudaMemcpyDeviceToHost, st));
+  SFEM_CUDA(cudaStreamSynchronize(st));
+  pat->inc_base = bounds[0];
+  pat->n_inc_block = bounds[1] - bounds[0];
+
+  int32_t* row_len = nullptr;
+  int64_t* len64 = nullptr;
+  int* overflow = nullptr;
+  SFEM_CUDA(cudaMalloc(&row_len, std::max<int64_t>(n, 1) * 4));
+  SFEM_CUDA(cudaMalloc(&len64, (n + 1) * 8));
+  SFEM_CUDA(cudaMalloc(&overflow, 4));
+  SFEM_CUDA(cudaMemsetAsync(overflow, 0, 4, st));
+  SFEM_CUDA(cudaMalloc(&pat->ent_rowptr, (n + 1) * 8));
+  const unsigned grid = (unsigned)((n + kWarpsPerBlock - 1) / kWarpsPerBlock);
+  if (n > 0)
+    k_pattern<false><<<grid, kWarpsPerBlock * 32, 0, st>>>(sv, sp->inc_ptr, sp->inc_cell, pat->ent_lo, n,
+                                                           pat->inc_base, row_len, nullptr, nullptr, nullptr,
+                                                           overflow);
+  k_len_to_i64<<<grid_for(n + 1), 256, 0, st>>>(row_len, len64, n);
+  size_t tb = 0;
+  SFEM_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tb, len64, pat->ent_rowptr, (int)(n + 1), st));
+  size_t tb2 = 0;
+  SFEM_CUDA(cub::DeviceReduce::Max(nullptr, tb2, row_len, (int32_t*)nullptr, (int)std::max<int64_t>(n, 1), st));
+  void* tmp = nullptr;
+  SFEM_CUDA(cudaMalloc(&tmp, std::max(tb, tb2) + 16));
+  SFEM_CUDA(cub::DeviceScan::ExclusiveSum(tmp, tb, len64, pat->ent_rowptr, (int)(n + 1), st));
+  int32_t* d_max = (int32_t*)len64;  // len64 is dead after the scan
+  if (n > 0) SFEM_CUDA(cub::DeviceReduce::Max(tmp, tb2, row_len, d_max, (int)n, st));
+  int h_over = 0, h_max = 0;
+  SFEM_CUDA(cudaMemcpyAsync(&pat->nnz_ent, pat->ent_rowptr + n, 8, cudaMemcpyDeviceToHost, st));
+  SFEM_CUDA(cudaMemcpyAsync(&h_over, overflow, 4, cudaMemcpyDeviceToHost, st));
+  if (n > 0) SFEM_CUDA(cudaMemcpyAsync(&h_max, d_max, 4, cudaMemcpyDeviceToHost, st));
+  SFEM_CUDA(cudaStreamSynchronize(st));
+  cudaFree(tmp);
+  cudaFree(len64);
+  cudaFree(row_len);
+  if (h_over) {
+    cudaFree(overflow);
+    set_error("an entity has more incident cells than the pattern builder supports (valence*entities > 1024)");
+    return 3;
+  }
+  pat->max_row_len = h_max;
+  SFEM_CUDA(cudaMalloc(&pat->ent_cols, std::max<int64_t>(pat->nnz_ent, 1) * 4));
+  SFEM_CUDA(cudaMalloc(&pat->pos, std::max<int64_t>(pat->n_inc_block * sp->n_ent_cell, 1) * 2));
+  if (n > 0)
+    k_pattern<true><<<grid, kWarpsPerBlock * 32, 0, st>>>(sv, sp->inc_ptr, sp->inc_cell, pat->ent_lo, n,
+                                                          pat->inc_base, nullptr, pat->ent_rowptr, pat->ent_cols,
+                                                          pat->pos, overflow);
+  SFEM_CUDA(cudaGetLastError());
+  SFEM_CUDA(cudaStreamSynchronize(st));
+  cudaFree(overflow);
+  return 0;
+}
+
+int export_pattern(const sfem_pattern_s* pat, int64_t* d_rowptr, int32_t* d_cols, cudaStream_t st) {
+  const int64_t n = pat->n_rows_ent;
+  const unsigned grid = (unsigned)((n + 1 + 7) / 8);
+  k_export<<<grid, 256, 0, st>>>(pat->ent_rowptr, pat->ent_cols, pat->space->order, n, d_rowptr, d_cols);
+  SFEM_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace sfem

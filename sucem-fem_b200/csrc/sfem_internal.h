@@ -1,0 +1,142 @@
+// Internal declarations shared by the translation units of libsucem_b200.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+
+#include "../../include/sucem_b200.h"
+
+namespace sfem {
+
+void set_error(const std::string& msg);
+
+#define SFEM_CUDA(call)                                                                          \
+  do {                                                                                           \
+    cudaError_t _e = (call);                                                                     \
+    if (_e != cudaSuccess) {                                                                     \
+      sfem::set_error(std::string(#call) + ": " + cudaGetErrorString(_e) + " (" + __FILE__ +     \
+                      ":" + std::to_string(__LINE__) + ")");                                     \
+      return 1;                                                                                  \
+    }                                                                                            \
+  } while (0)
+
+#define SFEM_CHECK(cond, msg)        \
+  do {                               \
+    if (!(cond)) {                   \
+      sfem::set_error(msg);          \
+      return 2;                      \
+    }                                \
+  } while (0)
+
+#define SFEM_TRY(expr)           \
+  do {                           \
+    int _rc = (expr);            \
+    if (_rc != 0) return _rc;    \
+  } while (0)
+
+// Local topology of the UFC reference cells.
+// tet edges e0=(2,3) e1=(1,3) e2=(1,2) e3=(0,3) e4=(0,2) e5=(0,1); faces f_i opposite v_i
+// triangle edges e_i opposite v_i
+__host__ __device__ inline int tet_edge_vertex(int e, int k) {
+  const int t[6][2] = {{2, 3}, {1, 3}, {1, 2}, {0, 3}, {0, 2}, {0, 1}};
+  return t[e][k];
+}
+__host__ __device__ inline int tet_face_vertex(int f, int k) {
+  const int t[4][3] = {{1, 2, 3}, {0, 2, 3}, {0, 1, 3}, {0, 1, 2}};
+  return t[f][k];
+}
+__host__ __device__ inline int tri_edge_vertex(int e, int k) {
+  const int t[3][2] = {{1, 2}, {0, 2}, {0, 1}};
+  return t[e][k];
+}
+// the three local edges of local tet face f (edges whose vertices both lie in the face)
+__host__ __device__ inline int tet_face_edge(int f, int k) {
+  const int t[4][3] = {{0, 1, 2}, {0, 3, 4}, {1, 3, 5}, {2, 4, 5}};
+  return t[f][k];
+}
+
+}  // namespace sfem
+
+struct sfem_mesh_s {
+  int device = 0;
+  int gdim = 0;   // 2 or 3
+  int nv = 0;     // vertices per cell
+  int64_t V = 0, C = 0;
+  const double* coords = nullptr;  // [V][gdim]   caller-owned
+  const int32_t* cells = nullptr;  // [C][nv]     caller-owned
+};
+
+struct sfem_space_s {
+  sfem_mesh_s* mesh = nullptr;
+  int device = 0;
+  int order = 0;         // = dofs per entity q
+  int ne_loc = 0;        // local edges per cell (6 | 3)
+  int nf_loc = 0;        // local faces per cell (4 | 0)
+  int n_ent_cell = 0;    // dof entities per cell: order 1: ne_loc; order 2: ne_loc + (4 faces | 1 interior)
+  int ndof_cell = 0;     // order * n_ent_cell
+  int64_t E = 0, F = 0;  // #edges, #faces (3-D)
+  int64_t n_ent = 0;     // dof entities: E (+ F in 3-D order 2, + C in 2-D order 2)
+  int64_t ndof = 0;
+  int32_t* cell_edges = nullptr;  // [C][ne_loc]
+  int32_t* cell_faces = nullptr;  // [C][4] (3-D only)
+  // entity -> cell incidences of the dof entities, ascending cell index within an entity
+  int64_t* inc_ptr = nullptr;     // [n_ent+1]
+  int32_t* inc_cell = nullptr;    // [n_inc]
+  uint8_t* inc_loc = nullptr;     // [n_inc] local dof-entity index t of the entity in that cell
+  int64_t n_inc = 0;
+  // facets (3-D faces / 2-D edges): number of incident cells and the first (cell, local facet)
+  int64_t n_facets = 0;
+  uint8_t* facet_ncells = nullptr;    // [n_facets]
+  int32_t* facet_first_cell = nullptr;// [n_facets]
+  uint8_t* facet_first_loc = nullptr; // [n_facets]
+  uint8_t* cell_extmask = nullptr;    // [C] bit lf set <=> local facet lf is exterior
+};
+
+struct sfem_pattern_s {
+  sfem_space_s* space = nullptr;
+  int device = 0;
+  int64_t ent_lo = 0, ent_hi = 0;
+  int64_t n_rows_ent = 0;
+  int64_t nnz_ent = 0;            // entity-level non-zeros of the block
+  int64_t* ent_rowptr = nullptr;  // [n_rows_ent+1], offsets into this block
+  int32_t* ent_cols = nullptr;    // [nnz_ent] global entity ids, ascending within a row
+  uint16_t* pos = nullptr;        // [n_inc_block][n_ent_cell]: slot of the cell's u-th entity in the row
+  int64_t inc_base = 0;           // = space->inc_ptr[ent_lo]
+  int64_t n_inc_block = 0;
+  int max_row_len = 0;            // longest entity row of the block
+};
+
+namespace sfem {
+// dof-entity u of cell c: edges first, then faces (3-D) / the cell interior (2-D)
+struct SpaceView {
+  const int32_t* cell_edges;
+  const int32_t* cell_faces;
+  int ne_loc, n_ent_cell;
+  int64_t E;
+  __device__ __forceinline__ int32_t ent(int64_t c, int u) const {
+    if (u < ne_loc) return cell_edges[c * ne_loc + u];
+    if (cell_faces) return (int32_t)(E + cell_faces[c * 4 + (u - ne_loc)]);
+    return (int32_t)(E + c);
+  }
+};
+inline SpaceView make_view(const sfem_space_s* s) {
+  SpaceView v;
+  v.cell_edges = s->cell_edges;
+  v.cell_faces = (s->mesh->gdim == 3 && s->order == 2) ? s->cell_faces : nullptr;
+  v.ne_loc = s->ne_loc;
+  v.n_ent_cell = s->n_ent_cell;
+  v.E = s->E;
+  return v;
+}
+
+int build_numbering(sfem_space_s* sp, cudaStream_t st);
+int build_pattern(sfem_pattern_s* pat, cudaStream_t st);
+int export_pattern(const sfem_pattern_s* pat, int64_t* d_rowptr, int32_t* d_cols, cudaStream_t st);
+int assemble_generic(const sfem_pattern_s* pat, int form, const double* coef_a, const double* coef_b,
+                     const uint8_t* facet_mask, const uint8_t* pec, double* out_a, double* out_b,
+                     cudaStream_t st);
+int assemble_canonical_ST(const sfem_pattern_s* pat, const double* eps, const double* mu, const uint8_t* pec,
+                          double* S, double* T, cudaStream_t st);
+bool canonical_supported(const sfem_pattern_s* pat);
+}  // namespace sfem

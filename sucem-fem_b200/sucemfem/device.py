@@ -1,0 +1,211 @@
+"""Device-side objects behind the sucemfem API: thin owners of C-ABI handles plus the torch tensors
+(device buffers only) the handles point into.  All arithmetic happens in libsucem_b200.so.
+
+  DeviceMesh      <- dolfin.Mesh            (coordinates / cells resident in HBM)
+  DeviceSpace     <- dolfin.FunctionSpace   (/root/reference/sucemfem/ProblemConfigurations/EMProblem.py:100-105)
+  DevicePattern   <- the tensor layout DOLFIN builds inside dolfin.assemble
+                     (/root/reference/sucemfem/SystemMatrices.py:54)
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _native as N
+
+
+def _stream_ptr():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+def require_cuda():
+    if not torch.cuda.is_available():
+        raise RuntimeError("sucemfem (B200 build) needs a CUDA device: there is no CPU fallback")
+
+
+class DeviceMesh(object):
+    def __init__(self, coords, cells, device=None):
+        """coords [V, gdim] float64, cells [C, gdim+1] integer (host numpy arrays or device tensors)."""
+        require_cuda()
+        dev = torch.device('cuda', torch.cuda.current_device()) if device is None else torch.device(device)
+        self.device = dev
+        with torch.cuda.device(dev):
+            if isinstance(coords, torch.Tensor):
+                self.coords = coords.to(dev, torch.float64).contiguous()
+                self.cells = cells.to(dev, torch.int32).contiguous()
+            else:
+                self.coords = torch.from_numpy(np.ascontiguousarray(coords, dtype=np.float64)).to(dev)
+                cells = np.sort(np.asarray(cells), axis=1)      # UFC ordering of the cell's vertices
+                self.cells = torch.from_numpy(np.ascontiguousarray(cells, dtype=np.int32)).to(dev)
+            self.gdim = int(self.coords.shape[1])
+            assert self.cells.shape[1] == self.gdim + 1
+            h = C.c_void_p()
+            N.check(N.lib.sfem_mesh_create(self.gdim, self.coords.shape[0], _ptr(self.coords), self.cells.shape[0],
+                                           _ptr(self.cells), _stream_ptr(), C.byref(h)))
+            self.handle = h
+
+    @classmethod
+    def unit(cls, nx, ny, nz=0, scale=None, shift=None, device=None):
+        """UnitCube(nx,ny,nz) / UnitSquare(nx,ny) generated directly in HBM (nz=0: 2-D)."""
+        require_cuda()
+        dev = torch.device('cuda', torch.cuda.current_device()) if device is None else torch.device(device)
+        gdim = 3 if nz > 0 else 2
+        V = (nx + 1) * (ny + 1) * (nz + 1)
+        ncell = 6 * nx * ny * nz if nz > 0 else 2 * nx * ny
+        with torch.cuda.device(dev):
+            coords = torch.empty((V, gdim), dtype=torch.float64, device=dev)
+            cells = torch.empty((ncell, gdim + 1), dtype=torch.int32, device=dev)
+            sc = (C.c_double * 3)(*(list(scale) + [1.0] * 3)[:3]) if scale is not None else None
+            sh = (C.c_double * 3)(*(list(shift) + [0.0] * 3)[:3]) if shift is not None else None
+            N.check(N.lib.sfem_fill_unit_mesh(nx, ny, nz, sc, sh, _ptr(coords), _ptr(cells), _stream_ptr()))
+        return cls(coords, cells, device=dev)
+
+    @property
+    def num_cells(self):
+        return int(self.cells.shape[0])
+
+    @property
+    def num_vertices(self):
+        return int(self.coords.shape[0])
+
+    def __del__(self):
+        h = getattr(self, 'handle', None)
+        if h:
+            N.lib.sfem_mesh_destroy(h)
+            self.handle = None
+
+
+class DeviceSpace(object):
+    def __init__(self, mesh, order):
+        self.mesh = mesh
+        self.order = int(order)
+        h = C.c_void_p()
+        with torch.cuda.device(mesh.device):
+            N.check(N.lib.sfem_space_create(mesh.handle, self.order, _stream_ptr(), C.byref(h)))
+        self.handle = h
+        nd, ne, nf, ndc, nfa = C.c_int64(), C.c_int64(), C.c_int64(), C.c_int(), C.c_int64()
+        N.check(N.lib.sfem_space_info(h, C.byref(nd), C.byref(ne), C.byref(nf), C.byref(ndc)))
+        N.check(N.lib.sfem_space_num_facets(h, C.byref(nfa)))
+        self.ndof, self.n_edges, self.n_faces, self.ndof_cell = nd.value, ne.value, nf.value, ndc.value
+        self.n_facets = nfa.value
+        self.n_entities = self.ndof // self.order
+        self._patterns = {}
+
+    def cell_dofs(self):
+        out = torch.empty((self.mesh.num_cells, self.ndof_cell), dtype=torch.int32, device=self.mesh.device)
+        with torch.cuda.device(self.mesh.device):
+            N.check(N.lib.sfem_space_cell_dofs(self.handle, _ptr(out), _stream_ptr()))
+        return out
+
+    def cell_entities(self):
+        dev = self.mesh.device
+        ce = torch.empty((self.mesh.num_cells, 6 if self.mesh.gdim == 3 else 3), dtype=torch.int32, device=dev)
+        cf = torch.empty((self.mesh.num_cells, 4), dtype=torch.int32, device=dev) if self.mesh.gdim == 3 else None
+        with torch.cuda.device(dev):
+            N.check(N.lib.sfem_space_cell_entities(self.handle, _ptr(ce), _ptr(cf), _stream_ptr()))
+        return ce, cf
+
+    def mark_exterior_facets(self, markers, value):
+        with torch.cuda.device(self.mesh.device):
+            N.check(N.lib.sfem_mark_exterior_facets(self.handle, _ptr(markers), int(value), _stream_ptr()))
+        return markers
+
+    def pec_row_flags(self, markers, region, flags=None):
+        if flags is None:
+            flags = torch.zeros(self.ndof, dtype=torch.uint8, device=self.mesh.device)
+        with torch.cuda.device(self.mesh.device):
+            N.check(N.lib.sfem_pec_row_flags(self.handle, _ptr(markers), int(region), _ptr(flags), _stream_ptr()))
+        return flags
+
+    def partition(self, nparts):
+        b = (C.c_int64 * (nparts + 1))()
+        with torch.cuda.device(self.mesh.device):
+            N.check(N.lib.sfem_partition_rows(self.handle, nparts, b, _stream_ptr()))
+        return [int(x) for x in b]
+
+    def pattern(self, ent_lo=0, ent_hi=-1):
+        key = (ent_lo, ent_hi)
+        if key not in self._patterns:
+            self._patterns[key] = DevicePattern(self, ent_lo, ent_hi)
+        return self._patterns[key]
+
+    def __del__(self):
+        self._patterns = {}
+        h = getattr(self, 'handle', None)
+        if h:
+            N.lib.sfem_space_destroy(h)
+            self.handle = None
+
+
+class DevicePattern(object):
+    def __init__(self, space, ent_lo=0, ent_hi=-1):
+        self.space = space
+        h = C.c_void_p()
+        with torch.cuda.device(space.mesh.device):
+            N.check(N.lib.sfem_pattern_create(space.handle, ent_lo, ent_hi, _stream_ptr(), C.byref(h)))
+        self.handle = h
+        rb, nr, nnz = C.c_int64(), C.c_int64(), C.c_int64()
+        N.check(N.lib.sfem_pattern_info(h, C.byref(rb), C.byref(nr), C.byref(nnz)))
+        self.row_begin, self.n_rows, self.nnz = rb.value, nr.value, nnz.value
+        self._csr = None
+
+    def csr(self):
+        """(rowptr int64 [n_rows+1], cols int32 [nnz]) device tensors, built once."""
+        if self._csr is None:
+            dev = self.space.mesh.device
+            rowptr = torch.empty(self.n_rows + 1, dtype=torch.int64, device=dev)
+            cols = torch.empty(self.nnz, dtype=torch.int32, device=dev)
+            with torch.cuda.device(dev):
+                N.check(N.lib.sfem_pattern_export(self.handle, _ptr(rowptr), _ptr(cols), _stream_ptr()))
+            self._csr = (rowptr, cols)
+        return self._csr
+
+    def new_values(self):
+        return torch.empty(self.nnz, dtype=torch.float64, device=self.space.mesh.device)
+
+    def assemble(self, form, coef=None, facet_mask=None, pec_flags=None, out=None, kernel=N.KERNEL_AUTO):
+        out = self.new_values() if out is None else out
+        with torch.cuda.device(self.space.mesh.device):
+            N.check(N.lib.sfem_assemble(self.handle, form, _ptr(coef), _ptr(facet_mask), _ptr(pec_flags), _ptr(out),
+                                        kernel, _stream_ptr()))
+        return out
+
+    def assemble_ST(self, eps_r=None, mu_r=None, pec_flags=None, S=None, T=None, kernel=N.KERNEL_AUTO):
+        S = self.new_values() if S is None else S
+        T = self.new_values() if T is None else T
+        with torch.cuda.device(self.space.mesh.device):
+            N.check(N.lib.sfem_assemble_ST(self.handle, _ptr(eps_r), _ptr(mu_r), _ptr(pec_flags), _ptr(S), _ptr(T),
+                                           kernel, _stream_ptr()))
+        return S, T
+
+    def apply_ident(self, flags, values):
+        with torch.cuda.device(self.space.mesh.device):
+            N.check(N.lib.sfem_apply_ident(self.handle, _ptr(flags), _ptr(values), _stream_ptr()))
+        return values
+
+    def __del__(self):
+        h = getattr(self, 'handle', None)
+        if h:
+            N.lib.sfem_pattern_destroy(h)
+            self.handle = None
+
+
+def expand_material(regions, region_values, n_cells=None):
+    """coef[c] = region_values[regions[c]] on the device; unknown region -> ValueError as Materials.py:147-148."""
+    ids = np.array(sorted(region_values), dtype=np.uint32)
+    vals = np.array([region_values[int(i)] for i in ids], dtype=np.float64)
+    out = torch.empty(regions.shape[0], dtype=torch.float64, device=regions.device)
+    bad = C.c_uint32(0)
+    with torch.cuda.device(regions.device):
+        rc = N.lib.sfem_expand_material(regions.shape[0], _ptr(regions), len(ids),
+                                        ids.ctypes.data_as(C.POINTER(C.c_uint32)),
+                                        vals.ctypes.data_as(C.POINTER(C.c_double)), _ptr(out), C.byref(bad),
+                                        _stream_ptr())
+    if rc == 4:
+        raise ValueError('Material number %d not found' % bad.value)
+    N.check(rc)
+    return out
