@@ -16,9 +16,12 @@ pytestmark = pytest.mark.gpu
 RTOL, FLOOR = 1e-12, 1e-15
 
 
-def close(a, b):
+def close(a, b, scale=None, floor=FLOOR):
+    """scale: magnitude the absolute floor refers to (default max|b|); for PEC-applied matrices pass the
+    un-constrained matrix so that round-off entries are judged against the entries they came from."""
     a, b = np.asarray(a), np.asarray(b)
-    return np.all(np.abs(a - b) <= RTOL * np.abs(b) + FLOOR * np.abs(b).max())
+    scale = np.abs(b).max() if scale is None else max(np.abs(scale).max(), np.abs(b).max())
+    return np.all(np.abs(a - b) <= RTOL * np.abs(b) + floor * scale)
 
 
 def _meshes():
@@ -85,7 +88,10 @@ def test_values_generic_vs_oracle(dev, name, order):
     M = pat.assemble(N.FORM_MASS, coef=d_eps, kernel=N.KERNEL_GENERIC).cpu().numpy()
     S = pat.assemble(N.FORM_STIFFNESS, coef=d_mu, kernel=N.KERNEL_GENERIC).cpu().numpy()
     S0 = pat.assemble(N.FORM_ABC, kernel=N.KERNEL_GENERIC).cpu().numpy()
-    assert close(M, ref['M']) and close(S, ref['S']) and close(S0, ref['S_0'])
+    assert close(M, ref['M']) and close(S, ref['S'])
+    # S_0 contracts the tangential projector (J^-1 J^-T - nu nu^T), whose entries cancel to zero for basis
+    # functions without tangential trace: round-off there is eps*|J^-1|^2*meas, not eps*max|S_0|
+    assert close(S0, ref['S_0'], floor=2e-14)
     S2, T2 = pat.assemble_ST(d_eps, d_mu, kernel=N.KERNEL_GENERIC)
     assert np.array_equal(S2.cpu().numpy(), S) and np.array_equal(T2.cpu().numpy(), M)
     # PEC: exterior facets marked on the device, closure dofs, row-only ident (fused and as a separate step)
@@ -95,9 +101,9 @@ def test_values_generic_vs_oracle(dev, name, order):
     flags = sp.pec_row_flags(markers, 999)
     assert np.array_equal(np.nonzero(flags.cpu().numpy())[0], refp['pec_dofs'])
     Sp, Tp = pat.assemble_ST(d_eps, d_mu, pec_flags=flags, kernel=N.KERNEL_GENERIC)
-    assert close(Sp.cpu().numpy(), refp['S']) and close(Tp.cpu().numpy(), refp['M'])
+    assert close(Sp.cpu().numpy(), refp['S'], ref['S']) and close(Tp.cpu().numpy(), refp['M'], ref['M'])
     S0p = pat.apply_ident(flags, pat.assemble(N.FORM_ABC, kernel=N.KERNEL_GENERIC)).cpu().numpy()
-    assert close(S0p, refp['S_0'])
+    assert close(S0p, refp['S_0'], ref['S_0'], floor=2e-14)
     Sp2 = pat.apply_ident(flags, torch.from_numpy(S).cuda()).cpu().numpy()
     assert np.array_equal(Sp2, Sp.cpu().numpy())
 
