@@ -128,6 +128,9 @@ SFEM_API int sfem_assemble(sfem_pattern_t pat, int form, const double* d_coef, c
 SFEM_API int sfem_assemble_ST(sfem_pattern_t pat, const double* d_eps_r, const double* d_mu_r,
                      const uint8_t* d_pec_row_flags, double* d_S, double* d_T, int kernel, void* stream);
 
+/* number of kernel launches one sfem_assemble_ST call issues with the given kernel variant (bench accounting) */
+SFEM_API int sfem_launches_per_assemble_ST(sfem_pattern_t pat, int kernel);
+
 /* DirichletBC.apply(A) -> GenericMatrix::ident (sucemfem/BoundaryConditions/essential.py:77-81, called from
  * sucemfem/BoundaryConditions/container.py:39-42) as a separate step on already assembled values:
  * flagged rows of the block become unit rows, pattern kept, columns untouched. */

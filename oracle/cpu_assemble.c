@@ -1,0 +1,200 @@
+/* TEST INFRASTRUCTURE -- CPU oracle / CPU baseline, never linked into or called by the product path.
+ *
+ * Plain-C restatement of the algorithm the reference's hot path runs inside DOLFIN 1.0
+ * (dolfin.assemble + DirichletBC.apply, called at /root/reference/sucemfem/SystemMatrices.py:54-55):
+ *
+ *   oc_number_entities  first-appearance numbering of edges/faces over (cell asc., local entity asc.)
+ *                       (DOLFIN mesh.init(d) triggered by FunctionSpace, EMProblem.py:100-105)
+ *   oc_pattern          per-row sorted union of the cell-dof sets (SparsityPatternBuilder)
+ *   oc_assemble_cells   serial loop over cells in index order: element tensors of
+ *                       eps_r*inner(v,u)*dx (Forms.py:76) and dot(curl v,curl u)/mu_r*dx (Forms.py:84)
+ *                       by contraction of per-cell geometry with pre-integrated reference tensors (what an
+ *                       FFC tensor-representation tabulate_tensor does), then A.add(block, dofs) as per-entry
+ *                       binary-search insertion into the preallocated CSR rows (uBLAS/PETSc MatSetValues)
+ *   oc_apply_ident      row-only ident (DirichletBC::apply -> GenericMatrix::ident)
+ *
+ * DOLFIN itself is not available here (un-vendored, un-pinned dependency; Python 2), so this is a "port"
+ * in bench.py's cpu_baseline vocabulary: "CPU restatement of the reference algorithm", never "DOLFIN".
+ * The reference tensors are passed in by the caller (oracle/refelem.py, exact rationals rounded to fp64),
+ * so this file shares no tables with the CUDA library.  Tets only (the benchmarked configs); 2-D goes
+ * through oracle/fem.py.
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+static const int TET_EDGES[6][2] = {{2, 3}, {1, 3}, {1, 2}, {0, 3}, {0, 2}, {0, 1}};
+static const int TET_FACES[4][3] = {{1, 2, 3}, {0, 2, 3}, {0, 1, 3}, {0, 1, 2}};
+
+typedef struct { int64_t k0, k1; int64_t seq; } key_t_;
+
+static int cmp_key(const void* a, const void* b) {
+  const key_t_* x = (const key_t_*)a; const key_t_* y = (const key_t_*)b;
+  if (x->k0 != y->k0) return x->k0 < y->k0 ? -1 : 1;
+  if (x->k1 != y->k1) return x->k1 < y->k1 ? -1 : 1;
+  return x->seq < y->seq ? -1 : (x->seq > y->seq);
+}
+static int cmp_i64(const void* a, const void* b) {
+  int64_t x = *(const int64_t*)a, y = *(const int64_t*)b;
+  return x < y ? -1 : (x > y);
+}
+
+/* number one entity class; nloc local entities of nvk vertices; out[c*nloc+l] = index; returns count */
+static int64_t number_class(const int32_t* cells, int64_t C, int nloc, int nvk, const int* topo, int64_t V,
+                            int32_t* out) {
+  int64_t n = C * nloc, i;
+  key_t_* keys = (key_t_*)malloc(sizeof(key_t_) * n);
+  for (i = 0; i < n; ++i) {
+    int64_t c = i / nloc; int l = (int)(i % nloc);
+    const int32_t* cv = cells + c * 4;
+    int64_t a = cv[topo[l * nvk]], b = cv[topo[l * nvk + 1]], d = nvk == 3 ? cv[topo[l * nvk + 2]] : 0;
+    keys[i].k0 = a * V + b; keys[i].k1 = d; keys[i].seq = i;
+  }
+  qsort(keys, n, sizeof(key_t_), cmp_key);
+  /* first appearance = smallest seq of each run (runs are sorted by seq); rank the first seqs */
+  int64_t* first = (int64_t*)malloc(sizeof(int64_t) * n); int64_t nf = 0;
+  for (i = 0; i < n; ++i)
+    if (i == 0 || keys[i].k0 != keys[i - 1].k0 || keys[i].k1 != keys[i - 1].k1) first[nf++] = keys[i].seq;
+  qsort(first, nf, sizeof(int64_t), cmp_i64);
+  int64_t head_seq = -1; int64_t idx = -1;
+  for (i = 0; i < n; ++i) {
+    if (i == 0 || keys[i].k0 != keys[i - 1].k0 || keys[i].k1 != keys[i - 1].k1) {
+      head_seq = keys[i].seq;
+      int64_t* p = (int64_t*)bsearch(&head_seq, first, nf, sizeof(int64_t), cmp_i64);
+      idx = p - first;
+    }
+    out[keys[i].seq] = (int32_t)idx;
+  }
+  free(first); free(keys);
+  return nf;
+}
+
+int oc_number_entities(const int32_t* cells, int64_t C, int64_t V, int32_t* cell_edges, int32_t* cell_faces,
+                       int64_t* nE, int64_t* nF) {
+  *nE = number_class(cells, C, 6, 2, &TET_EDGES[0][0], V, cell_edges);
+  *nF = number_class(cells, C, 4, 3, &TET_FACES[0][0], V, cell_faces);
+  return 0;
+}
+
+/* cell dofs, SURVEY 8.1-D: order 1: edge; order 2: 2*edge+k, then 2E + 2*face + k */
+void oc_cell_dofs(const int32_t* cell_edges, const int32_t* cell_faces, int64_t C, int64_t E, int order,
+                  int32_t* out) {
+  int64_t c; int u, k;
+  if (order == 1) { memcpy(out, cell_edges, sizeof(int32_t) * 6 * C); return; }
+  for (c = 0; c < C; ++c) {
+    for (u = 0; u < 6; ++u) for (k = 0; k < 2; ++k) out[c * 20 + 2 * u + k] = 2 * cell_edges[c * 6 + u] + k;
+    for (u = 0; u < 4; ++u) for (k = 0; k < 2; ++k) out[c * 20 + 12 + 2 * u + k] = (int32_t)(2 * E + 2 * cell_faces[c * 4 + u] + k);
+  }
+}
+
+/* pattern: two passes (count, fill) over a dof -> cells incidence built by counting sort */
+int64_t oc_pattern(const int32_t* cd, int64_t C, int nd, int64_t ndof, int64_t* rowptr, int32_t* cols /* may be NULL */) {
+  int64_t* ptr = (int64_t*)calloc(ndof + 1, sizeof(int64_t));
+  int64_t i, c, r; int j;
+  for (i = 0; i < C * nd; ++i) ptr[cd[i] + 1]++;
+  for (r = 0; r < ndof; ++r) ptr[r + 1] += ptr[r];
+  int32_t* inc = (int32_t*)malloc(sizeof(int32_t) * C * nd);
+  int64_t* fill = (int64_t*)malloc(sizeof(int64_t) * ndof);
+  memcpy(fill, ptr, sizeof(int64_t) * ndof);
+  for (c = 0; c < C; ++c) for (j = 0; j < nd; ++j) inc[fill[cd[c * nd + j]]++] = (int32_t)c;
+  int64_t cap = 4096; int64_t* tmp = (int64_t*)malloc(sizeof(int64_t) * cap);
+  int64_t nnz = 0;
+  rowptr[0] = 0;
+  for (r = 0; r < ndof; ++r) {
+    int64_t m = (ptr[r + 1] - ptr[r]) * nd, k = 0, u = 0;
+    if (m > cap) { cap = 2 * m; tmp = (int64_t*)realloc(tmp, sizeof(int64_t) * cap); }
+    for (i = ptr[r]; i < ptr[r + 1]; ++i) for (j = 0; j < nd; ++j) tmp[k++] = cd[(int64_t)inc[i] * nd + j];
+    qsort(tmp, m, sizeof(int64_t), cmp_i64);
+    for (i = 0; i < m; ++i) if (i == 0 || tmp[i] != tmp[i - 1]) { if (cols) cols[nnz + u] = (int32_t)tmp[i]; ++u; }
+    nnz += u; rowptr[r + 1] = nnz;
+  }
+  free(tmp); free(fill); free(inc); free(ptr);
+  return nnz;
+}
+
+static inline int64_t find_slot(const int64_t* rowptr, const int32_t* cols, int32_t r, int32_t c) {
+  int64_t lo = rowptr[r], hi = rowptr[r + 1] - 1;
+  while (lo < hi) { int64_t mid = (lo + hi) >> 1; if (cols[mid] < c) lo = mid + 1; else hi = mid; }
+  return lo;
+}
+
+/* Mhat, Chat: [3][3][nd][nd] as produced by oracle/refelem.py.  threads = 1: serial, ascending cell order
+ * (what DOLFIN 1.0 + sucemfem run); threads > 1: OpenMP over cells with atomic adds (order not fixed). */
+int oc_assemble_cells(const double* coords, const int32_t* cells, int64_t C, const int32_t* cd, int nd,
+                      const double* Mhat, const double* Chat, const double* eps, const double* mu,
+                      const int64_t* rowptr, const int32_t* cols, double* S, double* M, int threads) {
+  int64_t c;
+#ifdef _OPENMP
+  if (threads < 1) threads = omp_get_max_threads();
+#pragma omp parallel for num_threads(threads) schedule(static) if (threads > 1)
+#endif
+  for (c = 0; c < C; ++c) {
+    const int32_t* cv = cells + c * 4;
+    double J[3][3], Ji[3][3], G[3][3], Gi[3][3];
+    int a, b, d, i, j;
+    for (d = 0; d < 3; ++d) for (a = 0; a < 3; ++a) J[d][a] = coords[(int64_t)cv[a + 1] * 3 + d] - coords[(int64_t)cv[0] * 3 + d];
+    double c00 = J[1][1] * J[2][2] - J[1][2] * J[2][1], c01 = J[1][2] * J[2][0] - J[1][0] * J[2][2],
+           c02 = J[1][0] * J[2][1] - J[1][1] * J[2][0];
+    double det = J[0][0] * c00 + J[0][1] * c01 + J[0][2] * c02, id = 1.0 / det;
+    Ji[0][0] = c00 * id; Ji[1][0] = c01 * id; Ji[2][0] = c02 * id;
+    Ji[0][1] = (J[0][2] * J[2][1] - J[0][1] * J[2][2]) * id;
+    Ji[1][1] = (J[0][0] * J[2][2] - J[0][2] * J[2][0]) * id;
+    Ji[2][1] = (J[0][1] * J[2][0] - J[0][0] * J[2][1]) * id;
+    Ji[0][2] = (J[0][1] * J[1][2] - J[0][2] * J[1][1]) * id;
+    Ji[1][2] = (J[0][2] * J[1][0] - J[0][0] * J[1][2]) * id;
+    Ji[2][2] = (J[0][0] * J[1][1] - J[0][1] * J[1][0]) * id;
+    double ad = fabs(det), sm = ad * (eps ? eps[c] : 1.0), ss = 1.0 / (ad * (mu ? mu[c] : 1.0));
+    for (a = 0; a < 3; ++a) for (b = 0; b < 3; ++b) {
+      double gi = 0, gg = 0;
+      for (d = 0; d < 3; ++d) { gi += Ji[a][d] * Ji[b][d]; gg += J[d][a] * J[d][b]; }
+      Gi[a][b] = gi * sm; G[a][b] = gg * ss;
+    }
+    double Ae[2][20 * 20];
+    for (i = 0; i < nd * nd; ++i) {
+      double m = 0, s = 0;
+      for (a = 0; a < 3; ++a) for (b = 0; b < 3; ++b) {
+        m += Gi[a][b] * Mhat[(a * 3 + b) * nd * nd + i];
+        s += G[a][b] * Chat[(a * 3 + b) * nd * nd + i];
+      }
+      Ae[0][i] = s; Ae[1][i] = m;
+    }
+    const int32_t* dofs = cd + c * nd;
+    for (i = 0; i < nd; ++i) for (j = 0; j < nd; ++j) {
+      int64_t slot = find_slot(rowptr, cols, dofs[i], dofs[j]);
+      if (threads > 1) {
+#ifdef _OPENMP
+#pragma omp atomic
+#endif
+        S[slot] += Ae[0][i * nd + j];
+#ifdef _OPENMP
+#pragma omp atomic
+#endif
+        M[slot] += Ae[1][i * nd + j];
+      } else {
+        S[slot] += Ae[0][i * nd + j];
+        M[slot] += Ae[1][i * nd + j];
+      }
+    }
+  }
+  return 0;
+}
+
+void oc_apply_ident(const int64_t* rowptr, const int32_t* cols, double* vals, const int64_t* rows, int64_t nrows) {
+  int64_t k, i;
+  for (k = 0; k < nrows; ++k) {
+    int64_t r = rows[k];
+    for (i = rowptr[r]; i < rowptr[r + 1]; ++i) vals[i] = cols[i] == r ? 1.0 : 0.0;
+  }
+}
+
+int oc_max_threads(void) {
+#ifdef _OPENMP
+  return omp_get_max_threads();
+#else
+  return 1;
+#endif
+}

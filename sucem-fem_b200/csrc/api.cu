@@ -394,6 +394,12 @@ int sfem_partition_rows(sfem_space_t sp, int nparts, int64_t* ent_bounds, void* 
   return 0;
 }
 
+int sfem_launches_per_assemble_ST(sfem_pattern_t pat, int kernel) {
+  if (!pat) return 0;
+  if (kernel == SFEM_KERNEL_AUTO) kernel = canonical_supported(pat) ? SFEM_KERNEL_CANONICAL : SFEM_KERNEL_GENERIC;
+  return kernel == SFEM_KERNEL_CANONICAL ? canonical_launches(pat) : 2;  // generic: cell geometry + row gather
+}
+
 int sfem_apply_ident(sfem_pattern_t pat, const uint8_t* d_row_flags, double* d_values, void* stream) {
   SFEM_CHECK(pat && d_row_flags && d_values, "NULL argument");
   DeviceGuard dg(pat->space->mesh->device);

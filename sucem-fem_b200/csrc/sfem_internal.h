@@ -139,4 +139,5 @@ int assemble_generic(const sfem_pattern_s* pat, int form, const double* coef_a, 
 int assemble_canonical_ST(const sfem_pattern_s* pat, const double* eps, const double* mu, const uint8_t* pec,
                           double* S, double* T, cudaStream_t st);
 bool canonical_supported(const sfem_pattern_s* pat);
+int canonical_launches(const sfem_pattern_s* pat);
 }  // namespace sfem

@@ -46,6 +46,7 @@ def _load():
         'sfem_assemble': (i32, [vp, i32, vp, vp, vp, vp, i32, vp]),
         'sfem_assemble_ST': (i32, [vp, vp, vp, vp, vp, vp, i32, vp]),
         'sfem_apply_ident': (i32, [vp, vp, vp, vp]),
+        'sfem_launches_per_assemble_ST': (i32, [vp, i32]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)      # AttributeError here = the library does not export what the header declares
