@@ -148,11 +148,15 @@ int build_pattern(sfem_pattern_s* pat, cudaStream_t st) {
   SFEM_CUDA(cudaMalloc(&tmp, std::max(tb, tb2) + 16));
   SFEM_CUDA(cub::DeviceScan::ExclusiveSum(tmp, tb, len64, pat->ent_rowptr, (int)(n + 1), st));
   int32_t* d_max = (int32_t*)len64;  // len64 is dead after the scan
-  if (n > 0) SFEM_CUDA(cub::DeviceReduce::Max(tmp, tb2, row_len, d_max, (int)n, st));
-  int h_over = 0, h_max = 0;
+  const int64_t n_edge_rows = std::max<int64_t>(0, std::min(pat->ent_hi, sp->E) - pat->ent_lo);
+  if (n_edge_rows > 0) SFEM_CUDA(cub::DeviceReduce::Max(tmp, tb2, row_len, d_max, (int)n_edge_rows, st));
+  if (n > n_edge_rows)
+    SFEM_CUDA(cub::DeviceReduce::Max(tmp, tb2, row_len + n_edge_rows, d_max + 1, (int)(n - n_edge_rows), st));
+  int h_over = 0, h_max2[2] = {0, 0};
   SFEM_CUDA(cudaMemcpyAsync(&pat->nnz_ent, pat->ent_rowptr + n, 8, cudaMemcpyDeviceToHost, st));
   SFEM_CUDA(cudaMemcpyAsync(&h_over, overflow, 4, cudaMemcpyDeviceToHost, st));
-  if (n > 0) SFEM_CUDA(cudaMemcpyAsync(&h_max, d_max, 4, cudaMemcpyDeviceToHost, st));
+  if (n_edge_rows > 0) SFEM_CUDA(cudaMemcpyAsync(&h_max2[0], d_max, 4, cudaMemcpyDeviceToHost, st));
+  if (n > n_edge_rows) SFEM_CUDA(cudaMemcpyAsync(&h_max2[1], d_max + 1, 4, cudaMemcpyDeviceToHost, st));
   SFEM_CUDA(cudaStreamSynchronize(st));
   cudaFree(tmp);
   cudaFree(len64);
@@ -162,7 +166,9 @@ int build_pattern(sfem_pattern_s* pat, cudaStream_t st) {
     set_error("an entity has more incident cells than the pattern builder supports (valence*entities > 1024)");
     return 3;
   }
-  pat->max_row_len = h_max;
+  pat->max_row_len_edges = h_max2[0];
+  pat->max_row_len_other = h_max2[1];
+  pat->max_row_len = std::max(h_max2[0], h_max2[1]);
   SFEM_CUDA(cudaMalloc(&pat->ent_cols, std::max<int64_t>(pat->nnz_ent, 1) * 4));
   SFEM_CUDA(cudaMalloc(&pat->pos, std::max<int64_t>(pat->n_inc_block * sp->n_ent_cell, 1) * 2));
   if (n > 0)

@@ -105,6 +105,8 @@ struct sfem_pattern_s {
   int64_t inc_base = 0;           // = space->inc_ptr[ent_lo]
   int64_t n_inc_block = 0;
   int max_row_len = 0;            // longest entity row of the block
+  int max_row_len_edges = 0;      // ... among its edge rows
+  int max_row_len_other = 0;      // ... among its face / interior rows
 };
 
 namespace sfem {
