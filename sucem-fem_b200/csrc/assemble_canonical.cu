@@ -22,6 +22,7 @@
 #include "sfem_internal.h"
 
 #define SFEM_TABLE static __device__ const
+#include "generated/canonical_lut.inc"
 #include "generated/canonical_rows.inc"
 
 namespace sfem {
@@ -36,7 +37,7 @@ struct CanonArgs {
   const int32_t* __restrict__ inc_cell;
   const uint8_t* __restrict__ inc_loc;
   const int64_t* __restrict__ ent_rowptr;  // block-relative, indexed by r = g - ent_lo
-  const uint16_t* __restrict__ pos;
+  const uint32_t* __restrict__ posw;       // slot table, canonical column order, 5 x (2 x uint16) per incidence
   const uint8_t* __restrict__ pec;
   double* __restrict__ S;
   double* __restrict__ T;
@@ -47,25 +48,55 @@ struct CanonArgs {
   int max_chunks;    // 2 * (longest entity row in this launch)
 };
 
-// geometry factors of the relabelled cell (vertex ids v[0..3]) in symmetric order (00,11,22,01,02,12):
+// per-(entity, cell) inputs gathered from global memory
+struct Item {
+  double X[12];             // coordinates of the relabelled vertices
+  double eps, mu;
+  unsigned long long desc;  // generated/canonical_lut.inc
+  unsigned fsel;
+  uint32_t w[5];            // slots of the 10 canonical column entities (uint16 pairs)
+};
+
+__device__ __forceinline__ int slot_of(const Item& it, int U) { return (it.w[U >> 1] >> (16 * (U & 1))) & 0xffffu; }
+
+__device__ __forceinline__ void gather_item(const CanonArgs& p, const unsigned long long* __restrict__ s_desc,
+                                            const unsigned* __restrict__ s_fsel, int64_t i, int64_t c, int t, int4 cv,
+                                            Item& it) {
+  it.desc = s_desc[t];
+  it.fsel = s_fsel[t];
+  const int32_t a[4] = {cv.x, cv.y, cv.z, cv.w};
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const unsigned s = (unsigned)(it.desc >> (2 * k)) & 3u;
+    const uint32_t v = (uint32_t)(s == 0 ? a[0] : (s == 1 ? a[1] : (s == 2 ? a[2] : a[3])));
+    const double* x = p.coords + (size_t)(v * 3u);
+    it.X[3 * k] = x[0];
+    it.X[3 * k + 1] = x[1];
+    it.X[3 * k + 2] = x[2];
+  }
+  it.eps = p.eps ? p.eps[c] : 1.0;
+  it.mu = p.mu ? p.mu[c] : 1.0;
+  const uint32_t* pw = p.posw + (i - p.inc_base) * 5;
+#pragma unroll
+  for (int k = 0; k < 5; ++k) it.w[k] = pw[k];
+}
+
+// geometry factors of the relabelled cell in symmetric order (00,11,22,01,02,12):
 //   MASS: |detJ| eps (J^-1 J^-T)      else: (J^T J) / (|detJ| mu)
 template <bool MASS>
-__device__ __forceinline__ void canon_geometry(const double* __restrict__ coords, const int32_t (&v)[4], double coef,
-                                               double (&g)[6]) {
-  double x0[3], J[3][3];
-#pragma unroll
-  for (int d = 0; d < 3; ++d) x0[d] = coords[(int64_t)v[0] * 3 + d];
+__device__ __forceinline__ void canon_geometry(const Item& it, double (&g)[6]) {
+  double J[3][3];
 #pragma unroll
   for (int a = 0; a < 3; ++a)
 #pragma unroll
-    for (int d = 0; d < 3; ++d) J[d][a] = coords[(int64_t)v[a + 1] * 3 + d] - x0[d];
+    for (int d = 0; d < 3; ++d) J[d][a] = it.X[3 * (a + 1) + d] - it.X[d];
   const double c00 = J[1][1] * J[2][2] - J[1][2] * J[2][1];
   const double c01 = J[1][2] * J[2][0] - J[1][0] * J[2][2];
   const double c02 = J[1][0] * J[2][1] - J[1][1] * J[2][0];
   const double det = J[0][0] * c00 + J[0][1] * c01 + J[0][2] * c02;
   const double ad = fabs(det);
   if (MASS) {
-    // adj(J)[a][d] = det * Jinv[a][d];  Ginv = adj adj^T / det^2 ; times |det| eps -> adj adj^T * eps/|det|
+    // adj(J) = det J^-1;  J^-1 J^-T |det| eps = adj adj^T eps / |det|
     double A[3][3];
     A[0][0] = c00; A[1][0] = c01; A[2][0] = c02;
     A[0][1] = J[0][2] * J[2][1] - J[0][1] * J[2][2];
@@ -74,7 +105,7 @@ __device__ __forceinline__ void canon_geometry(const double* __restrict__ coords
     A[0][2] = J[0][1] * J[1][2] - J[0][2] * J[1][1];
     A[1][2] = J[0][2] * J[1][0] - J[0][0] * J[1][2];
     A[2][2] = J[0][0] * J[1][1] - J[0][1] * J[1][0];
-    const double s = coef / ad;
+    const double s = it.eps / ad;
     g[0] = (A[0][0] * A[0][0] + A[0][1] * A[0][1] + A[0][2] * A[0][2]) * s;
     g[1] = (A[1][0] * A[1][0] + A[1][1] * A[1][1] + A[1][2] * A[1][2]) * s;
     g[2] = (A[2][0] * A[2][0] + A[2][1] * A[2][1] + A[2][2] * A[2][2]) * s;
@@ -82,7 +113,7 @@ __device__ __forceinline__ void canon_geometry(const double* __restrict__ coords
     g[4] = (A[0][0] * A[2][0] + A[0][1] * A[2][1] + A[0][2] * A[2][2]) * s;
     g[5] = (A[1][0] * A[2][0] + A[1][1] * A[2][1] + A[1][2] * A[2][2]) * s;
   } else {
-    const double s = 1.0 / (ad * coef);
+    const double s = 1.0 / (ad * it.mu);
     g[0] = (J[0][0] * J[0][0] + J[1][0] * J[1][0] + J[2][0] * J[2][0]) * s;
     g[1] = (J[0][1] * J[0][1] + J[1][1] * J[1][1] + J[2][1] * J[2][1]) * s;
     g[2] = (J[0][2] * J[0][2] + J[1][2] * J[1][2] + J[2][2] * J[2][2]) * s;
@@ -109,18 +140,8 @@ __device__ __forceinline__ double2 fix_columns(unsigned long long desc, unsigned
   }
 }
 
-__device__ __forceinline__ void load_relabelled(const int32_t* __restrict__ cells, int64_t c, unsigned long long desc,
-                                                int32_t (&v)[4]) {
-  const int4 cv = *reinterpret_cast<const int4*>(cells + c * 4);
-  const int32_t a[4] = {cv.x, cv.y, cv.z, cv.w};
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const unsigned s = (unsigned)(desc >> (2 * i)) & 3u;
-    v[i] = s == 0 ? a[0] : (s == 1 ? a[1] : (s == 2 ? a[2] : a[3]));
-  }
-}
-
-// cooperative write-out of a warp's tile: 8 entities x 4 consecutive chunks per instruction
+// cooperative write-out of a warp's tile: 8 entities x 4 consecutive chunks per instruction (64-byte segments per
+// entity, conflict-free tile reads); 4 independent load->store pairs in flight; streaming stores (written once).
 __device__ __forceinline__ void write_out(const double2* __restrict__ tile, double* __restrict__ out, int64_t a_mine,
                                           int len_mine, int lane) {
   const int gg = lane & 7, cq = lane >> 3;
@@ -132,58 +153,89 @@ __device__ __forceinline__ void write_out(const double2* __restrict__ tile, doub
 #pragma unroll
     for (int o = 1; o < 8; o <<= 1) nmax = max(nmax, __shfl_xor_sync(0xffffffffu, nmax, o));
     double2* dst = reinterpret_cast<double2*>(out + 4 * a);
-    for (int cc = cq; cc < nmax; cc += 4)
-      if (cc < nch) dst[cc] = tile[cc * 32 + gb + gg];
+    const double2* src = tile + gb + gg;
+#pragma unroll 1
+    for (int c0 = cq; c0 < nmax; c0 += 16) {
+      double2 v[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (c0 + 4 * j < nch) v[j] = src[(c0 + 4 * j) * 32];
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (c0 + 4 * j < nch) __stcs(dst + c0 + 4 * j, v[j]);
+    }
   }
+}
+
+__device__ __forceinline__ void pec_overwrite(const CanonArgs& p, double2* __restrict__ col, int64_t g, int len, int self) {
+#pragma unroll
+  for (int k = 0; k < 2; ++k)
+    if (p.pec[2 * g + k]) {
+      for (int s = 0; s < len; ++s) col[(k * len + s) * 32] = make_double2(0.0, 0.0);
+      col[(k * len + self) * 32] = k == 0 ? make_double2(1.0, 0.0) : make_double2(0.0, 1.0);
+    }
 }
 
 constexpr int kThreadsEdges = 64;   // CTAs per SM are bounded by the shared-memory tile (2*max_len*512 B per warp)
 constexpr int kThreadsFaces = 128;
 
-// ---- edges: accumulate over the incident cells ----------------------------------------------------------------
+// ---- edges: accumulate over the incident cells, software-pipelined gathers ---------------------------------------
+// The gather chain of an item is three dependent global loads (incidence -> cell vertices -> coordinates).  With
+// only a handful of resident warps (the tile bounds occupancy) it is hidden by issuing it one (coordinates) and two
+// (incidence, vertices) items ahead of the item being computed.
 template <bool MASS>
-__device__ __forceinline__ void edge_pass(const CanonArgs& p, double2* __restrict__ tile, int lane, bool valid,
-                                          int64_t g, int64_t a, int len, int64_t i0, int64_t i1) {
-  if (valid)
-    for (int cc = 0; cc < 2 * len; ++cc) tile[cc * 32 + lane] = make_double2(0.0, 0.0);
+__device__ __forceinline__ void edge_pass(const CanonArgs& p, const unsigned long long* __restrict__ s_desc,
+                                          const unsigned* __restrict__ s_fsel, double2* __restrict__ tile, int lane,
+                                          bool valid, int64_t g, int64_t a, int len, int64_t i0, int64_t i1) {
+  double2* col = tile + lane;
   if (valid) {
+    for (int cc = 0; cc < 2 * len; ++cc) col[cc * 32] = make_double2(0.0, 0.0);
+    Item cur, nxt;
+    int64_t c1 = 0;
+    int t1 = 0;
+    int4 cv1 = make_int4(0, 0, 0, 0);
+    {
+      const int64_t c0 = p.inc_cell[i0];
+      const int t0 = p.inc_loc[i0];
+      if (i0 + 1 < i1) {
+        c1 = p.inc_cell[i0 + 1];
+        t1 = p.inc_loc[i0 + 1];
+      }
+      const int4 cv0 = *reinterpret_cast<const int4*>(p.cells + c0 * 4);
+      if (i0 + 1 < i1) cv1 = *reinterpret_cast<const int4*>(p.cells + c1 * 4);
+      gather_item(p, s_desc, s_fsel, i0, c0, t0, cv0, cur);
+    }
 #pragma unroll 1
     for (int64_t i = i0; i < i1; ++i) {
-      const int64_t c = p.inc_cell[i];
-      const int t = p.inc_loc[i];
-      const unsigned long long desc = kCanonDesc_edge[t];
-      const unsigned facesel = kCanonFaceSel_edge[t];
-      int32_t v[4];
-      load_relabelled(p.cells, c, desc, v);
+      int64_t c2 = 0;
+      int t2 = 0;
+      int4 cv2 = make_int4(0, 0, 0, 0);
+      if (i + 2 < i1) {
+        c2 = p.inc_cell[i + 2];
+        t2 = p.inc_loc[i + 2];
+      }
+      if (i + 1 < i1) gather_item(p, s_desc, s_fsel, i + 1, c1, t1, cv1, nxt);
+      if (i + 2 < i1) cv2 = *reinterpret_cast<const int4*>(p.cells + c2 * 4);
       double gm[6], o[40];
-      const double coef = MASS ? (p.eps ? p.eps[c] : 1.0) : (p.mu ? p.mu[c] : 1.0);
-      canon_geometry<MASS>(p.coords, v, coef, gm);
+      canon_geometry<MASS>(cur, gm);
       if (MASS) canon_edge_mass(gm, o); else canon_edge_curl(gm, o);
-      const uint16_t* ps = p.pos + (i - p.inc_base) * 10;
-#define SFEM_EDGE_ACC(U)                                                                   \
-      {                                                                                    \
-        const int slot = ps[(unsigned)(desc >> (8 + 4 * U)) & 15u];                        \
-        const double2 r0 = fix_columns<U>(desc, facesel, o[2 * U], o[2 * U + 1]);          \
-        const double2 r1 = fix_columns<U>(desc, facesel, o[20 + 2 * U], o[20 + 2 * U + 1]);\
-        double2* q0 = tile + slot * 32 + lane;                                             \
-        double2* q1 = tile + (len + slot) * 32 + lane;                                     \
-        double2 t0 = *q0, t1 = *q1;                                                        \
-        t0.x += r0.x; t0.y += r0.y; t1.x += r1.x; t1.y += r1.y;                            \
-        *q0 = t0; *q1 = t1;                                                                \
+#define SFEM_EDGE_ACC(U)                                                                        \
+      {                                                                                         \
+        const int slot = slot_of(cur, U);                                                       \
+        const double2 r0 = fix_columns<U>(cur.desc, cur.fsel, o[2 * U], o[2 * U + 1]);          \
+        const double2 r1 = fix_columns<U>(cur.desc, cur.fsel, o[20 + 2 * U], o[20 + 2 * U + 1]);\
+        double2* q0 = col + slot * 32;                                                          \
+        double2* q1 = col + (len + slot) * 32;                                                  \
+        double2 t0 = *q0, t1v = *q1;                                                            \
+        t0.x += r0.x; t0.y += r0.y; t1v.x += r1.x; t1v.y += r1.y;                               \
+        *q0 = t0; *q1 = t1v;                                                                    \
       }
       SFEM_EDGE_ACC(0) SFEM_EDGE_ACC(1) SFEM_EDGE_ACC(2) SFEM_EDGE_ACC(3) SFEM_EDGE_ACC(4)
       SFEM_EDGE_ACC(5) SFEM_EDGE_ACC(6) SFEM_EDGE_ACC(7) SFEM_EDGE_ACC(8) SFEM_EDGE_ACC(9)
 #undef SFEM_EDGE_ACC
-    }
-    if (p.pec) {
-      // unit rows: the row entity's own slot = slot of canonical entity 5 (= itself) in any incident cell
-      const int self = p.pos[(i0 - p.inc_base) * 10 + p.inc_loc[i0]];
-#pragma unroll
-      for (int k = 0; k < 2; ++k)
-        if (p.pec[2 * g + k]) {
-          for (int s = 0; s < len; ++s) tile[(k * len + s) * 32 + lane] = make_double2(0.0, 0.0);
-          tile[(k * len + self) * 32 + lane] = k == 0 ? make_double2(1.0, 0.0) : make_double2(0.0, 1.0);
-        }
+      if (i + 1 == i1 && p.pec) pec_overwrite(p, col, g, len, slot_of(cur, 5));  // canonical entity 5 = the row edge
+      cur = nxt;
+      c1 = c2; t1 = t2; cv1 = cv2;
     }
   }
   __syncwarp();
@@ -191,8 +243,19 @@ __device__ __forceinline__ void edge_pass(const CanonArgs& p, double2* __restric
   __syncwarp();
 }
 
+__device__ __forceinline__ void stage_lut(unsigned long long* s_desc, unsigned* s_fsel) {
+  if (threadIdx.x < 10) {
+    s_desc[threadIdx.x] = kCanonDesc[threadIdx.x];
+    s_fsel[threadIdx.x] = kCanonFaceSel[threadIdx.x];
+  }
+  __syncthreads();
+}
+
 __global__ void __launch_bounds__(kThreadsEdges) k_canon_edges(CanonArgs p) {
   extern __shared__ double2 smem[];
+  __shared__ unsigned long long s_desc[10];
+  __shared__ unsigned s_fsel[10];
+  stage_lut(s_desc, s_fsel);
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   double2* tile = smem + (size_t)w * p.max_chunks * 32;
   const int64_t r = p.r_begin + blockIdx.x * (int64_t)kThreadsEdges + threadIdx.x;
@@ -206,64 +269,46 @@ __global__ void __launch_bounds__(kThreadsEdges) k_canon_edges(CanonArgs p) {
     i0 = p.inc_ptr[g];
     i1 = p.inc_ptr[g + 1];
   }
-  edge_pass<false>(p, tile, lane, valid, g, a, len, i0, i1);
-  edge_pass<true>(p, tile, lane, valid, g, a, len, i0, i1);
+  edge_pass<false>(p, s_desc, s_fsel, tile, lane, valid, g, a, len, i0, i1);
+  edge_pass<true>(p, s_desc, s_fsel, tile, lane, valid, g, a, len, i0, i1);
 }
 
 // ---- faces: at most two cells; shared entities summed in registers, tile is store-only --------------------------
 template <bool MASS>
 __device__ __forceinline__ void face_pass(const CanonArgs& p, double2* __restrict__ tile, int lane, bool valid,
-                                          int64_t g, int64_t a, int len, int64_t i0, int ncell) {
+                                          int64_t g, int64_t a, int len, int ncell, const Item& A, const Item& B) {
+  double2* col = tile + lane;
   if (valid) {
-    const int64_t cA = p.inc_cell[i0];
-    const int tA = p.inc_loc[i0] - 6;
-    const unsigned long long dA = kCanonDesc_face[tA];
-    const unsigned fA = kCanonFaceSel_face[tA];
-    const uint16_t* psA = p.pos + (i0 - p.inc_base) * 10;
-    int32_t v[4];
     double gm[6], oA[40];
-    load_relabelled(p.cells, cA, dA, v);
-    canon_geometry<MASS>(p.coords, v, MASS ? (p.eps ? p.eps[cA] : 1.0) : (p.mu ? p.mu[cA] : 1.0), gm);
-    if (MASS) canon_face_mass(gm, oA); else canon_face_curl(gm, oA);
+#define SFEM_FACE_PUT(U, IT, O)                                                                        \
+    {                                                                                                  \
+      const int slot = slot_of(IT, U);                                                                 \
+      col[slot * 32] = fix_columns<U>(IT.desc, IT.fsel, O[2 * U], O[2 * U + 1]);                       \
+      col[(len + slot) * 32] = fix_columns<U>(IT.desc, IT.fsel, O[20 + 2 * U], O[20 + 2 * U + 1]);     \
+    }
     if (ncell > 1) {
-      const int64_t cB = p.inc_cell[i0 + 1];
-      const int tB = p.inc_loc[i0 + 1] - 6;
-      const unsigned long long dB = kCanonDesc_face[tB];
-      const unsigned fB = kCanonFaceSel_face[tB];
-      const uint16_t* psB = psA + 10;
       double oB[40];
-      load_relabelled(p.cells, cB, dB, v);
-      canon_geometry<MASS>(p.coords, v, MASS ? (p.eps ? p.eps[cB] : 1.0) : (p.mu ? p.mu[cB] : 1.0), gm);
+      canon_geometry<MASS>(B, gm);
       if (MASS) canon_face_mass(gm, oB); else canon_face_curl(gm, oB);
+      SFEM_FACE_PUT(0, B, oB) SFEM_FACE_PUT(1, B, oB) SFEM_FACE_PUT(3, B, oB)
+      SFEM_FACE_PUT(6, B, oB) SFEM_FACE_PUT(7, B, oB) SFEM_FACE_PUT(8, B, oB)
+      canon_geometry<MASS>(A, gm);
+      if (MASS) canon_face_mass(gm, oA); else canon_face_curl(gm, oA);
       // entities of the shared face (canonical 2,4,5 = its edges, 9 = itself) are seen identically from both cells
 #define SFEM_FACE_SHARED(U)                                                    \
       oA[2 * U] += oB[2 * U]; oA[2 * U + 1] += oB[2 * U + 1];                  \
       oA[20 + 2 * U] += oB[20 + 2 * U]; oA[20 + 2 * U + 1] += oB[20 + 2 * U + 1];
       SFEM_FACE_SHARED(2) SFEM_FACE_SHARED(4) SFEM_FACE_SHARED(5) SFEM_FACE_SHARED(9)
 #undef SFEM_FACE_SHARED
-#define SFEM_FACE_PUT(U, DESC, FSEL, PS, O)                                                           \
-      {                                                                                               \
-        const int slot = PS[(unsigned)(DESC >> (8 + 4 * U)) & 15u];                                   \
-        tile[slot * 32 + lane] = fix_columns<U>(DESC, FSEL, O[2 * U], O[2 * U + 1]);                  \
-        tile[(len + slot) * 32 + lane] = fix_columns<U>(DESC, FSEL, O[20 + 2 * U], O[20 + 2 * U + 1]);\
-      }
-      SFEM_FACE_PUT(0, dB, fB, psB, oB) SFEM_FACE_PUT(1, dB, fB, psB, oB) SFEM_FACE_PUT(3, dB, fB, psB, oB)
-      SFEM_FACE_PUT(6, dB, fB, psB, oB) SFEM_FACE_PUT(7, dB, fB, psB, oB) SFEM_FACE_PUT(8, dB, fB, psB, oB)
+    } else {
+      canon_geometry<MASS>(A, gm);
+      if (MASS) canon_face_mass(gm, oA); else canon_face_curl(gm, oA);
     }
-    SFEM_FACE_PUT(0, dA, fA, psA, oA) SFEM_FACE_PUT(1, dA, fA, psA, oA) SFEM_FACE_PUT(2, dA, fA, psA, oA)
-    SFEM_FACE_PUT(3, dA, fA, psA, oA) SFEM_FACE_PUT(4, dA, fA, psA, oA) SFEM_FACE_PUT(5, dA, fA, psA, oA)
-    SFEM_FACE_PUT(6, dA, fA, psA, oA) SFEM_FACE_PUT(7, dA, fA, psA, oA) SFEM_FACE_PUT(8, dA, fA, psA, oA)
-    SFEM_FACE_PUT(9, dA, fA, psA, oA)
+    SFEM_FACE_PUT(0, A, oA) SFEM_FACE_PUT(1, A, oA) SFEM_FACE_PUT(2, A, oA) SFEM_FACE_PUT(3, A, oA)
+    SFEM_FACE_PUT(4, A, oA) SFEM_FACE_PUT(5, A, oA) SFEM_FACE_PUT(6, A, oA) SFEM_FACE_PUT(7, A, oA)
+    SFEM_FACE_PUT(8, A, oA) SFEM_FACE_PUT(9, A, oA)
 #undef SFEM_FACE_PUT
-    if (p.pec) {
-      const int self = psA[p.inc_loc[i0]];
-#pragma unroll
-      for (int k = 0; k < 2; ++k)
-        if (p.pec[2 * g + k]) {
-          for (int s = 0; s < len; ++s) tile[(k * len + s) * 32 + lane] = make_double2(0.0, 0.0);
-          tile[(k * len + self) * 32 + lane] = k == 0 ? make_double2(1.0, 0.0) : make_double2(0.0, 1.0);
-        }
-    }
+    if (p.pec) pec_overwrite(p, col, g, len, slot_of(A, 9));  // canonical entity 9 = the row face
   }
   __syncwarp();
   write_out(tile, MASS ? p.T : p.S, a, valid ? len : 0, lane);
@@ -272,21 +317,34 @@ __device__ __forceinline__ void face_pass(const CanonArgs& p, double2* __restric
 
 __global__ void __launch_bounds__(kThreadsFaces) k_canon_faces(CanonArgs p) {
   extern __shared__ double2 smem[];
+  __shared__ unsigned long long s_desc[10];
+  __shared__ unsigned s_fsel[10];
+  stage_lut(s_desc, s_fsel);
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   double2* tile = smem + (size_t)w * p.max_chunks * 32;
   const int64_t r = p.r_begin + blockIdx.x * (int64_t)kThreadsFaces + threadIdx.x;
   const bool valid = r < p.r_end;
-  int64_t g = 0, a = 0, i0 = 0;
+  int64_t g = 0, a = 0;
   int len = 0, ncell = 0;
+  Item A, B;
   if (valid) {
     g = p.ent_lo + r;
     a = p.ent_rowptr[r];
     len = (int)(p.ent_rowptr[r + 1] - a);
-    i0 = p.inc_ptr[g];
+    const int64_t i0 = p.inc_ptr[g];
     ncell = (int)(p.inc_ptr[g + 1] - i0);
+    // both gather chains are issued before anything is consumed
+    const int64_t cA = p.inc_cell[i0];
+    const int tA = p.inc_loc[i0];
+    const int64_t cB = ncell > 1 ? p.inc_cell[i0 + 1] : cA;
+    const int tB = ncell > 1 ? p.inc_loc[i0 + 1] : tA;
+    const int4 cvA = *reinterpret_cast<const int4*>(p.cells + cA * 4);
+    const int4 cvB = *reinterpret_cast<const int4*>(p.cells + cB * 4);
+    gather_item(p, s_desc, s_fsel, i0, cA, tA, cvA, A);
+    gather_item(p, s_desc, s_fsel, ncell > 1 ? i0 + 1 : i0, cB, tB, cvB, B);
   }
-  face_pass<false>(p, tile, lane, valid, g, a, len, i0, ncell);
-  face_pass<true>(p, tile, lane, valid, g, a, len, i0, ncell);
+  face_pass<false>(p, tile, lane, valid, g, a, len, ncell, A, B);
+  face_pass<true>(p, tile, lane, valid, g, a, len, ncell, A, B);
 }
 
 }  // namespace
@@ -307,7 +365,7 @@ int assemble_canonical_ST(const sfem_pattern_s* pat, const double* eps, const do
   CanonArgs p;
   p.coords = m->coords; p.cells = m->cells; p.eps = eps; p.mu = mu;
   p.inc_ptr = sp->inc_ptr; p.inc_cell = sp->inc_cell; p.inc_loc = sp->inc_loc;
-  p.ent_rowptr = pat->ent_rowptr; p.pos = pat->pos; p.pec = pec; p.S = S; p.T = T;
+  p.ent_rowptr = pat->ent_rowptr; p.posw = reinterpret_cast<const uint32_t*>(pat->pos); p.pec = pec; p.S = S; p.T = T;
   p.ent_lo = pat->ent_lo; p.inc_base = pat->inc_base;
   // faces meet at most two cells (a face shared by more is a broken mesh and is refused when the space is built)
   const int64_t E = sp->E;

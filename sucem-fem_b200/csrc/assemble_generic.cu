@@ -13,6 +13,7 @@
 
 #define SFEM_TABLE static __device__ const
 #include "generated/n1curl_tables.inc"
+#include "generated/canonical_lut.inc"
 
 namespace sfem {
 namespace {
@@ -185,6 +186,7 @@ struct PatView {
   const uint16_t* pos;
   int64_t ent_lo, n_rows, inc_base;
   int nec;
+  bool canon;  // slot table in canonical column order
 };
 
 constexpr int kWarps = 8;
@@ -220,6 +222,7 @@ k_values_generic(PatView pv, const double* __restrict__ geo, const double* __res
           for (int uu = 0; uu < pv.nec; ++uu)
             if (ps[uu] == s) u = uu;
           if (u < 0) continue;
+          if (pv.canon) u = (int)((kCanonDesc[pv.inc_loc[i]] >> (8 + 4 * u)) & 15ull);
           const int64_t c = pv.inc_cell[i];
           const int li = pv.inc_loc[i] * Q + k, lj = u * Q + kp;
           if (FORM == 2) {
@@ -270,7 +273,7 @@ int launch_generic(const sfem_pattern_s* pat, int form, const double* coef_a, co
   const sfem_space_s* sp = pat->space;
   const sfem_mesh_s* m = sp->mesh;
   PatView pv{sp->inc_ptr, sp->inc_cell, sp->inc_loc, pat->ent_rowptr, pat->ent_cols, pat->pos,
-             pat->ent_lo, pat->n_rows_ent, pat->inc_base, sp->n_ent_cell};
+             pat->ent_lo, pat->n_rows_ent, pat->inc_base, sp->n_ent_cell, pos_is_canonical(sp)};
   if (pat->n_rows_ent == 0) return 0;
   const unsigned grid = (unsigned)((pat->n_rows_ent + kWarps - 1) / kWarps);
   const int32_t* cell_facets = DIM == 3 ? sp->cell_faces : sp->cell_edges;

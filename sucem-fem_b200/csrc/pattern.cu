@@ -11,6 +11,9 @@
 
 #include "sfem_internal.h"
 
+#define SFEM_TABLE static __device__ const
+#include "generated/canonical_lut.inc"
+
 namespace sfem {
 namespace {
 
@@ -20,7 +23,8 @@ constexpr int kCap = 1024;  // candidates per row entity (valence * entities per
 template <bool FILL>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 k_pattern(SpaceView sv, const int64_t* __restrict__ inc_ptr, const int32_t* __restrict__ inc_cell,
-          int64_t ent_lo, int64_t n_rows, int64_t inc_base, int32_t* __restrict__ row_len,
+          const uint8_t* __restrict__ inc_loc, bool canon, int64_t ent_lo, int64_t n_rows, int64_t inc_base,
+          int32_t* __restrict__ row_len,
           const int64_t* __restrict__ ent_rowptr, int32_t* __restrict__ ent_cols, uint16_t* __restrict__ pos,
           int* __restrict__ overflow) {
   __shared__ int32_t s_cand[kWarpsPerBlock][kCap];
@@ -70,16 +74,19 @@ k_pattern(SpaceView sv, const int64_t* __restrict__ inc_ptr, const int32_t* __re
   }
   const int64_t rp = ent_rowptr[r];
   for (int k = lane; k < nu; k += 32) ent_cols[rp + k] = cand[k];
-  // slot of every (incidence, local entity) in the unique list
+  // slot of every (incidence, column entity) in the unique list.  Column entities are stored in the order the
+  // value kernels visit them: for order-2 tets the CANONICAL order of the cell relabelled around the row entity
+  // (u = umap[t][u'], generated/canonical_lut.inc), otherwise the cell-local order.
   for (int idx = lane; idx < L; idx += 32) {
     int i = idx / nec, u = idx - i * nec;
+    if (canon) u = (int)((kCanonDesc[inc_loc[i0 + i]] >> (8 + 4 * u)) & 15ull);
     int32_t x = sv.ent(inc_cell[i0 + i], u);
     int lo = 0, hi = nu - 1;
     while (lo < hi) {
       int mid = (lo + hi) >> 1;
       if (cand[mid] < x) lo = mid + 1; else hi = mid;
     }
-    pos[(i0 - inc_base + i) * nec + u] = (uint16_t)lo;
+    pos[(i0 - inc_base) * nec + idx] = (uint16_t)lo;
   }
 }
 
@@ -119,6 +126,7 @@ int build_pattern(sfem_pattern_s* pat, cudaStream_t st) {
   const sfem_space_s* sp = pat->space;
   const int64_t n = pat->n_rows_ent;
   SpaceView sv = make_view(sp);
+  const bool canon = pos_is_canonical(sp);
   int64_t bounds[2];
   SFEM_CUDA(cudaMemcpyAsync(&bounds[0], sp->inc_ptr + pat->ent_lo, 8, cudaMemcpyDeviceToHost, st));
   SFEM_CUDA(cudaMemcpyAsync(&bounds[1], sp->inc_ptr + pat->ent_hi, 8, cudaMemcpyDeviceToHost, st));
@@ -136,7 +144,7 @@ int build_pattern(sfem_pattern_s* pat, cudaStream_t st) {
   SFEM_CUDA(cudaMalloc(&pat->ent_rowptr, (n + 1) * 8));
   const unsigned grid = (unsigned)((n + kWarpsPerBlock - 1) / kWarpsPerBlock);
   if (n > 0)
-    k_pattern<false><<<grid, kWarpsPerBlock * 32, 0, st>>>(sv, sp->inc_ptr, sp->inc_cell, pat->ent_lo, n,
+    k_pattern<false><<<grid, kWarpsPerBlock * 32, 0, st>>>(sv, sp->inc_ptr, sp->inc_cell, sp->inc_loc, canon, pat->ent_lo, n,
                                                            pat->inc_base, row_len, nullptr, nullptr, nullptr,
                                                            overflow);
   k_len_to_i64<<<grid_for(n + 1), 256, 0, st>>>(row_len, len64, n);
@@ -172,7 +180,7 @@ int build_pattern(sfem_pattern_s* pat, cudaStream_t st) {
   SFEM_CUDA(cudaMalloc(&pat->ent_cols, std::max<int64_t>(pat->nnz_ent, 1) * 4));
   SFEM_CUDA(cudaMalloc(&pat->pos, std::max<int64_t>(pat->n_inc_block * sp->n_ent_cell, 1) * 2));
   if (n > 0)
-    k_pattern<true><<<grid, kWarpsPerBlock * 32, 0, st>>>(sv, sp->inc_ptr, sp->inc_cell, pat->ent_lo, n,
+    k_pattern<true><<<grid, kWarpsPerBlock * 32, 0, st>>>(sv, sp->inc_ptr, sp->inc_cell, sp->inc_loc, canon, pat->ent_lo, n,
                                                           pat->inc_base, nullptr, pat->ent_rowptr, pat->ent_cols,
                                                           pat->pos, overflow);
   SFEM_CUDA(cudaGetLastError());

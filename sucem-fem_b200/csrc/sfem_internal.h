@@ -101,7 +101,8 @@ struct sfem_pattern_s {
   int64_t nnz_ent = 0;            // entity-level non-zeros of the block
   int64_t* ent_rowptr = nullptr;  // [n_rows_ent+1], offsets into this block
   int32_t* ent_cols = nullptr;    // [nnz_ent] global entity ids, ascending within a row
-  uint16_t* pos = nullptr;        // [n_inc_block][n_ent_cell]: slot of the cell's u-th entity in the row
+  uint16_t* pos = nullptr;        // [n_inc_block][n_ent_cell]: slot of the cell's u-th column entity in the row
+                                  // (u in canonical order when pos_is_canonical(space))
   int64_t inc_base = 0;           // = space->inc_ptr[ent_lo]
   int64_t n_inc_block = 0;
   int max_row_len = 0;            // longest entity row of the block
@@ -131,6 +132,9 @@ inline SpaceView make_view(const sfem_space_s* s) {
   v.E = s->E;
   return v;
 }
+
+// order-2 tets: the slot table is stored in canonical column order (see pattern.cu / assemble_canonical.cu)
+inline bool pos_is_canonical(const sfem_space_s* s) { return s->mesh->gdim == 3 && s->order == 2; }
 
 int build_numbering(sfem_space_s* sp, cudaStream_t st);
 int build_pattern(sfem_pattern_s* pat, cudaStream_t st);
