@@ -244,6 +244,7 @@ int sfem_space_destroy(sfem_space_t sp) {
   cudaFree(sp->facet_first_cell);
   cudaFree(sp->facet_first_loc);
   cudaFree(sp->cell_extmask);
+  cudaFree(sp->coords4);
   delete sp;
   return 0;
 }
@@ -360,6 +361,7 @@ int sfem_pattern_destroy(sfem_pattern_t pat) {
   cudaFree(pat->ent_rowptr);
   cudaFree(pat->ent_cols);
   cudaFree(pat->pos);
+  cudaFree(pat->rec);
   delete pat;
   return 0;
 }

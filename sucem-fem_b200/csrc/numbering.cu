@@ -134,6 +134,14 @@ __global__ void k_cell_extmask(const int32_t* __restrict__ cell_facets, int nloc
   mask[c] = (uint8_t)m;
 }
 
+__global__ void k_pad_coords(const double* __restrict__ c3, double* __restrict__ c4, int64_t V) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= V * 4) return;
+  const int64_t v = i >> 2;
+  const int d = (int)(i & 3);
+  c4[i] = d < 3 ? c3[v * 3 + d] : 0.0;
+}
+
 __global__ void k_interior_incidence(int64_t* __restrict__ ptr, int32_t* __restrict__ inc_cell,
                                      uint8_t* __restrict__ inc_loc, int64_t base, int loc, int64_t C) {
   int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
@@ -308,6 +316,10 @@ int build_numbering(sfem_space_s* sp, cudaStream_t st) {
   } else if (q == 2) {
     k_interior_incidence<<<grid_for(C + 1), 256, 0, st>>>(sp->inc_ptr + sp->E, sp->inc_cell, sp->inc_loc,
                                                           inc_edges, 3, C);
+  }
+  if (d3) {
+    SFEM_CUDA(cudaMalloc(&sp->coords4, m->V * 32));
+    k_pad_coords<<<grid_for(m->V * 4), 256, 0, st>>>(m->coords, sp->coords4, m->V);
   }
   SFEM_CUDA(cudaGetLastError());
   SFEM_CUDA(cudaStreamSynchronize(st));

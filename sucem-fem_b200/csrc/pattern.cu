@@ -26,7 +26,7 @@ k_pattern(SpaceView sv, const int64_t* __restrict__ inc_ptr, const int32_t* __re
           const uint8_t* __restrict__ inc_loc, bool canon, int64_t ent_lo, int64_t n_rows, int64_t inc_base,
           int32_t* __restrict__ row_len,
           const int64_t* __restrict__ ent_rowptr, int32_t* __restrict__ ent_cols, uint16_t* __restrict__ pos,
-          int* __restrict__ overflow) {
+          uint8_t* __restrict__ rec, int* __restrict__ overflow) {
   __shared__ int32_t s_cand[kWarpsPerBlock][kCap];
   __shared__ int32_t s_sorted[kWarpsPerBlock][kCap];
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -74,11 +74,19 @@ k_pattern(SpaceView sv, const int64_t* __restrict__ inc_ptr, const int32_t* __re
   }
   const int64_t rp = ent_rowptr[r];
   for (int k = lane; k < nu; k += 32) ent_cols[rp + k] = cand[k];
+  if (rec)  // packed item records: bytes 0-3 cell, 4 local position t, 5-14 slots, 15 unused
+    for (int i = lane; i < (int)(i1 - i0); i += 32) {
+      uint8_t* q = rec + (i0 - inc_base + i) * 16;
+      *reinterpret_cast<int32_t*>(q) = inc_cell[i0 + i];
+      q[4] = inc_loc[i0 + i];
+      q[15] = 0;
+    }
   // slot of every (incidence, column entity) in the unique list.  Column entities are stored in the order the
   // value kernels visit them: for order-2 tets the CANONICAL order of the cell relabelled around the row entity
   // (u = umap[t][u'], generated/canonical_lut.inc), otherwise the cell-local order.
   for (int idx = lane; idx < L; idx += 32) {
     int i = idx / nec, u = idx - i * nec;
+    const int u_canon = u;
     if (canon) u = (int)((kCanonDesc[inc_loc[i0 + i]] >> (8 + 4 * u)) & 15ull);
     int32_t x = sv.ent(inc_cell[i0 + i], u);
     int lo = 0, hi = nu - 1;
@@ -87,6 +95,7 @@ k_pattern(SpaceView sv, const int64_t* __restrict__ inc_ptr, const int32_t* __re
       if (cand[mid] < x) lo = mid + 1; else hi = mid;
     }
     pos[(i0 - inc_base) * nec + idx] = (uint16_t)lo;
+    if (rec) rec[(i0 - inc_base + i) * 16 + 5 + u_canon] = (uint8_t)lo;
   }
 }
 
@@ -146,7 +155,7 @@ int build_pattern(sfem_pattern_s* pat, cudaStream_t st) {
   if (n > 0)
     k_pattern<false><<<grid, kWarpsPerBlock * 32, 0, st>>>(sv, sp->inc_ptr, sp->inc_cell, sp->inc_loc, canon, pat->ent_lo, n,
                                                            pat->inc_base, row_len, nullptr, nullptr, nullptr,
-                                                           overflow);
+                                                           nullptr, overflow);
   k_len_to_i64<<<grid_for(n + 1), 256, 0, st>>>(row_len, len64, n);
   size_t tb = 0;
   SFEM_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tb, len64, pat->ent_rowptr, (int)(n + 1), st));
@@ -179,10 +188,11 @@ int build_pattern(sfem_pattern_s* pat, cudaStream_t st) {
   pat->max_row_len = std::max(h_max2[0], h_max2[1]);
   SFEM_CUDA(cudaMalloc(&pat->ent_cols, std::max<int64_t>(pat->nnz_ent, 1) * 4));
   SFEM_CUDA(cudaMalloc(&pat->pos, std::max<int64_t>(pat->n_inc_block * sp->n_ent_cell, 1) * 2));
+  if (canon && pat->max_row_len <= 255) SFEM_CUDA(cudaMalloc(&pat->rec, std::max<int64_t>(pat->n_inc_block, 1) * 16));
   if (n > 0)
     k_pattern<true><<<grid, kWarpsPerBlock * 32, 0, st>>>(sv, sp->inc_ptr, sp->inc_cell, sp->inc_loc, canon, pat->ent_lo, n,
                                                           pat->inc_base, nullptr, pat->ent_rowptr, pat->ent_cols,
-                                                          pat->pos, overflow);
+                                                          pat->pos, reinterpret_cast<uint8_t*>(pat->rec), overflow);
   SFEM_CUDA(cudaGetLastError());
   SFEM_CUDA(cudaStreamSynchronize(st));
   cudaFree(overflow);

@@ -91,6 +91,7 @@ struct sfem_space_s {
   int32_t* facet_first_cell = nullptr;// [n_facets]
   uint8_t* facet_first_loc = nullptr; // [n_facets]
   uint8_t* cell_extmask = nullptr;    // [C] bit lf set <=> local facet lf is exterior
+  double* coords4 = nullptr;          // [V][4] 32-byte padded copy of the coordinates (3-D; vector gathers)
 };
 
 struct sfem_pattern_s {
@@ -103,6 +104,7 @@ struct sfem_pattern_s {
   int32_t* ent_cols = nullptr;    // [nnz_ent] global entity ids, ascending within a row
   uint16_t* pos = nullptr;        // [n_inc_block][n_ent_cell]: slot of the cell's u-th column entity in the row
                                   // (u in canonical order when pos_is_canonical(space))
+  uint4* rec = nullptr;           // [n_inc_block] packed {cell, t, 10 uint8 slots} (order-2 tets, rows <= 255 entities)
   int64_t inc_base = 0;           // = space->inc_ptr[ent_lo]
   int64_t n_inc_block = 0;
   int max_row_len = 0;            // longest entity row of the block

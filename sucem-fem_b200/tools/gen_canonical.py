@@ -91,19 +91,24 @@ def pack_descriptor(rowtype, t):
     return d, hi
 
 
-def emit_rows(name, table, rows):
-    """o[k*20 + j] = sum_p table[row_k][j][p] * g[p]"""
-    out = '__device__ __forceinline__ void %s(const double (&g)[6], double (&o)[40]) {\n' % name
+def emit_rows(name, table, row, coefs):
+    """o[j] = sum_p table[row][j][p] * g[p]; coefficients referenced from the __constant__ pool kCanonCoef so that
+    they become constant-bank operands of the DFMAs (literals would be materialised through UMOV pairs)."""
+    out = '__device__ __forceinline__ void %s(const double (&g)[6], double (&o)[20]) {\n' % name
     nterms = 0
-    for k, row in enumerate(rows):
-        for j in range(20):
-            terms = [(p, table[row, j, p]) for p in range(6) if table[row, j, p] != 0.0]
-            nterms += len(terms)
-            if not terms:
-                out += '  o[%d] = 0.0;\n' % (k * 20 + j)
-                continue
-            expr = ' + '.join('%s * g[%d]' % (repr(float(c)), p) for p, c in terms)
-            out += '  o[%d] = %s;\n' % (k * 20 + j, expr)
+    for j in range(20):
+        terms = [(p, table[row, j, p]) for p in range(6) if table[row, j, p] != 0.0]
+        nterms += len(terms)
+        if not terms:
+            out += '  o[%d] = 0.0;\n' % j
+            continue
+        parts = []
+        for p, c in terms:
+            c = float(c)
+            if c not in coefs:
+                coefs[c] = len(coefs)
+            parts.append('kCanonCoef[%d] * g[%d]' % (coefs[c], p))
+        out += '  o[%d] = %s;\n' % (j, ' + '.join(parts))
     out += '}\n'
     return out, nterms
 
@@ -112,11 +117,16 @@ def main():
     mass, curl = load_table('kMassTet2'), load_table('kCurlTet2')
     src = '// GENERATED by tools/gen_canonical.py -- do not edit.\n'
     stats = {}
+    coefs, body = {}, ''
     for nm, tab in (('mass', mass), ('curl', curl)):
         for rt, rows in (('edge', (10, 11)), ('face', (18, 19))):
-            code, n = emit_rows('canon_%s_%s' % (rt, nm), tab, rows)
-            src += code
-            stats['%s_%s' % (rt, nm)] = n
+            for k, row in enumerate(rows):
+                code, n = emit_rows('canon_%s_%s_k%d' % (rt, nm, k), tab, row, coefs)
+                body += code
+                stats['%s_%s_k%d' % (rt, nm, k)] = n
+    pool = sorted(coefs, key=coefs.get)
+    src += '__constant__ double kCanonCoef[%d] = {%s};\n' % (len(pool), ', '.join(repr(c) for c in pool))
+    src += body
     with open(os.path.join(GEN, 'canonical_rows.inc'), 'w') as f:
         f.write(src)
     # descriptors, indexed by the true local entity t of the row entity in its cell (0-5 edges, 6-9 faces):
