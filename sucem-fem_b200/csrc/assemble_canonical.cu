@@ -14,8 +14,10 @@
 //   * contributions are staged in a per-warp shared-memory tile that is the warp's output span in its FINAL
 //     layout; the span leaves the SM as ONE bulk asynchronous copy (cp.async.bulk shared -> global, the TMA
 //     engine), so global stores cost no LSU wavefronts and are perfectly coalesced.  Faces (<= 2 cells; the 4
-//     shared entities are summed in registers) only store into the tile; edges accumulate over their cells in
-//     ascending order (read-modify-write, loads of an item batched ahead of its adds).
+//     shared entities are summed in registers) only store into the tile.  Edges visit their cells in RING order
+//     (consecutive cells share a face through the edge; order precomputed in pattern.cu), carry the three column
+//     entities two neighbouring cells have in common in registers and therefore also store every slot exactly once
+//     (the one exception: where a closed ring closes, three chunks per row are added to the first cell's).
 //   * gathers are the other LSU consumer: one 16-byte record, one 16-byte vertex quadruple, four 32-byte padded
 //     coordinates and one coefficient per (entity, cell); for edges the three dependent hops are software-pipelined
 //     three items deep because the tile limits residency to a few warps per SM.
@@ -176,9 +178,9 @@ __device__ __forceinline__ void pec_overwrite(const CanonArgs& p, double2* __res
 }
 
 __device__ __forceinline__ void stage_lut(unsigned long long* s_desc, unsigned* s_fsel) {
-  if (threadIdx.x < 10) {
-    s_desc[threadIdx.x] = kCanonDesc[threadIdx.x];
-    s_fsel[threadIdx.x] = kCanonFaceSel[threadIdx.x];
+  if (threadIdx.x < 16) {
+    s_desc[threadIdx.x] = kRingDesc[threadIdx.x];
+    s_fsel[threadIdx.x] = kRingFaceSel[threadIdx.x];
   }
   __syncthreads();
 }
@@ -186,43 +188,65 @@ __device__ __forceinline__ void stage_lut(unsigned long long* s_desc, unsigned* 
 constexpr int kThreadsEdges = 64;
 constexpr int kThreadsFaces = 128;
 
-// ---- edges -------------------------------------------------------------------------------------------------------
+// ---- edges: cells visited in ring order, every slot stored exactly once ------------------------------------------
+// Relabelled cell = (a, b, entry, exit).  Canonical column entities by role:
+//   self   5 = (0,1)                         accumulated in registers over all cells, stored at the end
+//   prev   4 = (0,2), 2 = (1,2), 9 = (0,1,2)  shared with the previous cell of the ring: carry + own, then stored
+//   own    0 = (2,3), 7 = (0,2,3), 6 = (1,2,3) this cell only: stored
+//   next   3 = (0,3), 1 = (1,3), 8 = (0,1,3)  shared with the next cell: kept as the carry; stored if the fan ends
+//                                              here, added to the first cell's slots if the ring closes here
+struct RingState {
+  double2 carry[2][3];
+  double2 self[2];
+};
+
 template <bool MASS>
-__device__ __forceinline__ void edge_item(const Item& it, double2* __restrict__ row0, int len) {
+__device__ __forceinline__ void edge_item(const Item& it, double2* __restrict__ row0, int len, RingState& st) {
   double gm[6], o[20];
   canon_geometry<MASS>(it, gm);
-  double2* q[10];
-  q[0] = row0 + slot_of<0>(it); q[1] = row0 + slot_of<1>(it); q[2] = row0 + slot_of<2>(it);
-  q[3] = row0 + slot_of<3>(it); q[4] = row0 + slot_of<4>(it); q[5] = row0 + slot_of<5>(it);
-  q[6] = row0 + slot_of<6>(it); q[7] = row0 + slot_of<7>(it); q[8] = row0 + slot_of<8>(it);
-  q[9] = row0 + slot_of<9>(it);
-  // the 10 column entities of a cell are distinct slots: load the whole row's targets before any is written back
-#define SFEM_EDGE_ROW(K, FN)                                                                \
-  {                                                                                         \
-    double2 acc[10];                                                                        \
-    _Pragma("unroll") for (int u = 0; u < 10; ++u) acc[u] = q[u][K * len];                  \
-    FN(gm, o);                                                                              \
-    double2 r;                                                                              \
-    r = fix_columns<0>(it, o[0], o[1]);   acc[0].x += r.x; acc[0].y += r.y;                 \
-    r = fix_columns<1>(it, o[2], o[3]);   acc[1].x += r.x; acc[1].y += r.y;                 \
-    r = fix_columns<2>(it, o[4], o[5]);   acc[2].x += r.x; acc[2].y += r.y;                 \
-    r = fix_columns<3>(it, o[6], o[7]);   acc[3].x += r.x; acc[3].y += r.y;                 \
-    r = fix_columns<4>(it, o[8], o[9]);   acc[4].x += r.x; acc[4].y += r.y;                 \
-    r = fix_columns<5>(it, o[10], o[11]); acc[5].x += r.x; acc[5].y += r.y;                 \
-    r = fix_columns<6>(it, o[12], o[13]); acc[6].x += r.x; acc[6].y += r.y;                 \
-    r = fix_columns<7>(it, o[14], o[15]); acc[7].x += r.x; acc[7].y += r.y;                 \
-    r = fix_columns<8>(it, o[16], o[17]); acc[8].x += r.x; acc[8].y += r.y;                 \
-    r = fix_columns<9>(it, o[18], o[19]); acc[9].x += r.x; acc[9].y += r.y;                 \
-    _Pragma("unroll") for (int u = 0; u < 10; ++u) q[u][K * len] = acc[u];                  \
+  const unsigned flags = it.s2 >> 24;
+  const bool has_prev = flags & 1u, has_next = flags & 2u, wrap = flags & 4u;
+#define SFEM_RING_ROW(K, FN)                                                                       \
+  {                                                                                                \
+    FN(gm, o);                                                                                     \
+    double2* row = row0 + K * len;                                                                 \
+    double2 r;                                                                                     \
+    r = fix_columns<5>(it, o[10], o[11]); st.self[K].x += r.x; st.self[K].y += r.y;                \
+    r = fix_columns<4>(it, o[8], o[9]);                                                            \
+    if (has_prev) { r.x += st.carry[K][0].x; r.y += st.carry[K][0].y; }                            \
+    row[slot_of<4>(it)] = r;                                                                       \
+    r = fix_columns<2>(it, o[4], o[5]);                                                            \
+    if (has_prev) { r.x += st.carry[K][1].x; r.y += st.carry[K][1].y; }                            \
+    row[slot_of<2>(it)] = r;                                                                       \
+    r = fix_columns<9>(it, o[18], o[19]);                                                          \
+    if (has_prev) { r.x += st.carry[K][2].x; r.y += st.carry[K][2].y; }                            \
+    row[slot_of<9>(it)] = r;                                                                       \
+    row[slot_of<0>(it)] = fix_columns<0>(it, o[0], o[1]);                                          \
+    row[slot_of<7>(it)] = fix_columns<7>(it, o[14], o[15]);                                        \
+    row[slot_of<6>(it)] = fix_columns<6>(it, o[12], o[13]);                                        \
+    st.carry[K][0] = fix_columns<3>(it, o[6], o[7]);                                               \
+    st.carry[K][1] = fix_columns<1>(it, o[2], o[3]);                                               \
+    st.carry[K][2] = fix_columns<8>(it, o[16], o[17]);                                             \
+    if (!has_next) {                                                                               \
+      double2* q3 = row + slot_of<3>(it);                                                          \
+      double2* q1 = row + slot_of<1>(it);                                                          \
+      double2* q8 = row + slot_of<8>(it);                                                          \
+      double2 c3 = st.carry[K][0], c1 = st.carry[K][1], c8 = st.carry[K][2];                       \
+      if (wrap) {                                                                                  \
+        const double2 t3 = *q3, t1 = *q1, t8 = *q8;                                                \
+        c3.x += t3.x; c3.y += t3.y; c1.x += t1.x; c1.y += t1.y; c8.x += t8.x; c8.y += t8.y;        \
+      }                                                                                            \
+      *q3 = c3; *q1 = c1; *q8 = c8;                                                                \
+    }                                                                                              \
   }
   if (MASS) {
-    SFEM_EDGE_ROW(0, canon_edge_mass_k0)
-    SFEM_EDGE_ROW(1, canon_edge_mass_k1)
+    SFEM_RING_ROW(0, canon_edge_mass_k0)
+    SFEM_RING_ROW(1, canon_edge_mass_k1)
   } else {
-    SFEM_EDGE_ROW(0, canon_edge_curl_k0)
-    SFEM_EDGE_ROW(1, canon_edge_curl_k1)
+    SFEM_RING_ROW(0, canon_edge_curl_k0)
+    SFEM_RING_ROW(1, canon_edge_curl_k1)
   }
-#undef SFEM_EDGE_ROW
+#undef SFEM_RING_ROW
 }
 
 // The gather chain of an item is three dependent global loads (record -> cell vertices -> coordinates).  With only
@@ -252,12 +276,17 @@ __device__ __forceinline__ void edge_pass(const CanonArgs& p, const unsigned lon
     }
     gather_coords(p, s_desc, s_fsel, rc0, cv0, cf0, bufA);
   }
-  // the previous pass's bulk store must have finished reading the tile before it is cleared
+  // the previous pass's bulk store must have finished reading the tile before it is overwritten
   tile_store_wait(lane);
-  for (int j = lane; j < span; j += 32) tile[j] = make_double2(0.0, 0.0);
-  __syncwarp();
   double2* row0 = tile + off;
   if (valid) {
+    RingState st;
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      st.self[k] = make_double2(0.0, 0.0);
+#pragma unroll
+      for (int j = 0; j < 3; ++j) st.carry[k][j] = make_double2(0.0, 0.0);
+    }
     // STEP: hop 1 of item I+3, hop 2 of item I+2, hop 3 of item I+1 (into NXT), then consume item I (CUR)
 #define SFEM_EDGE_STEP(CUR, NXT, I)                                                                       \
     {                                                                                                     \
@@ -270,7 +299,7 @@ __device__ __forceinline__ void edge_pass(const CanonArgs& p, const unsigned lon
         cf2 = coefs ? coefs[(int)rc2.x] : 1.0;                                                            \
       }                                                                                                   \
       if ((I) + 1 < i1) gather_coords(p, s_desc, s_fsel, rc1, cv1, cf1, NXT);                             \
-      edge_item<MASS>(CUR, row0, len);                                                                    \
+      edge_item<MASS>(CUR, row0, len, st);                                                                \
       rc1 = rc2; rc2 = rc3; cv1 = cv2; cf1 = cf2;                                                         \
     }
     const int self = slot_of<5>(bufA);  // canonical entity 5 = the row edge itself
@@ -280,6 +309,8 @@ __device__ __forceinline__ void edge_pass(const CanonArgs& p, const unsigned lon
       if (i + 1 < i1) SFEM_EDGE_STEP(bufB, bufA, i + 1)
     }
 #undef SFEM_EDGE_STEP
+    row0[self] = st.self[0];
+    row0[len + self] = st.self[1];
     if (p.pec) pec_overwrite(p, row0, g, len, self);
   }
   tile_store_issue(tile, out_first, (unsigned)span * 16u, lane);
@@ -287,8 +318,8 @@ __device__ __forceinline__ void edge_pass(const CanonArgs& p, const unsigned lon
 
 __global__ void __launch_bounds__(kThreadsEdges) k_canon_edges(CanonArgs p) {
   extern __shared__ double2 smem[];
-  __shared__ unsigned long long s_desc[10];
-  __shared__ unsigned s_fsel[10];
+  __shared__ unsigned long long s_desc[16];
+  __shared__ unsigned s_fsel[16];
   stage_lut(s_desc, s_fsel);
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   double2* tile = smem + (size_t)w * p.tile_chunks;
@@ -364,8 +395,8 @@ __device__ __forceinline__ void face_pass(const CanonArgs& p, double2* __restric
 
 __global__ void __launch_bounds__(kThreadsFaces, 3) k_canon_faces(CanonArgs p) {
   extern __shared__ double2 smem[];
-  __shared__ unsigned long long s_desc[10];
-  __shared__ unsigned s_fsel[10];
+  __shared__ unsigned long long s_desc[16];
+  __shared__ unsigned s_fsel[16];
   stage_lut(s_desc, s_fsel);
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   double2* tile = smem + (size_t)w * p.tile_chunks;
@@ -410,7 +441,7 @@ __global__ void __launch_bounds__(kThreadsFaces, 3) k_canon_faces(CanonArgs p) {
 }  // namespace
 
 bool canonical_supported(const sfem_pattern_s* pat) {
-  return pat->space->mesh->gdim == 3 && pat->space->order == 2 && pat->rec != nullptr;
+  return pat->space->mesh->gdim == 3 && pat->space->order == 2 && pat->rec != nullptr && pat->ring_ok;
 }
 
 int canonical_launches(const sfem_pattern_s* pat) {

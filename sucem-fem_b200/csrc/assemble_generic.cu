@@ -22,28 +22,28 @@ template <int DIM, int ORDER>
 struct Elem;
 template <>
 struct Elem<3, 1> {
-  static constexpr int N = 6, NP = 6;
+  static constexpr int NP = 6;
   __device__ static const double* mass(int i, int j) { return kMassTet1[i][j]; }
   __device__ static const double* curl(int i, int j) { return kCurlTet1[i][j]; }
   __device__ static const double* facet(int f, int i, int j) { return kFacetTet1[f][i][j]; }
 };
 template <>
 struct Elem<3, 2> {
-  static constexpr int N = 20, NP = 6;
+  static constexpr int NP = 6;
   __device__ static const double* mass(int i, int j) { return kMassTet2[i][j]; }
   __device__ static const double* curl(int i, int j) { return kCurlTet2[i][j]; }
   __device__ static const double* facet(int f, int i, int j) { return kFacetTet2[f][i][j]; }
 };
 template <>
 struct Elem<2, 1> {
-  static constexpr int N = 3, NP = 3;
+  static constexpr int NP = 3;
   __device__ static const double* mass(int i, int j) { return kMassTri1[i][j]; }
   __device__ static const double* curl(int i, int j) { return &kCurlTri1[i][j]; }
   __device__ static const double* facet(int f, int i, int j) { return kFacetTri1[f][i][j]; }
 };
 template <>
 struct Elem<2, 2> {
-  static constexpr int N = 8, NP = 3;
+  static constexpr int NP = 3;
   __device__ static const double* mass(int i, int j) { return kMassTri2[i][j]; }
   __device__ static const double* curl(int i, int j) { return &kCurlTri2[i][j]; }
   __device__ static const double* facet(int f, int i, int j) { return kFacetTri2[f][i][j]; }

@@ -74,11 +74,14 @@ k_pattern(SpaceView sv, const int64_t* __restrict__ inc_ptr, const int32_t* __re
   }
   const int64_t rp = ent_rowptr[r];
   for (int k = lane; k < nu; k += 32) ent_cols[rp + k] = cand[k];
-  if (rec)  // packed item records: bytes 0-3 cell, 4 local position t, 5-14 slots, 15 unused
+  // packed item records (order-2 tets): bytes 0-3 cell, 4 descriptor index into kRingDesc, 5-14 slots, 15 flags.
+  // Face rows are written here (descriptor 12 + local face); edge rows by k_edge_ring in ring order.
+  const bool rec_here = rec && g >= sv.E;
+  if (rec_here)
     for (int i = lane; i < (int)(i1 - i0); i += 32) {
       uint8_t* q = rec + (i0 - inc_base + i) * 16;
       *reinterpret_cast<int32_t*>(q) = inc_cell[i0 + i];
-      q[4] = inc_loc[i0 + i];
+      q[4] = (uint8_t)(inc_loc[i0 + i] + 6);
       q[15] = 0;
     }
   // slot of every (incidence, column entity) in the unique list.  Column entities are stored in the order the
@@ -95,7 +98,103 @@ k_pattern(SpaceView sv, const int64_t* __restrict__ inc_ptr, const int32_t* __re
       if (cand[mid] < x) lo = mid + 1; else hi = mid;
     }
     pos[(i0 - inc_base) * nec + idx] = (uint16_t)lo;
-    if (rec) rec[(i0 - inc_base + i) * 16 + 5 + u_canon] = (uint8_t)lo;
+    if (rec_here) rec[(i0 - inc_base + i) * 16 + 5 + u_canon] = (uint8_t)lo;
+  }
+}
+
+
+// Edge rows of order-2 tets: the cells around an edge are re-ordered into RING order (consecutive cells share a
+// face containing the edge), so that the value kernel can carry the contributions two neighbouring cells make to
+// their three common column entities in registers and store every CSR slot exactly once.  One thread per edge.
+// Output: packed records in ring order.  Record byte 4 = 2*t + swap (descriptor index, see canonical_lut.inc: the
+// cell is relabelled (a, b, entry, exit)), byte 15 = flags: 1 has_prev (shares its entry face with the previous
+// record), 2 has_next, 4 wrap (last cell of a closed ring: its exit face is the first cell's entry face).
+constexpr int kMaxRing = 64;
+__global__ void k_edge_ring(SpaceView sv, const int32_t* __restrict__ cells, const int64_t* __restrict__ inc_ptr,
+                            const int32_t* __restrict__ inc_cell, const uint8_t* __restrict__ inc_loc, int64_t ent_lo,
+                            int64_t n_edge_rows, int64_t inc_base, const int64_t* __restrict__ ent_rowptr,
+                            const int32_t* __restrict__ ent_cols, uint8_t* __restrict__ rec, int* __restrict__ bad) {
+  const int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (r >= n_edge_rows) return;
+  const int64_t g = ent_lo + r;
+  const int64_t i0 = inc_ptr[g];
+  const int m = (int)(inc_ptr[g + 1] - i0);
+  if (m > kMaxRing) {
+    atomicMax(bad, 1);
+    return;
+  }
+  int32_t X[kMaxRing], Y[kMaxRing];
+  for (int j = 0; j < m; ++j) {
+    const int64_t c = inc_cell[i0 + j];
+    const int t = inc_loc[i0 + j];
+    const int e0 = tet_edge_vertex(t, 0), e1 = tet_edge_vertex(t, 1);
+    int o0 = -1, o1 = -1;
+    for (int v = 0; v < 4; ++v)
+      if (v != e0 && v != e1) {
+        if (o0 < 0) o0 = v; else o1 = v;
+      }
+    X[j] = cells[c * 4 + o0];
+    Y[j] = cells[c * 4 + o1];
+  }
+  auto degree = [&](int32_t v) {
+    int d = 0;
+    for (int j = 0; j < m; ++j) d += (X[j] == v) + (Y[j] == v);
+    return d;
+  };
+  for (int j = 0; j < m; ++j)
+    if (degree(X[j]) > 2 || degree(Y[j]) > 2) {
+      atomicMax(bad, 2);  // a face shared by more than two cells
+      return;
+    }
+  const int64_t a = ent_rowptr[r];
+  const int len = (int)(ent_rowptr[r + 1] - a);
+  unsigned long long visited = 0ull;
+  int pos = 0;
+  while (pos < m) {
+    // start of a chain: the lowest unvisited cell that has an open side (fan end); none -> closed ring
+    int start = -1;
+    int32_t entry = 0;
+    for (int j = 0; j < m && start < 0; ++j) {
+      if ((visited >> j) & 1ull) continue;
+      if (degree(X[j]) == 1) { start = j; entry = X[j]; }
+      else if (degree(Y[j]) == 1) { start = j; entry = Y[j]; }
+    }
+    const bool closed = start < 0;
+    if (closed)
+      for (int j = 0; j < m; ++j)
+        if (!((visited >> j) & 1ull)) { start = j; entry = X[j]; break; }
+    const int first_pos = pos;
+    int cur = start;
+    while (true) {
+      const int32_t exitv = entry == X[cur] ? Y[cur] : X[cur];
+      const int swap = entry == Y[cur];
+      visited |= 1ull << cur;
+      int nxt = -1;
+      for (int j = 0; j < m; ++j)
+        if (!((visited >> j) & 1ull) && (X[j] == exitv || Y[j] == exitv)) { nxt = j; break; }
+      unsigned flags = (pos > first_pos ? 1u : 0u) | (nxt >= 0 ? 2u : 0u) | (nxt < 0 && closed && pos > first_pos ? 4u : 0u);
+      // record
+      const int64_t c = inc_cell[i0 + cur];
+      const int t = inc_loc[i0 + cur];
+      const unsigned long long desc = kRingDesc[2 * t + swap];
+      uint8_t* q = rec + (i0 - inc_base + pos) * 16;
+      *reinterpret_cast<int32_t*>(q) = (int32_t)c;
+      q[4] = (uint8_t)(2 * t + swap);
+      for (int u = 0; u < 10; ++u) {
+        const int32_t x = sv.ent(c, (int)((desc >> (8 + 4 * u)) & 15ull));
+        int lo = 0, hi = len - 1;
+        while (lo < hi) {
+          const int mid = (lo + hi) >> 1;
+          if (ent_cols[a + mid] < x) lo = mid + 1; else hi = mid;
+        }
+        q[5 + u] = (uint8_t)lo;
+      }
+      q[15] = (uint8_t)flags;
+      ++pos;
+      if (nxt < 0) break;
+      entry = exitv;
+      cur = nxt;
+    }
   }
 }
 
@@ -193,6 +292,19 @@ int build_pattern(sfem_pattern_s* pat, cudaStream_t st) {
     k_pattern<true><<<grid, kWarpsPerBlock * 32, 0, st>>>(sv, sp->inc_ptr, sp->inc_cell, sp->inc_loc, canon, pat->ent_lo, n,
                                                           pat->inc_base, nullptr, pat->ent_rowptr, pat->ent_cols,
                                                           pat->pos, reinterpret_cast<uint8_t*>(pat->rec), overflow);
+  pat->ring_ok = false;
+  if (pat->rec && n_edge_rows > 0) {
+    SFEM_CUDA(cudaMemsetAsync(overflow, 0, 4, st));
+    k_edge_ring<<<grid_for(n_edge_rows, 128), 128, 0, st>>>(sv, sp->mesh->cells, sp->inc_ptr, sp->inc_cell, sp->inc_loc,
+                                                            pat->ent_lo, n_edge_rows, pat->inc_base, pat->ent_rowptr,
+                                                            pat->ent_cols, reinterpret_cast<uint8_t*>(pat->rec), overflow);
+    int h_bad = 0;
+    SFEM_CUDA(cudaMemcpyAsync(&h_bad, overflow, 4, cudaMemcpyDeviceToHost, st));
+    SFEM_CUDA(cudaStreamSynchronize(st));
+    pat->ring_ok = h_bad == 0;
+  } else if (pat->rec) {
+    pat->ring_ok = true;
+  }
   SFEM_CUDA(cudaGetLastError());
   SFEM_CUDA(cudaStreamSynchronize(st));
   cudaFree(overflow);

@@ -105,6 +105,7 @@ struct sfem_pattern_s {
   uint16_t* pos = nullptr;        // [n_inc_block][n_ent_cell]: slot of the cell's u-th column entity in the row
                                   // (u in canonical order when pos_is_canonical(space))
   uint4* rec = nullptr;           // [n_inc_block] packed {cell, t, 10 uint8 slots} (order-2 tets, rows <= 255 entities)
+  bool ring_ok = false;           // edge records are in ring order (manifold edges of bounded valence)
   int64_t inc_base = 0;           // = space->inc_ptr[ent_lo]
   int64_t n_inc_block = 0;
   int max_row_len = 0;            // longest entity row of the block

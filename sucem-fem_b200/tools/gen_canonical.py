@@ -37,7 +37,7 @@ def load_table(name):
     return np.array(vals).reshape(dims)
 
 
-def relabel_lut(rowtype, t):
+def relabel_lut(rowtype, t, swap=0):
     """sigma (relabelled vertex -> true local vertex), umap (canonical entity -> true local entity),
     Q (2x2 per canonical entity: phi_true = Q phi_canonical)."""
     eidx = {frozenset(e): i for i, e in enumerate(TET_EDGES)}
@@ -45,7 +45,7 @@ def relabel_lut(rowtype, t):
     if rowtype == 'edge':
         i = TET_EDGES[t]
         others = [v for v in range(4) if v not in i]
-        sigma = [i[0], i[1], others[0], others[1]]
+        sigma = [i[0], i[1], others[swap], others[1 - swap]]
     else:
         f = TET_FACES[t]
         sigma = [f[0], f[1], f[2], t]
@@ -70,10 +70,10 @@ def relabel_lut(rowtype, t):
 SEL = {(1, 0): 0, (0, 1): 1, (-1, -1): 2}
 
 
-def pack_descriptor(rowtype, t):
+def pack_descriptor(rowtype, t, swap=0):
     """64-bit descriptor: bits 0-7 sigma (2 bits each), 8-47 umap (4 bits each), 48-53 edge flips,
     54-61 (or up to 63) face selectors: per canonical face f: 2 bits out0, 2 bits out1 -> 16 bits starting at 48+6."""
-    sigma, umap, Q = relabel_lut(rowtype, t)
+    sigma, umap, Q = relabel_lut(rowtype, t, swap)
     d = 0
     for i, s in enumerate(sigma):
         d |= s << (2 * i)
@@ -129,12 +129,20 @@ def main():
     src += body
     with open(os.path.join(GEN, 'canonical_rows.inc'), 'w') as f:
         f.write(src)
-    # descriptors, indexed by the true local entity t of the row entity in its cell (0-5 edges, 6-9 faces):
-    # low 64 bits (sigma, umap, edge flips), separate 16 bits of face selectors
+    # descriptors: low 64 bits (sigma, umap, edge flips), separate 16 bits of face selectors.
+    #   kCanonDesc[t], t = 0..9: true local entity of the row entity in its cell (0-5 edges, 6-9 faces); the cell's
+    #     other vertices follow in ascending order.
+    #   kRingDesc[2 t + swap], t = 0..5, and [12 + f], f = 0..3: edge rows visited in RING order around the edge:
+    #     relabelled vertices (a, b, entry, exit) with (entry, exit) = the cell's two other vertices in ascending
+    #     (swap = 0) or descending (swap = 1) local order; face rows as above.
     lut = '// GENERATED by tools/gen_canonical.py -- do not edit.\n'
     lo, hi = zip(*([pack_descriptor('edge', t) for t in range(6)] + [pack_descriptor('face', t) for t in range(4)]))
     lut += 'SFEM_TABLE unsigned long long kCanonDesc[10] = {%s};\n' % ', '.join('0x%xull' % x for x in lo)
     lut += 'SFEM_TABLE unsigned int kCanonFaceSel[10] = {%s};\n' % ', '.join('0x%xu' % x for x in hi)
+    lo, hi = zip(*([pack_descriptor('edge', t, sw) for t in range(6) for sw in range(2)] +
+                   [pack_descriptor('face', t) for t in range(4)]))
+    lut += 'SFEM_TABLE unsigned long long kRingDesc[16] = {%s};\n' % ', '.join('0x%xull' % x for x in lo)
+    lut += 'SFEM_TABLE unsigned int kRingFaceSel[16] = {%s};\n' % ', '.join('0x%xu' % x for x in hi)
     with open(os.path.join(GEN, 'canonical_lut.inc'), 'w') as f:
         f.write(lut)
     sys.stderr.write('multiply-add terms: %r\n' % stats)
