@@ -3,8 +3,9 @@
 // /root/reference/sucemfem/SystemMatrices.py:54-55 for the forms of /root/reference/sucemfem/Forms.py:76,84.
 //
 // Work decomposition (row-owner gather, no atomics, bit-reproducible):
-//   * one THREAD owns one row entity (edge or face) = 2 CSR rows of S and 2 of T; a warp owns 32 consecutive
-//     entities, i.e. one contiguous span of the value arrays.
+//   * a PAIR of lanes owns one row entity (edge or face) = 2 CSR rows of S and 2 of T, and splits the entity's
+//     incident cells between its two lanes; a warp owns 16 consecutive entities, i.e. one contiguous span of the
+//     value arrays.
 //   * for every incident cell the thread relabels the cell's vertices so that its entity sits at the canonical
 //     position (edge (v0,v1) / face (v0,v1,v2)).  The two element-matrix rows are then straight-line DFMAs whose
 //     reference-tensor coefficients are constant-bank operands (generated/canonical_rows.inc), identical for all
@@ -48,7 +49,7 @@ struct CanonArgs {
   int64_t r_begin;   // first block-relative row entity handled by this launch
   int64_t r_end;
   int64_t inc_base;
-  int tile_chunks;   // 16-byte chunks per warp tile = 32 * 2 * (longest entity row in this launch)
+  int tile_chunks;   // 16-byte chunks per warp tile = 16 entities * 2 rows * (longest entity row in this launch)
 };
 
 // per-(entity, cell) inputs
@@ -185,145 +186,147 @@ __device__ __forceinline__ void stage_lut(unsigned long long* s_desc, unsigned* 
   __syncthreads();
 }
 
-constexpr int kThreadsEdges = 64;
-constexpr int kThreadsFaces = 128;
+constexpr int kThreadsEdges = 128;  // 4 warps x 16 edges; CTAs per SM are bounded by the shared-memory tiles
+constexpr int kThreadsFaces = 128;  // 4 warps x 16 faces
 
-// ---- edges: cells visited in ring order, every slot stored exactly once ------------------------------------------
-// Relabelled cell = (a, b, entry, exit).  Canonical column entities by role:
-//   self   5 = (0,1)                         accumulated in registers over all cells, stored at the end
-//   prev   4 = (0,2), 2 = (1,2), 9 = (0,1,2)  shared with the previous cell of the ring: carry + own, then stored
-//   own    0 = (2,3), 7 = (0,2,3), 6 = (1,2,3) this cell only: stored
-//   next   3 = (0,3), 1 = (1,3), 8 = (0,1,3)  shared with the next cell: kept as the carry; stored if the fan ends
-//                                              here, added to the first cell's slots if the ring closes here
-struct RingState {
-  double2 carry[2][3];
-  double2 self[2];
-};
-
-template <bool MASS>
-__device__ __forceinline__ void edge_item(const Item& it, double2* __restrict__ row0, int len, RingState& st) {
-  double gm[6], o[20];
-  canon_geometry<MASS>(it, gm);
-  const unsigned flags = it.s2 >> 24;
-  const bool has_prev = flags & 1u, has_next = flags & 2u, wrap = flags & 4u;
-#define SFEM_RING_ROW(K, FN)                                                                       \
-  {                                                                                                \
-    FN(gm, o);                                                                                     \
-    double2* row = row0 + K * len;                                                                 \
-    double2 r;                                                                                     \
-    r = fix_columns<5>(it, o[10], o[11]); st.self[K].x += r.x; st.self[K].y += r.y;                \
-    r = fix_columns<4>(it, o[8], o[9]);                                                            \
-    if (has_prev) { r.x += st.carry[K][0].x; r.y += st.carry[K][0].y; }                            \
-    row[slot_of<4>(it)] = r;                                                                       \
-    r = fix_columns<2>(it, o[4], o[5]);                                                            \
-    if (has_prev) { r.x += st.carry[K][1].x; r.y += st.carry[K][1].y; }                            \
-    row[slot_of<2>(it)] = r;                                                                       \
-    r = fix_columns<9>(it, o[18], o[19]);                                                          \
-    if (has_prev) { r.x += st.carry[K][2].x; r.y += st.carry[K][2].y; }                            \
-    row[slot_of<9>(it)] = r;                                                                       \
-    row[slot_of<0>(it)] = fix_columns<0>(it, o[0], o[1]);                                          \
-    row[slot_of<7>(it)] = fix_columns<7>(it, o[14], o[15]);                                        \
-    row[slot_of<6>(it)] = fix_columns<6>(it, o[12], o[13]);                                        \
-    st.carry[K][0] = fix_columns<3>(it, o[6], o[7]);                                               \
-    st.carry[K][1] = fix_columns<1>(it, o[2], o[3]);                                               \
-    st.carry[K][2] = fix_columns<8>(it, o[16], o[17]);                                             \
-    if (!has_next) {                                                                               \
-      double2* q3 = row + slot_of<3>(it);                                                          \
-      double2* q1 = row + slot_of<1>(it);                                                          \
-      double2* q8 = row + slot_of<8>(it);                                                          \
-      double2 c3 = st.carry[K][0], c1 = st.carry[K][1], c8 = st.carry[K][2];                       \
-      if (wrap) {                                                                                  \
-        const double2 t3 = *q3, t1 = *q1, t8 = *q8;                                                \
-        c3.x += t3.x; c3.y += t3.y; c1.x += t1.x; c1.y += t1.y; c8.x += t8.x; c8.y += t8.y;        \
-      }                                                                                            \
-      *q3 = c3; *q1 = c1; *q8 = c8;                                                                \
-    }                                                                                              \
-  }
-  if (MASS) {
-    SFEM_RING_ROW(0, canon_edge_mass_k0)
-    SFEM_RING_ROW(1, canon_edge_mass_k1)
-  } else {
-    SFEM_RING_ROW(0, canon_edge_curl_k0)
-    SFEM_RING_ROW(1, canon_edge_curl_k1)
-  }
-#undef SFEM_RING_ROW
+__device__ __forceinline__ double2 shfl_xor1(double2 v) {
+  return make_double2(__shfl_xor_sync(0xffffffffu, v.x, 1), __shfl_xor_sync(0xffffffffu, v.y, 1));
 }
 
-// The gather chain of an item is three dependent global loads (record -> cell vertices -> coordinates).  With only
-// a few resident warps (the tile bounds occupancy) it is hidden by issuing the hops three, two and one items ahead
-// of the item being computed; the two Item buffers ping-pong.
+// ---- edges: a PAIR of lanes per edge; cells visited in ring order, every slot stored exactly once ---------------
+// The two lanes of a pair take alternate cells of the ring (lane h: cells h, h+2, ...), so an edge's dependent
+// chain of cells is half as long and a warp's tile covers 16 edges: twice the resident warps for the same shared
+// memory, no redundant work.  Relabelled cell = (a, b, entry, exit).  Canonical column entities by role:
+//   self   5 = (0,1)                          partial sums per lane, combined and stored at the end
+//   prev   4 = (0,2), 2 = (1,2), 9 = (0,1,2)   shared with the previous cell of the ring: carry + own, then stored
+//   own    0 = (2,3), 7 = (0,2,3), 6 = (1,2,3)  this cell only: stored
+//   next   3 = (0,3), 1 = (1,3), 8 = (0,1,3)   shared with the next cell, which the PARTNER lane is working on:
+//                                               handed over by shuffle; stored if the fan ends here, added to the
+//                                               first cell's slots if the ring closes here
 template <bool MASS>
 __device__ __forceinline__ void edge_pass(const CanonArgs& p, const unsigned long long* __restrict__ s_desc,
                                           const unsigned* __restrict__ s_fsel, double2* __restrict__ tile, int lane,
                                           bool valid, int64_t g, int len, int off, int span, int64_t i0, int64_t i1,
-                                          double* __restrict__ out_first) {
+                                          int nsteps, double* __restrict__ out_first) {
+  const int h = lane & 1;
   const double* __restrict__ coefs = MASS ? p.eps : p.mu;
   const uint4* __restrict__ rec = p.rec - p.inc_base;
-  // prologue of the chain (independent of the tile): records of items 0..2, vertices of items 0..1
-  uint4 rc0 = make_uint4(0, 0, 0, 0), rc1 = rc0, rc2 = rc0;
-  int4 cv1 = make_int4(0, 0, 0, 0);
-  double cf1 = 1.0;
-  Item bufA, bufB;
-  if (valid) {
-    rc0 = rec[i0];
-    if (i0 + 1 < i1) rc1 = rec[i0 + 1];
-    if (i0 + 2 < i1) rc2 = rec[i0 + 2];
+  // prologue of this lane's gather chain: records of its items 0,1 (i0+h, i0+h+2), vertices and coordinates of item 0
+  Item cur, nxt;
+  uint4 rc1 = make_uint4(0, 0, 0, 0);
+  int64_t i = i0 + h;
+  if (valid && i < i1) {
+    const uint4 rc0 = rec[i];
+    if (i + 2 < i1) rc1 = rec[i + 2];
     const int4 cv0 = *reinterpret_cast<const int4*>(p.cells + (int64_t)(int)rc0.x * 4);
     const double cf0 = coefs ? coefs[(int)rc0.x] : 1.0;
-    if (i0 + 1 < i1) {
-      cv1 = *reinterpret_cast<const int4*>(p.cells + (int64_t)(int)rc1.x * 4);
-      cf1 = coefs ? coefs[(int)rc1.x] : 1.0;
-    }
-    gather_coords(p, s_desc, s_fsel, rc0, cv0, cf0, bufA);
+    gather_coords(p, s_desc, s_fsel, rc0, cv0, cf0, cur);
   }
   // the previous pass's bulk store must have finished reading the tile before it is overwritten
   tile_store_wait(lane);
   double2* row0 = tile + off;
-  if (valid) {
-    RingState st;
+  double2 self[2] = {make_double2(0.0, 0.0), make_double2(0.0, 0.0)};
+  double2 saved[2][3];  // even lane: what the partner handed over at the end of the previous step
 #pragma unroll
-    for (int k = 0; k < 2; ++k) {
-      st.self[k] = make_double2(0.0, 0.0);
+  for (int k = 0; k < 2; ++k)
 #pragma unroll
-      for (int j = 0; j < 3; ++j) st.carry[k][j] = make_double2(0.0, 0.0);
-    }
-    // STEP: hop 1 of item I+3, hop 2 of item I+2, hop 3 of item I+1 (into NXT), then consume item I (CUR)
-#define SFEM_EDGE_STEP(CUR, NXT, I)                                                                       \
-    {                                                                                                     \
-      uint4 rc3 = make_uint4(0, 0, 0, 0);                                                                 \
-      int4 cv2 = make_int4(0, 0, 0, 0);                                                                   \
-      double cf2 = 1.0;                                                                                   \
-      if ((I) + 3 < i1) rc3 = rec[(I) + 3];                                                               \
-      if ((I) + 2 < i1) {                                                                                 \
-        cv2 = *reinterpret_cast<const int4*>(p.cells + (int64_t)(int)rc2.x * 4);                          \
-        cf2 = coefs ? coefs[(int)rc2.x] : 1.0;                                                            \
-      }                                                                                                   \
-      if ((I) + 1 < i1) gather_coords(p, s_desc, s_fsel, rc1, cv1, cf1, NXT);                             \
-      edge_item<MASS>(CUR, row0, len, st);                                                                \
-      rc1 = rc2; rc2 = rc3; cv1 = cv2; cf1 = cf2;                                                         \
-    }
-    const int self = slot_of<5>(bufA);  // canonical entity 5 = the row edge itself
+    for (int j = 0; j < 3; ++j) saved[k][j] = make_double2(0.0, 0.0);
+  int self_slot = 0;
 #pragma unroll 1
-    for (int64_t i = i0; i < i1; i += 2) {
-      SFEM_EDGE_STEP(bufA, bufB, i)
-      if (i + 1 < i1) SFEM_EDGE_STEP(bufB, bufA, i + 1)
+  for (int s = 0; s < nsteps; ++s, i += 2) {
+    const bool active = valid && i < i1;
+    // prefetch this lane's next item (record two ahead)
+    uint4 rc2 = make_uint4(0, 0, 0, 0);
+    if (active && i + 2 < i1) {
+      if (i + 4 < i1) rc2 = rec[i + 4];
+      const int4 cv1 = *reinterpret_cast<const int4*>(p.cells + (int64_t)(int)rc1.x * 4);
+      const double cf1 = coefs ? coefs[(int)rc1.x] : 1.0;
+      gather_coords(p, s_desc, s_fsel, rc1, cv1, cf1, nxt);
     }
-#undef SFEM_EDGE_STEP
-    row0[self] = st.self[0];
-    row0[len + self] = st.self[1];
-    if (p.pec) pec_overwrite(p, row0, g, len, self);
+    const unsigned flags = active ? (cur.s2 >> 24) : 0u;
+    const bool has_prev = flags & 1u, has_next = flags & 2u, wrap = flags & 4u;
+    double gm[6], o[20];
+    if (active) {
+      canon_geometry<MASS>(cur, gm);
+      if (s == 0 && h == 0) self_slot = slot_of<5>(cur);
+    }
+    __syncwarp();
+#define SFEM_RING_ROW(K, FN)                                                                       \
+    {                                                                                              \
+      double2 n3 = make_double2(0.0, 0.0), n1 = n3, n8 = n3;                                       \
+      if (active) {                                                                                \
+        FN(gm, o);                                                                                 \
+        n3 = fix_columns<3>(cur, o[6], o[7]);                                                      \
+        n1 = fix_columns<1>(cur, o[2], o[3]);                                                      \
+        n8 = fix_columns<8>(cur, o[16], o[17]);                                                    \
+      }                                                                                            \
+      /* hand the next-side blocks to the partner, which owns the next cell of the ring */         \
+      const double2 g3 = shfl_xor1(n3), g1 = shfl_xor1(n1), g8 = shfl_xor1(n8);                    \
+      const double2 c4 = h ? g3 : saved[K][0], c2 = h ? g1 : saved[K][1], c9 = h ? g8 : saved[K][2]; \
+      saved[K][0] = g3; saved[K][1] = g1; saved[K][2] = g8;                                        \
+      if (active) {                                                                                \
+        double2* row = row0 + K * len;                                                             \
+        double2 r;                                                                                 \
+        r = fix_columns<5>(cur, o[10], o[11]); self[K].x += r.x; self[K].y += r.y;                 \
+        r = fix_columns<4>(cur, o[8], o[9]);                                                       \
+        if (has_prev) { r.x += c4.x; r.y += c4.y; }                                                \
+        row[slot_of<4>(cur)] = r;                                                                  \
+        r = fix_columns<2>(cur, o[4], o[5]);                                                       \
+        if (has_prev) { r.x += c2.x; r.y += c2.y; }                                                \
+        row[slot_of<2>(cur)] = r;                                                                  \
+        r = fix_columns<9>(cur, o[18], o[19]);                                                     \
+        if (has_prev) { r.x += c9.x; r.y += c9.y; }                                                \
+        row[slot_of<9>(cur)] = r;                                                                  \
+        row[slot_of<0>(cur)] = fix_columns<0>(cur, o[0], o[1]);                                    \
+        row[slot_of<7>(cur)] = fix_columns<7>(cur, o[14], o[15]);                                  \
+        row[slot_of<6>(cur)] = fix_columns<6>(cur, o[12], o[13]);                                  \
+        if (!has_next) {                                                                           \
+          double2* q3 = row + slot_of<3>(cur);                                                     \
+          double2* q1 = row + slot_of<1>(cur);                                                     \
+          double2* q8 = row + slot_of<8>(cur);                                                     \
+          if (wrap) {                                                                              \
+            const double2 t3 = *q3, t1 = *q1, t8 = *q8;                                            \
+            n3.x += t3.x; n3.y += t3.y; n1.x += t1.x; n1.y += t1.y; n8.x += t8.x; n8.y += t8.y;    \
+          }                                                                                        \
+          *q3 = n3; *q1 = n1; *q8 = n8;                                                            \
+        }                                                                                          \
+      }                                                                                            \
+    }
+    if (MASS) {
+      SFEM_RING_ROW(0, canon_edge_mass_k0)
+      SFEM_RING_ROW(1, canon_edge_mass_k1)
+    } else {
+      SFEM_RING_ROW(0, canon_edge_curl_k0)
+      SFEM_RING_ROW(1, canon_edge_curl_k1)
+    }
+#undef SFEM_RING_ROW
+    cur = nxt;
+    rc1 = rc2;
+  }
+  // the row edge's own block: both lanes' partial sums, stored by the even lane
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    const double2 other = shfl_xor1(self[k]);
+    self[k].x += other.x;
+    self[k].y += other.y;
+  }
+  __syncwarp();
+  if (valid && h == 0) {
+    row0[self_slot] = self[0];
+    row0[len + self_slot] = self[1];
+    if (p.pec) pec_overwrite(p, row0, g, len, self_slot);
   }
   tile_store_issue(tile, out_first, (unsigned)span * 16u, lane);
 }
 
-__global__ void __launch_bounds__(kThreadsEdges) k_canon_edges(CanonArgs p) {
+__global__ void __launch_bounds__(kThreadsEdges, 3) k_canon_edges(CanonArgs p) {
   extern __shared__ double2 smem[];
   __shared__ unsigned long long s_desc[16];
   __shared__ unsigned s_fsel[16];
   stage_lut(s_desc, s_fsel);
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   double2* tile = smem + (size_t)w * p.tile_chunks;
-  const int64_t r = p.r_begin + blockIdx.x * (int64_t)kThreadsEdges + threadIdx.x;
+  const int64_t r = p.r_begin + (blockIdx.x * (int64_t)(kThreadsEdges / 32) + w) * 16 + (lane >> 1);
   const bool valid = r < p.r_end;
   int64_t g = 0, a = 0, a1 = 0, i0 = 0, i1 = 0;
   if (valid) {
@@ -334,7 +337,7 @@ __global__ void __launch_bounds__(kThreadsEdges) k_canon_edges(CanonArgs p) {
     i1 = p.inc_ptr[g + 1];
   }
   const int len = (int)(a1 - a);
-  // the warp's span: chunks [2 a_first, 2 a_last_end) of the value arrays (lanes are consecutive entities)
+  // the warp's span: chunks [2 a_first, 2 a_last_end) of the value arrays (lane pairs are consecutive entities)
   const unsigned vmask = __ballot_sync(0xffffffffu, valid);
   if (vmask == 0) return;
   const int last = 31 - __clz((int)vmask);
@@ -342,86 +345,90 @@ __global__ void __launch_bounds__(kThreadsEdges) k_canon_edges(CanonArgs p) {
   const int64_t a_end = __shfl_sync(0xffffffffu, a1, last);
   const int span = (int)(2 * (a_end - a_first));
   const int off = (int)(2 * (a - a_first));
-  edge_pass<false>(p, s_desc, s_fsel, tile, lane, valid, g, len, off, span, i0, i1, p.S + 4 * a_first);
-  edge_pass<true>(p, s_desc, s_fsel, tile, lane, valid, g, len, off, span, i0, i1, p.T + 4 * a_first);
+  int nsteps = (int)((i1 - i0 + 1) >> 1);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) nsteps = max(nsteps, __shfl_xor_sync(0xffffffffu, nsteps, o));
+  edge_pass<false>(p, s_desc, s_fsel, tile, lane, valid, g, len, off, span, i0, i1, nsteps, p.S + 4 * a_first);
+  edge_pass<true>(p, s_desc, s_fsel, tile, lane, valid, g, len, off, span, i0, i1, nsteps, p.T + 4 * a_first);
   tile_store_wait(lane);
 }
 
-// ---- faces: at most two cells; shared entities summed in registers, tile is store-only --------------------------
+// ---- faces: a PAIR of lanes per face, one lane per incident cell; the tile is store-only -------------------------
+// Entities of the shared face (canonical 2,4,5 = its edges, 9 = itself) look alike from both cells (identity
+// fix-up): the odd lane hands its values over by shuffle and the even lane stores the sums.
 template <bool MASS>
 __device__ __forceinline__ void face_pass(const CanonArgs& p, double2* __restrict__ tile, int lane, bool valid,
-                                          int64_t g, int len, int off, int span, int ncell, Item& A, Item& B,
+                                          bool active, int64_t g, int len, int off, int span, const Item& it,
                                           double* __restrict__ out_first) {
+  const int h = lane & 1;
   tile_store_wait(lane);
   double2* row0 = tile + off;
-  if (valid) {
-    double gA[6], gB[6], oA[20];
-    canon_geometry<MASS>(A, gA);
-    if (ncell > 1) canon_geometry<MASS>(B, gB);
-#define SFEM_FACE_PUT(U, K, IT, O) row0[K * len + slot_of<U>(IT)] = fix_columns<U>(IT, O[2 * U], O[2 * U + 1]);
-#define SFEM_FACE_SHARED(U) oA[2 * U] += oB[2 * U]; oA[2 * U + 1] += oB[2 * U + 1];
+  double gm[6], o[20];
+  if (active) canon_geometry<MASS>(it, gm);
 #define SFEM_FACE_ROW(K, FN)                                                                              \
-    {                                                                                                     \
-      if (ncell > 1) {                                                                                    \
-        double oB[20];                                                                                    \
-        FN(gB, oB);                                                                                       \
-        SFEM_FACE_PUT(0, K, B, oB) SFEM_FACE_PUT(1, K, B, oB) SFEM_FACE_PUT(3, K, B, oB)                  \
-        SFEM_FACE_PUT(6, K, B, oB) SFEM_FACE_PUT(7, K, B, oB) SFEM_FACE_PUT(8, K, B, oB)                  \
-        FN(gA, oA);                                                                                       \
-        /* entities of the shared face (canonical 2,4,5 = its edges, 9 = itself) look alike from both cells */ \
-        SFEM_FACE_SHARED(2) SFEM_FACE_SHARED(4) SFEM_FACE_SHARED(5) SFEM_FACE_SHARED(9)                   \
-      } else {                                                                                            \
-        FN(gA, oA);                                                                                       \
+  {                                                                                                       \
+    double2 s2 = make_double2(0.0, 0.0), s4 = s2, s5 = s2, s9 = s2;                                       \
+    if (active) {                                                                                         \
+      FN(gm, o);                                                                                          \
+      s2 = make_double2(o[4], o[5]); s4 = make_double2(o[8], o[9]);                                       \
+      s5 = make_double2(o[10], o[11]); s9 = make_double2(o[18], o[19]);                                   \
+    }                                                                                                     \
+    const double2 t2 = shfl_xor1(s2), t4 = shfl_xor1(s4), t5 = shfl_xor1(s5), t9 = shfl_xor1(s9);         \
+    if (active) {                                                                                         \
+      double2* row = row0 + K * len;                                                                      \
+      row[slot_of<0>(it)] = fix_columns<0>(it, o[0], o[1]);                                               \
+      row[slot_of<1>(it)] = fix_columns<1>(it, o[2], o[3]);                                               \
+      row[slot_of<3>(it)] = fix_columns<3>(it, o[6], o[7]);                                               \
+      row[slot_of<6>(it)] = fix_columns<6>(it, o[12], o[13]);                                             \
+      row[slot_of<7>(it)] = fix_columns<7>(it, o[14], o[15]);                                             \
+      row[slot_of<8>(it)] = fix_columns<8>(it, o[16], o[17]);                                             \
+      if (h == 0) {  /* the odd lane of a boundary face is inactive and handed over zeros */              \
+        row[slot_of<2>(it)] = make_double2(s2.x + t2.x, s2.y + t2.y);                                     \
+        row[slot_of<4>(it)] = make_double2(s4.x + t4.x, s4.y + t4.y);                                     \
+        row[slot_of<5>(it)] = make_double2(s5.x + t5.x, s5.y + t5.y);                                     \
+        row[slot_of<9>(it)] = make_double2(s9.x + t9.x, s9.y + t9.y);                                     \
       }                                                                                                   \
-      SFEM_FACE_PUT(0, K, A, oA) SFEM_FACE_PUT(1, K, A, oA) SFEM_FACE_PUT(2, K, A, oA)                    \
-      SFEM_FACE_PUT(3, K, A, oA) SFEM_FACE_PUT(4, K, A, oA) SFEM_FACE_PUT(5, K, A, oA)                    \
-      SFEM_FACE_PUT(6, K, A, oA) SFEM_FACE_PUT(7, K, A, oA) SFEM_FACE_PUT(8, K, A, oA)                    \
-      SFEM_FACE_PUT(9, K, A, oA)                                                                          \
-    }
-    if (MASS) {
-      SFEM_FACE_ROW(0, canon_face_mass_k0)
-      SFEM_FACE_ROW(1, canon_face_mass_k1)
-    } else {
-      SFEM_FACE_ROW(0, canon_face_curl_k0)
-      SFEM_FACE_ROW(1, canon_face_curl_k1)
-    }
-#undef SFEM_FACE_ROW
-#undef SFEM_FACE_SHARED
-#undef SFEM_FACE_PUT
-    if (p.pec) pec_overwrite(p, row0, g, len, slot_of<9>(A));  // canonical entity 9 = the row face itself
+    }                                                                                                     \
   }
+  if (MASS) {
+    SFEM_FACE_ROW(0, canon_face_mass_k0)
+    SFEM_FACE_ROW(1, canon_face_mass_k1)
+  } else {
+    SFEM_FACE_ROW(0, canon_face_curl_k0)
+    SFEM_FACE_ROW(1, canon_face_curl_k1)
+  }
+#undef SFEM_FACE_ROW
+  __syncwarp();
+  if (valid && h == 0 && p.pec) pec_overwrite(p, row0, g, len, slot_of<9>(it));  // canonical 9 = the row face
   tile_store_issue(tile, out_first, (unsigned)span * 16u, lane);
 }
 
-__global__ void __launch_bounds__(kThreadsFaces, 3) k_canon_faces(CanonArgs p) {
+__global__ void __launch_bounds__(kThreadsFaces, 4) k_canon_faces(CanonArgs p) {
   extern __shared__ double2 smem[];
   __shared__ unsigned long long s_desc[16];
   __shared__ unsigned s_fsel[16];
   stage_lut(s_desc, s_fsel);
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, h = lane & 1;
   double2* tile = smem + (size_t)w * p.tile_chunks;
-  const int64_t r = p.r_begin + blockIdx.x * (int64_t)kThreadsFaces + threadIdx.x;
+  const int64_t r = p.r_begin + (blockIdx.x * (int64_t)(kThreadsFaces / 32) + w) * 16 + (lane >> 1);
   const bool valid = r < p.r_end;
   int64_t g = 0, a = 0, a1 = 0;
-  int ncell = 0;
-  Item A, B;
-  double mu_A = 1.0, mu_B = 1.0, eps_A = 1.0, eps_B = 1.0;
+  bool active = false;
+  Item it;
+  double eps_c = 1.0;
   if (valid) {
     g = p.ent_lo + r;
     a = p.ent_rowptr[r];
     a1 = p.ent_rowptr[r + 1];
     const int64_t i0 = p.inc_ptr[g];
-    ncell = (int)(p.inc_ptr[g + 1] - i0);
-    // both gather chains are issued before anything is consumed
-    const uint4* __restrict__ rec = p.rec - p.inc_base;
-    const uint4 rA = rec[i0];
-    const uint4 rB = ncell > 1 ? rec[i0 + 1] : rA;
-    const int4 cvA = *reinterpret_cast<const int4*>(p.cells + (int64_t)(int)rA.x * 4);
-    const int4 cvB = *reinterpret_cast<const int4*>(p.cells + (int64_t)(int)rB.x * 4);
-    if (p.mu) { mu_A = p.mu[(int)rA.x]; mu_B = p.mu[(int)rB.x]; }
-    if (p.eps) { eps_A = p.eps[(int)rA.x]; eps_B = p.eps[(int)rB.x]; }
-    gather_coords(p, s_desc, s_fsel, rA, cvA, mu_A, A);
-    gather_coords(p, s_desc, s_fsel, rB, cvB, mu_B, B);
+    active = i0 + h < p.inc_ptr[g + 1];
+    if (active) {
+      const uint4 rc = (p.rec - p.inc_base)[i0 + h];
+      const int4 cv = *reinterpret_cast<const int4*>(p.cells + (int64_t)(int)rc.x * 4);
+      const double mu_c = p.mu ? p.mu[(int)rc.x] : 1.0;
+      if (p.eps) eps_c = p.eps[(int)rc.x];
+      gather_coords(p, s_desc, s_fsel, rc, cv, mu_c, it);
+    }
   }
   const int len = (int)(a1 - a);
   const unsigned vmask = __ballot_sync(0xffffffffu, valid);
@@ -431,10 +438,9 @@ __global__ void __launch_bounds__(kThreadsFaces, 3) k_canon_faces(CanonArgs p) {
   const int64_t a_end = __shfl_sync(0xffffffffu, a1, last);
   const int span = (int)(2 * (a_end - a_first));
   const int off = (int)(2 * (a - a_first));
-  face_pass<false>(p, tile, lane, valid, g, len, off, span, ncell, A, B, p.S + 4 * a_first);
-  A.coef = eps_A;
-  B.coef = eps_B;
-  face_pass<true>(p, tile, lane, valid, g, len, off, span, ncell, A, B, p.T + 4 * a_first);
+  face_pass<false>(p, tile, lane, valid, active, g, len, off, span, it, p.S + 4 * a_first);
+  it.coef = eps_c;
+  face_pass<true>(p, tile, lane, valid, active, g, len, off, span, it, p.T + 4 * a_first);
   tile_store_wait(lane);
 }
 
@@ -462,21 +468,21 @@ int assemble_canonical_ST(const sfem_pattern_s* pat, const double* eps, const do
   const int64_t n_rows = pat->n_rows_ent;
   if (n_edge_rows > 0) {
     p.r_begin = 0; p.r_end = n_edge_rows;
-    p.tile_chunks = 32 * 2 * pat->max_row_len_edges;
+    p.tile_chunks = 16 * 2 * pat->max_row_len_edges;
     const size_t smem = (size_t)(kThreadsEdges / 32) * p.tile_chunks * sizeof(double2);
     SFEM_CHECK(smem <= 227 * 1024, "edge valence too high for the canonical kernel's shared-memory tile; use the generic kernel");
     SFEM_CUDA(cudaFuncSetAttribute(k_canon_edges, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const unsigned grid = (unsigned)((n_edge_rows + kThreadsEdges - 1) / kThreadsEdges);
+    const unsigned grid = (unsigned)((n_edge_rows + kThreadsEdges / 2 - 1) / (kThreadsEdges / 2));
     k_canon_edges<<<grid, kThreadsEdges, smem, st>>>(p);
   }
   if (n_rows > n_edge_rows) {
     // a face shared by more than two cells is not a valid tetrahedral mesh
     SFEM_CHECK(pat->max_row_len_other <= 16, "a face is shared by more than two cells: not a valid tetrahedral mesh");
     p.r_begin = n_edge_rows; p.r_end = n_rows;
-    p.tile_chunks = 32 * 2 * 16;
+    p.tile_chunks = 16 * 2 * 16;
     const size_t smem = (size_t)(kThreadsFaces / 32) * p.tile_chunks * sizeof(double2);
     SFEM_CUDA(cudaFuncSetAttribute(k_canon_faces, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const unsigned grid = (unsigned)((n_rows - n_edge_rows + kThreadsFaces - 1) / kThreadsFaces);
+    const unsigned grid = (unsigned)((n_rows - n_edge_rows + kThreadsFaces / 2 - 1) / (kThreadsFaces / 2));
     k_canon_faces<<<grid, kThreadsFaces, smem, st>>>(p);
   }
   SFEM_CUDA(cudaGetLastError());
