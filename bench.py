@@ -44,32 +44,43 @@ def peak_hbm():
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks + throttle reasons sampled DURING the timed region."""
-    Q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
-         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
-         'clocks_event_reasons.sw_power_cap')
+    """SM clock, power and throttle reasons sampled DURING the timed region (NVML, ~1 ms period; the same
+    counters `nvidia-smi --query-gpu=clocks.sm,clocks_event_reasons.*` prints)."""
 
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index, self.stop_flag, self.rows = index, False, []
+        self.max_mhz = None
 
     def run(self):
-        while not self.stop_flag:
-            try:
-                out = subprocess.run(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
-                                      '--format=csv,noheader,nounits'], capture_output=True, text=True, timeout=5).stdout
-                self.rows.append([x.strip() for x in out.strip().split(',')])
-            except Exception:
-                pass
-            time.sleep(0.05)
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            vis = os.environ.get('CUDA_VISIBLE_DEVICES')
+            idx = int(vis.split(',')[self.index]) if vis and vis.split(',')[self.index].isdigit() else self.index
+            h = nv.nvmlDeviceGetHandleByIndex(idx)
+            self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            while not self.stop_flag:
+                self.rows.append((nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM),
+                                  nv.nvmlDeviceGetCurrentClocksThrottleReasons(h),
+                                  nv.nvmlDeviceGetPowerUsage(h) / 1000.0))
+                time.sleep(0.001)
+        except Exception as e:  # noqa: BLE001
+            self.error = repr(e)
 
     def summary(self):
-        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
-        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
-        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
-        reasons = [n for i, n in enumerate(names) if any(len(r) > 3 + i and r[3 + i] == 'Active' for r in self.rows)]
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(self.rows)}
+        import pynvml as nv
+        sm = sorted(r[0] for r in self.rows)
+        bits = 0
+        for r in self.rows:
+            bits |= r[1]
+        names = [('hw_slowdown', nv.nvmlClocksThrottleReasonHwSlowdown),
+                 ('hw_thermal_slowdown', nv.nvmlClocksThrottleReasonHwThermalSlowdown),
+                 ('sw_thermal_slowdown', nv.nvmlClocksThrottleReasonSwThermalSlowdown),
+                 ('sw_power_cap', nv.nvmlClocksThrottleReasonSwPowerCap)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.max_mhz,
+                "reasons": [n for n, b in names if bits & b], "samples": len(self.rows),
+                "power_w_max": max((r[2] for r in self.rows), default=None)}
 
 
 def cpu_port_run(n, threads, steps, warmup=0):
@@ -174,6 +185,7 @@ def main():
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
         sampler.start()
+        time.sleep(0.05)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
     e0.record()

@@ -1,0 +1,9 @@
+"""Physical constants (mirror of /root/reference/sucemfem/Consts.py:27-31; the values are definitions)."""
+import numpy as N
+
+pi = N.pi
+e = N.e
+mu0 = N.pi * 4 * 1e-7
+c0 = 299792458
+eps0 = 10 ** 7 / 4 / N.pi / c0 / c0
+Z0 = mu0 * c0
