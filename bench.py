@@ -209,9 +209,20 @@ def main():
     share = pat.n_rows / float(space.ndof)
     b_alg = algorithmic_bytes(C_total * share, mesh.num_vertices * share, pat.nnz)
     achieved = b_alg / (ms_local / K * 1e-3) / 1e9
+    traffic = None
+    try:  # DRAM bytes per step from the committed ncu capture of this workload (profiles/), if it is this workload
+        with open(os.path.join(ROOT, 'profiles', 'traffic.json')) as f:
+            tj = json.load(f)
+        if tj.get('n') == n and world == 1:
+            traffic = tj['dram_bytes_per_step']
+    except Exception:
+        pass
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": b_alg,
-                "kernel_ms": ms_local / K}
+                "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": b_alg,
+                "kernel_ms": ms_local / K,
+                "note": "one step = the launches of one sfem_assemble_ST call (k_canon_edges + k_canon_faces), timed "
+                        "back to back with CUDA events on the launching stream; achieved = algorithmic bytes of the "
+                        "step / step time; traffic = ncu DRAM bytes of the same two launches"}
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
