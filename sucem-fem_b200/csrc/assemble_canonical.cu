@@ -41,7 +41,7 @@ struct CanonArgs {
   const double* __restrict__ mu;
   const int64_t* __restrict__ inc_ptr;
   const int64_t* __restrict__ ent_rowptr;  // block-relative, indexed by r = g - ent_lo
-  const uint4* __restrict__ rec;           // packed {cell, t, slots[10]} per (entity, cell), block-relative
+  const uint4* __restrict__ rec;           // packed 32-byte item records (pattern.cu), 2 x uint4 per (entity, cell)
   const uint8_t* __restrict__ pec;
   double* __restrict__ S;
   double* __restrict__ T;
@@ -54,41 +54,34 @@ struct CanonArgs {
 
 // per-(entity, cell) inputs
 struct Item {
-  double X[12];             // coordinates of the relabelled vertices
-  double coef;              // eps_r (mass pass) or mu_r (stiffness pass) of the cell
-  unsigned long long desc;  // generated/canonical_lut.inc
-  unsigned fsel;
-  uint32_t s0, s1, s2;      // bytes 4..15 of the record: t, slots[10]
+  double X[12];         // coordinates of the relabelled vertices
+  double cmu, ceps;     // the cell's coefficients
+  uint32_t w1, w2, w3;  // record bytes 20..31: descriptor index, flags, slots[10]
 };
 
 template <int U>
 __device__ __forceinline__ int slot_of(const Item& it) {
-  // record byte 5+U
-  if constexpr (U < 3) return (it.s0 >> (8 * (U + 1))) & 0xffu;
-  else if constexpr (U < 7) return (it.s1 >> (8 * (U - 3))) & 0xffu;
-  else return (it.s2 >> (8 * (U - 7))) & 0xffu;
+  if constexpr (U < 2) return (it.w1 >> (16 + 8 * U)) & 0xffu;
+  else if constexpr (U < 6) return (it.w2 >> (8 * (U - 2))) & 0xffu;
+  else return (it.w3 >> (8 * (U - 6))) & 0xffu;
 }
+__device__ __forceinline__ unsigned flags_of(const Item& it) { return (it.w1 >> 8) & 0xffu; }
+__device__ __forceinline__ unsigned desc_index(const Item& it) { return it.w1 & 0xffu; }
 
-// stage 3 of the gather chain: coordinates (needs the record and the cell's vertex quadruple)
-__device__ __forceinline__ void gather_coords(const CanonArgs& p, const unsigned long long* __restrict__ s_desc,
-                                              const unsigned* __restrict__ s_fsel, uint4 rc, int4 cv, double coef,
-                                              Item& it) {
-  const int t = rc.y & 0xffu;
-  it.desc = s_desc[t];
-  it.fsel = s_fsel[t];
-  it.s0 = rc.y; it.s1 = rc.z; it.s2 = rc.w;
-  it.coef = coef;
-  const int32_t a[4] = {cv.x, cv.y, cv.z, cv.w};
+// last hop of the gather chain: coordinates + coefficients, from the record (vertex ids already relabelled)
+__device__ __forceinline__ void gather_item(const CanonArgs& p, uint4 ra, uint4 rb, Item& it) {
+  it.w1 = rb.y; it.w2 = rb.z; it.w3 = rb.w;
+  const uint32_t v[4] = {ra.x, ra.y, ra.z, ra.w};
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
-    const unsigned s = (unsigned)(it.desc >> (2 * k)) & 3u;
-    const uint32_t v = (uint32_t)(s == 0 ? a[0] : (s == 1 ? a[1] : (s == 2 ? a[2] : a[3])));
-    const double2* x = reinterpret_cast<const double2*>(p.coords4 + (size_t)v * 4);
+    const double2* x = reinterpret_cast<const double2*>(p.coords4 + (size_t)v[k] * 4);
     const double2 xy = x[0], z = x[1];
     it.X[3 * k] = xy.x;
     it.X[3 * k + 1] = xy.y;
     it.X[3 * k + 2] = z.x;
   }
+  it.cmu = p.mu ? p.mu[(int)rb.x] : 1.0;
+  it.ceps = p.eps ? p.eps[(int)rb.x] : 1.0;
 }
 
 // geometry factors of the relabelled cell in symmetric order (00,11,22,01,02,12):
@@ -115,7 +108,7 @@ __device__ __forceinline__ void canon_geometry(const Item& it, double (&g)[6]) {
     A[0][2] = J[0][1] * J[1][2] - J[0][2] * J[1][1];
     A[1][2] = J[0][2] * J[1][0] - J[0][0] * J[1][2];
     A[2][2] = J[0][0] * J[1][1] - J[0][1] * J[1][0];
-    const double s = it.coef / ad;
+    const double s = it.ceps / ad;
     g[0] = (A[0][0] * A[0][0] + A[0][1] * A[0][1] + A[0][2] * A[0][2]) * s;
     g[1] = (A[1][0] * A[1][0] + A[1][1] * A[1][1] + A[1][2] * A[1][2]) * s;
     g[2] = (A[2][0] * A[2][0] + A[2][1] * A[2][1] + A[2][2] * A[2][2]) * s;
@@ -123,7 +116,7 @@ __device__ __forceinline__ void canon_geometry(const Item& it, double (&g)[6]) {
     g[4] = (A[0][0] * A[2][0] + A[0][1] * A[2][1] + A[0][2] * A[2][2]) * s;
     g[5] = (A[1][0] * A[2][0] + A[1][1] * A[2][1] + A[1][2] * A[2][2]) * s;
   } else {
-    const double s = 1.0 / (ad * it.coef);
+    const double s = 1.0 / (ad * it.cmu);
     g[0] = (J[0][0] * J[0][0] + J[1][0] * J[1][0] + J[2][0] * J[2][0]) * s;
     g[1] = (J[0][1] * J[0][1] + J[1][1] * J[1][1] + J[2][1] * J[2][1]) * s;
     g[2] = (J[0][2] * J[0][2] + J[1][2] * J[1][2] + J[2][2] * J[2][2]) * s;
@@ -137,14 +130,20 @@ __device__ __forceinline__ double sel3(unsigned code, double v0, double v1, doub
   return code == 0 ? v0 : (code == 1 ? v1 : w);
 }
 
+// orientation fix-up context of one item (generated/canonical_lut.inc)
+struct Fix {
+  unsigned long long desc;
+  unsigned fsel;
+};
+
 // true-frame values of the 2 columns of canonical column entity U, from canonical-frame values (v0, v1)
 template <int U>
-__device__ __forceinline__ double2 fix_columns(const Item& it, double v0, double v1) {
+__device__ __forceinline__ double2 fix_columns(const Fix& f, double v0, double v1) {
   if constexpr (U < 6) {
-    const bool flip = (it.desc >> (48 + U)) & 1ull;
+    const bool flip = (f.desc >> (48 + U)) & 1ull;
     return flip ? make_double2(-v1, -v0) : make_double2(v0, v1);
   } else {
-    const unsigned nib = (it.fsel >> (4 * (U - 6))) & 15u;
+    const unsigned nib = (f.fsel >> (4 * (U - 6))) & 15u;
     const double w = -(v0 + v1);
     return make_double2(sel3(nib & 3u, v0, v1, w), sel3(nib >> 2, v0, v1, w));
   }
@@ -186,6 +185,12 @@ __device__ __forceinline__ void stage_lut(unsigned long long* s_desc, unsigned* 
   __syncthreads();
 }
 
+#ifndef SFEM_EDGE_CTAS
+#define SFEM_EDGE_CTAS 2
+#endif
+#ifndef SFEM_FACE_CTAS
+#define SFEM_FACE_CTAS 2
+#endif
 constexpr int kThreadsEdges = 128;  // 4 warps x 16 edges; CTAs per SM are bounded by the shared-memory tiles
 constexpr int kThreadsFaces = 128;  // 4 warps x 16 faces
 
@@ -203,25 +208,43 @@ __device__ __forceinline__ double2 shfl_xor1(double2 v) {
 //   next   3 = (0,3), 1 = (1,3), 8 = (0,1,3)   shared with the next cell, which the PARTNER lane is working on:
 //                                               handed over by shuffle; stored if the fan ends here, added to the
 //                                               first cell's slots if the ring closes here
+// Gathers: the chain record -> coordinates of a lane's next item is issued one item ahead (record two ahead); at the
+// LAST step of a pass the free buffer instead receives the first item of the NEXT pass (same batch for S -> T, the
+// next batch for T -> S), so no pass starts with an exposed chain.
+struct EdgeMeta {
+  int64_t a, a1, i0, i1;  // entity-row range [a, a1) and record range [i0, i1) of this lane's edge (i0 > i1: none)
+};
+
+__device__ __forceinline__ EdgeMeta load_edge_meta(const CanonArgs& p, int64_t batch, int lane) {
+  EdgeMeta m;
+  const int64_t r = p.r_begin + batch * 16 + (lane >> 1);
+  if (r < p.r_end) {
+    const int64_t g = p.ent_lo + r;
+    m.a = p.ent_rowptr[r];
+    m.a1 = p.ent_rowptr[r + 1];
+    m.i0 = p.inc_ptr[g] - p.inc_base;
+    m.i1 = p.inc_ptr[g + 1] - p.inc_base;
+  } else {
+    m.a = m.a1 = 0;
+    m.i0 = 1; m.i1 = 0;
+  }
+  return m;
+}
+
 template <bool MASS>
 __device__ __forceinline__ void edge_pass(const CanonArgs& p, const unsigned long long* __restrict__ s_desc,
                                           const unsigned* __restrict__ s_fsel, double2* __restrict__ tile, int lane,
-                                          bool valid, int64_t g, int len, int off, int span, int64_t i0, int64_t i1,
-                                          int nsteps, double* __restrict__ out_first) {
+                                          const EdgeMeta& m, int64_t g, int off, int span, int nsteps,
+                                          Item& cur, Item& nxt, uint4& rc1a, uint4& rc1b,
+                                          int64_t nf, int64_t nf_end, double* __restrict__ out_first) {
+  // cur: this lane's first item (loaded or in flight); rc1: record of its second item; [nf, nf_end): this lane's
+  // record range in the next pass (nf = first item; nf >= nf_end: none)
   const int h = lane & 1;
-  const double* __restrict__ coefs = MASS ? p.eps : p.mu;
-  const uint4* __restrict__ rec = p.rec - p.inc_base;
-  // prologue of this lane's gather chain: records of its items 0,1 (i0+h, i0+h+2), vertices and coordinates of item 0
-  Item cur, nxt;
-  uint4 rc1 = make_uint4(0, 0, 0, 0);
-  int64_t i = i0 + h;
-  if (valid && i < i1) {
-    const uint4 rc0 = rec[i];
-    if (i + 2 < i1) rc1 = rec[i + 2];
-    const int4 cv0 = *reinterpret_cast<const int4*>(p.cells + (int64_t)(int)rc0.x * 4);
-    const double cf0 = coefs ? coefs[(int)rc0.x] : 1.0;
-    gather_coords(p, s_desc, s_fsel, rc0, cv0, cf0, cur);
-  }
+  const bool valid = m.i0 <= m.i1 && m.a1 > m.a;
+  const int len = (int)(m.a1 - m.a);
+  const uint4* __restrict__ rec = p.rec;
+  uint4 rfa = make_uint4(0, 0, 0, 0), rfb = rfa;
+  if (nf < nf_end) { rfa = rec[2 * nf]; rfb = rec[2 * nf + 1]; }
   // the previous pass's bulk store must have finished reading the tile before it is overwritten
   tile_store_wait(lane);
   double2* row0 = tile + off;
@@ -232,22 +255,33 @@ __device__ __forceinline__ void edge_pass(const CanonArgs& p, const unsigned lon
 #pragma unroll
     for (int j = 0; j < 3; ++j) saved[k][j] = make_double2(0.0, 0.0);
   int self_slot = 0;
+  int64_t i = m.i0 + h;
 #pragma unroll 1
   for (int s = 0; s < nsteps; ++s, i += 2) {
-    const bool active = valid && i < i1;
-    // prefetch this lane's next item (record two ahead)
-    uint4 rc2 = make_uint4(0, 0, 0, 0);
-    if (active && i + 2 < i1) {
-      if (i + 4 < i1) rc2 = rec[i + 4];
-      const int4 cv1 = *reinterpret_cast<const int4*>(p.cells + (int64_t)(int)rc1.x * 4);
-      const double cf1 = coefs ? coefs[(int)rc1.x] : 1.0;
-      gather_coords(p, s_desc, s_fsel, rc1, cv1, cf1, nxt);
+    const bool active = valid && i < m.i1;
+    uint4 rc2a = make_uint4(0, 0, 0, 0), rc2b = rc2a;
+    if (s + 1 < nsteps) {
+      // this lane's next item of the pass (record two ahead)
+      if (i + 2 < m.i1) {
+        if (i + 4 < m.i1) { rc2a = rec[2 * (i + 4)]; rc2b = rec[2 * (i + 4) + 1]; }
+        gather_item(p, rc1a, rc1b, nxt);
+      }
+    } else {
+      // last step: the first item of the next pass, and the record of its second item
+      if (nf < nf_end) {
+        if (nf + 2 < nf_end) { rc2a = rec[2 * (nf + 2)]; rc2b = rec[2 * (nf + 2) + 1]; }
+        gather_item(p, rfa, rfb, nxt);
+      }
     }
-    const unsigned flags = active ? (cur.s2 >> 24) : 0u;
+    const unsigned flags = active ? flags_of(cur) : 0u;
     const bool has_prev = flags & 1u, has_next = flags & 2u, wrap = flags & 4u;
     double gm[6], o[20];
+    Fix fx;
+    fx.desc = 0ull; fx.fsel = 0u;
     if (active) {
       canon_geometry<MASS>(cur, gm);
+      fx.desc = s_desc[desc_index(cur)];
+      fx.fsel = s_fsel[desc_index(cur)];
       if (s == 0 && h == 0) self_slot = slot_of<5>(cur);
     }
     __syncwarp();
@@ -256,9 +290,9 @@ __device__ __forceinline__ void edge_pass(const CanonArgs& p, const unsigned lon
       double2 n3 = make_double2(0.0, 0.0), n1 = n3, n8 = n3;                                       \
       if (active) {                                                                                \
         FN(gm, o);                                                                                 \
-        n3 = fix_columns<3>(cur, o[6], o[7]);                                                      \
-        n1 = fix_columns<1>(cur, o[2], o[3]);                                                      \
-        n8 = fix_columns<8>(cur, o[16], o[17]);                                                    \
+        n3 = fix_columns<3>(fx, o[6], o[7]);                                                       \
+        n1 = fix_columns<1>(fx, o[2], o[3]);                                                       \
+        n8 = fix_columns<8>(fx, o[16], o[17]);                                                     \
       }                                                                                            \
       /* hand the next-side blocks to the partner, which owns the next cell of the ring */         \
       const double2 g3 = shfl_xor1(n3), g1 = shfl_xor1(n1), g8 = shfl_xor1(n8);                    \
@@ -267,19 +301,19 @@ __device__ __forceinline__ void edge_pass(const CanonArgs& p, const unsigned lon
       if (active) {                                                                                \
         double2* row = row0 + K * len;                                                             \
         double2 r;                                                                                 \
-        r = fix_columns<5>(cur, o[10], o[11]); self[K].x += r.x; self[K].y += r.y;                 \
-        r = fix_columns<4>(cur, o[8], o[9]);                                                       \
+        r = fix_columns<5>(fx, o[10], o[11]); self[K].x += r.x; self[K].y += r.y;                  \
+        r = fix_columns<4>(fx, o[8], o[9]);                                                        \
         if (has_prev) { r.x += c4.x; r.y += c4.y; }                                                \
         row[slot_of<4>(cur)] = r;                                                                  \
-        r = fix_columns<2>(cur, o[4], o[5]);                                                       \
+        r = fix_columns<2>(fx, o[4], o[5]);                                                        \
         if (has_prev) { r.x += c2.x; r.y += c2.y; }                                                \
         row[slot_of<2>(cur)] = r;                                                                  \
-        r = fix_columns<9>(cur, o[18], o[19]);                                                     \
+        r = fix_columns<9>(fx, o[18], o[19]);                                                      \
         if (has_prev) { r.x += c9.x; r.y += c9.y; }                                                \
         row[slot_of<9>(cur)] = r;                                                                  \
-        row[slot_of<0>(cur)] = fix_columns<0>(cur, o[0], o[1]);                                    \
-        row[slot_of<7>(cur)] = fix_columns<7>(cur, o[14], o[15]);                                  \
-        row[slot_of<6>(cur)] = fix_columns<6>(cur, o[12], o[13]);                                  \
+        row[slot_of<0>(cur)] = fix_columns<0>(fx, o[0], o[1]);                                     \
+        row[slot_of<7>(cur)] = fix_columns<7>(fx, o[14], o[15]);                                   \
+        row[slot_of<6>(cur)] = fix_columns<6>(fx, o[12], o[13]);                                   \
         if (!has_next) {                                                                           \
           double2* q3 = row + slot_of<3>(cur);                                                     \
           double2* q1 = row + slot_of<1>(cur);                                                     \
@@ -301,7 +335,7 @@ __device__ __forceinline__ void edge_pass(const CanonArgs& p, const unsigned lon
     }
 #undef SFEM_RING_ROW
     cur = nxt;
-    rc1 = rc2;
+    rc1a = rc2a; rc1b = rc2b;
   }
   // the row edge's own block: both lanes' partial sums, stored by the even lane
 #pragma unroll
@@ -319,37 +353,50 @@ __device__ __forceinline__ void edge_pass(const CanonArgs& p, const unsigned lon
   tile_store_issue(tile, out_first, (unsigned)span * 16u, lane);
 }
 
-__global__ void __launch_bounds__(kThreadsEdges, 3) k_canon_edges(CanonArgs p) {
+__global__ void __launch_bounds__(kThreadsEdges, SFEM_EDGE_CTAS) k_canon_edges(CanonArgs p) {
   extern __shared__ double2 smem[];
   __shared__ unsigned long long s_desc[16];
   __shared__ unsigned s_fsel[16];
   stage_lut(s_desc, s_fsel);
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, h = lane & 1;
   double2* tile = smem + (size_t)w * p.tile_chunks;
-  const int64_t r = p.r_begin + (blockIdx.x * (int64_t)(kThreadsEdges / 32) + w) * 16 + (lane >> 1);
-  const bool valid = r < p.r_end;
-  int64_t g = 0, a = 0, a1 = 0, i0 = 0, i1 = 0;
-  if (valid) {
-    g = p.ent_lo + r;
-    a = p.ent_rowptr[r];
-    a1 = p.ent_rowptr[r + 1];
-    i0 = p.inc_ptr[g];
-    i1 = p.inc_ptr[g + 1];
+  const int64_t nb = (p.r_end - p.r_begin + 15) / 16;
+  const int64_t W = (int64_t)gridDim.x * (kThreadsEdges / 32);
+  int64_t b = blockIdx.x * (int64_t)(kThreadsEdges / 32) + w;
+  if (b >= nb) return;
+  // prologue: this lane's first item and the record of its second one
+  EdgeMeta m = load_edge_meta(p, b, lane);
+  Item cur, nxt;
+  uint4 rc1a = make_uint4(0, 0, 0, 0), rc1b = rc1a;
+  {
+    const int64_t i = m.i0 + h;
+    if (i < m.i1) {
+      const uint4 ra = p.rec[2 * i], rb = p.rec[2 * i + 1];
+      if (i + 2 < m.i1) { rc1a = p.rec[2 * (i + 2)]; rc1b = p.rec[2 * (i + 2) + 1]; }
+      gather_item(p, ra, rb, cur);
+    }
   }
-  const int len = (int)(a1 - a);
-  // the warp's span: chunks [2 a_first, 2 a_last_end) of the value arrays (lane pairs are consecutive entities)
-  const unsigned vmask = __ballot_sync(0xffffffffu, valid);
-  if (vmask == 0) return;
-  const int last = 31 - __clz((int)vmask);
-  const int64_t a_first = __shfl_sync(0xffffffffu, a, 0);
-  const int64_t a_end = __shfl_sync(0xffffffffu, a1, last);
-  const int span = (int)(2 * (a_end - a_first));
-  const int off = (int)(2 * (a - a_first));
-  int nsteps = (int)((i1 - i0 + 1) >> 1);
+#pragma unroll 1
+  for (; b < nb; b += W) {
+    const EdgeMeta mn = load_edge_meta(p, b + W, lane);  // beyond the end: empty
+    const bool valid = m.i0 <= m.i1 && m.a1 > m.a;
+    // the warp's span: chunks [2 a_first, 2 a_last_end) of the value arrays (lane pairs are consecutive entities)
+    const unsigned vmask = __ballot_sync(0xffffffffu, valid);
+    const int last = 31 - __clz((int)vmask);
+    const int64_t a_first = __shfl_sync(0xffffffffu, m.a, 0);
+    const int64_t a_end = __shfl_sync(0xffffffffu, m.a1, last);
+    const int span = (int)(2 * (a_end - a_first));
+    const int off = (int)(2 * (m.a - a_first));
+    int nsteps = valid ? (int)((m.i1 - m.i0 + 1) >> 1) : 0;
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) nsteps = max(nsteps, __shfl_xor_sync(0xffffffffu, nsteps, o));
-  edge_pass<false>(p, s_desc, s_fsel, tile, lane, valid, g, len, off, span, i0, i1, nsteps, p.S + 4 * a_first);
-  edge_pass<true>(p, s_desc, s_fsel, tile, lane, valid, g, len, off, span, i0, i1, nsteps, p.T + 4 * a_first);
+    for (int o = 16; o > 0; o >>= 1) nsteps = max(nsteps, __shfl_xor_sync(0xffffffffu, nsteps, o));
+    const int64_t g = p.ent_lo + p.r_begin + b * 16 + (lane >> 1);
+    edge_pass<false>(p, s_desc, s_fsel, tile, lane, m, g, off, span, nsteps, cur, nxt, rc1a, rc1b, m.i0 + h, m.i1,
+                     p.S + 4 * a_first);
+    edge_pass<true>(p, s_desc, s_fsel, tile, lane, m, g, off, span, nsteps, cur, nxt, rc1a, rc1b, mn.i0 + h, mn.i1,
+                    p.T + 4 * a_first);
+    m = mn;
+  }
   tile_store_wait(lane);
 }
 
@@ -359,7 +406,7 @@ __global__ void __launch_bounds__(kThreadsEdges, 3) k_canon_edges(CanonArgs p) {
 template <bool MASS>
 __device__ __forceinline__ void face_pass(const CanonArgs& p, double2* __restrict__ tile, int lane, bool valid,
                                           bool active, int64_t g, int len, int off, int span, const Item& it,
-                                          double* __restrict__ out_first) {
+                                          const Fix& fx, double* __restrict__ out_first) {
   const int h = lane & 1;
   tile_store_wait(lane);
   double2* row0 = tile + off;
@@ -376,12 +423,12 @@ __device__ __forceinline__ void face_pass(const CanonArgs& p, double2* __restric
     const double2 t2 = shfl_xor1(s2), t4 = shfl_xor1(s4), t5 = shfl_xor1(s5), t9 = shfl_xor1(s9);         \
     if (active) {                                                                                         \
       double2* row = row0 + K * len;                                                                      \
-      row[slot_of<0>(it)] = fix_columns<0>(it, o[0], o[1]);                                               \
-      row[slot_of<1>(it)] = fix_columns<1>(it, o[2], o[3]);                                               \
-      row[slot_of<3>(it)] = fix_columns<3>(it, o[6], o[7]);                                               \
-      row[slot_of<6>(it)] = fix_columns<6>(it, o[12], o[13]);                                             \
-      row[slot_of<7>(it)] = fix_columns<7>(it, o[14], o[15]);                                             \
-      row[slot_of<8>(it)] = fix_columns<8>(it, o[16], o[17]);                                             \
+      row[slot_of<0>(it)] = fix_columns<0>(fx, o[0], o[1]);                                               \
+      row[slot_of<1>(it)] = fix_columns<1>(fx, o[2], o[3]);                                               \
+      row[slot_of<3>(it)] = fix_columns<3>(fx, o[6], o[7]);                                               \
+      row[slot_of<6>(it)] = fix_columns<6>(fx, o[12], o[13]);                                             \
+      row[slot_of<7>(it)] = fix_columns<7>(fx, o[14], o[15]);                                             \
+      row[slot_of<8>(it)] = fix_columns<8>(fx, o[16], o[17]);                                             \
       if (h == 0) {  /* the odd lane of a boundary face is inactive and handed over zeros */              \
         row[slot_of<2>(it)] = make_double2(s2.x + t2.x, s2.y + t2.y);                                     \
         row[slot_of<4>(it)] = make_double2(s4.x + t4.x, s4.y + t4.y);                                     \
@@ -403,44 +450,65 @@ __device__ __forceinline__ void face_pass(const CanonArgs& p, double2* __restric
   tile_store_issue(tile, out_first, (unsigned)span * 16u, lane);
 }
 
-__global__ void __launch_bounds__(kThreadsFaces, 4) k_canon_faces(CanonArgs p) {
+// record index of this lane's cell in batch `batch` (or -1), block-relative
+__device__ __forceinline__ int64_t face_item_index(const CanonArgs& p, int64_t batch, int64_t nb, int lane) {
+  const int64_t r = p.r_begin + batch * 16 + (lane >> 1);
+  if (batch >= nb || r >= p.r_end) return -1;
+  const int64_t g = p.ent_lo + r;
+  const int64_t i = p.inc_ptr[g] + (lane & 1);
+  return i < p.inc_ptr[g + 1] ? i - p.inc_base : -1;
+}
+
+// Persistent warps over batches of 16 faces; the gather chain (incidence pointer -> record -> coordinates) of the
+// batches 3, 2 and 1 iterations ahead is in flight while the current batch is computed.
+__global__ void __launch_bounds__(kThreadsFaces, SFEM_FACE_CTAS) k_canon_faces(CanonArgs p) {
   extern __shared__ double2 smem[];
   __shared__ unsigned long long s_desc[16];
   __shared__ unsigned s_fsel[16];
   stage_lut(s_desc, s_fsel);
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, h = lane & 1;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   double2* tile = smem + (size_t)w * p.tile_chunks;
-  const int64_t r = p.r_begin + (blockIdx.x * (int64_t)(kThreadsFaces / 32) + w) * 16 + (lane >> 1);
-  const bool valid = r < p.r_end;
-  int64_t g = 0, a = 0, a1 = 0;
-  bool active = false;
-  Item it;
-  double eps_c = 1.0;
-  if (valid) {
-    g = p.ent_lo + r;
-    a = p.ent_rowptr[r];
-    a1 = p.ent_rowptr[r + 1];
-    const int64_t i0 = p.inc_ptr[g];
-    active = i0 + h < p.inc_ptr[g + 1];
-    if (active) {
-      const uint4 rc = (p.rec - p.inc_base)[i0 + h];
-      const int4 cv = *reinterpret_cast<const int4*>(p.cells + (int64_t)(int)rc.x * 4);
-      const double mu_c = p.mu ? p.mu[(int)rc.x] : 1.0;
-      if (p.eps) eps_c = p.eps[(int)rc.x];
-      gather_coords(p, s_desc, s_fsel, rc, cv, mu_c, it);
-    }
+  const int64_t nb = (p.r_end - p.r_begin + 15) / 16;
+  const int64_t W = (int64_t)gridDim.x * (kThreadsFaces / 32);
+  int64_t b = blockIdx.x * (int64_t)(kThreadsFaces / 32) + w;
+  if (b >= nb) return;
+  Item cur, nxt;
+  int64_t i0 = face_item_index(p, b, nb, lane);
+  int64_t i1 = face_item_index(p, b + W, nb, lane);
+  int64_t i2 = face_item_index(p, b + 2 * W, nb, lane);
+  uint4 r1a = make_uint4(0, 0, 0, 0), r1b = r1a;
+  if (i0 >= 0) gather_item(p, p.rec[2 * i0], p.rec[2 * i0 + 1], cur);
+  if (i1 >= 0) { r1a = p.rec[2 * i1]; r1b = p.rec[2 * i1 + 1]; }
+#pragma unroll 1
+  for (; b < nb; b += W) {
+    // stage 3 / 2 / 1 of the batches ahead
+    const int64_t i3 = face_item_index(p, b + 3 * W, nb, lane);
+    uint4 r2a = make_uint4(0, 0, 0, 0), r2b = r2a;
+    if (i2 >= 0) { r2a = p.rec[2 * i2]; r2b = p.rec[2 * i2 + 1]; }
+    if (i1 >= 0) gather_item(p, r1a, r1b, nxt);
+    // current batch
+    const int64_t r = p.r_begin + b * 16 + (lane >> 1);
+    const bool valid = r < p.r_end;
+    const bool active = i0 >= 0;
+    int64_t a = 0, a1 = 0;
+    if (valid) { a = p.ent_rowptr[r]; a1 = p.ent_rowptr[r + 1]; }
+    const int64_t g = p.ent_lo + r;
+    const int len = (int)(a1 - a);
+    const unsigned vmask = __ballot_sync(0xffffffffu, valid);
+    const int last = 31 - __clz((int)vmask);
+    const int64_t a_first = __shfl_sync(0xffffffffu, a, 0);
+    const int64_t a_end = __shfl_sync(0xffffffffu, a1, last);
+    const int span = (int)(2 * (a_end - a_first));
+    const int off = (int)(2 * (a - a_first));
+    Fix fx;
+    fx.desc = 0ull; fx.fsel = 0u;
+    if (active) { fx.desc = s_desc[desc_index(cur)]; fx.fsel = s_fsel[desc_index(cur)]; }
+    face_pass<false>(p, tile, lane, valid, active, g, len, off, span, cur, fx, p.S + 4 * a_first);
+    face_pass<true>(p, tile, lane, valid, active, g, len, off, span, cur, fx, p.T + 4 * a_first);
+    cur = nxt;
+    r1a = r2a; r1b = r2b;
+    i0 = i1; i1 = i2; i2 = i3;
   }
-  const int len = (int)(a1 - a);
-  const unsigned vmask = __ballot_sync(0xffffffffu, valid);
-  if (vmask == 0) return;
-  const int last = 31 - __clz((int)vmask);
-  const int64_t a_first = __shfl_sync(0xffffffffu, a, 0);
-  const int64_t a_end = __shfl_sync(0xffffffffu, a1, last);
-  const int span = (int)(2 * (a_end - a_first));
-  const int off = (int)(2 * (a - a_first));
-  face_pass<false>(p, tile, lane, valid, active, g, len, off, span, it, p.S + 4 * a_first);
-  it.coef = eps_c;
-  face_pass<true>(p, tile, lane, valid, active, g, len, off, span, it, p.T + 4 * a_first);
   tile_store_wait(lane);
 }
 
@@ -466,13 +534,16 @@ int assemble_canonical_ST(const sfem_pattern_s* pat, const double* eps, const do
   const int64_t E = sp->E;
   const int64_t n_edge_rows = std::max<int64_t>(0, std::min(pat->ent_hi, E) - pat->ent_lo);
   const int64_t n_rows = pat->n_rows_ent;
+  int num_sms = 148;
+  SFEM_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, sp->device));
   if (n_edge_rows > 0) {
     p.r_begin = 0; p.r_end = n_edge_rows;
     p.tile_chunks = 16 * 2 * pat->max_row_len_edges;
     const size_t smem = (size_t)(kThreadsEdges / 32) * p.tile_chunks * sizeof(double2);
     SFEM_CHECK(smem <= 227 * 1024, "edge valence too high for the canonical kernel's shared-memory tile; use the generic kernel");
     SFEM_CUDA(cudaFuncSetAttribute(k_canon_edges, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const unsigned grid = (unsigned)((n_edge_rows + kThreadsEdges / 2 - 1) / (kThreadsEdges / 2));
+    const int64_t nblocks = (n_edge_rows + kThreadsEdges / 2 - 1) / (kThreadsEdges / 2);
+    const unsigned grid = (unsigned)std::min<int64_t>(nblocks, (int64_t)num_sms * SFEM_EDGE_CTAS);  // persistent
     k_canon_edges<<<grid, kThreadsEdges, smem, st>>>(p);
   }
   if (n_rows > n_edge_rows) {
@@ -482,7 +553,8 @@ int assemble_canonical_ST(const sfem_pattern_s* pat, const double* eps, const do
     p.tile_chunks = 16 * 2 * 16;
     const size_t smem = (size_t)(kThreadsFaces / 32) * p.tile_chunks * sizeof(double2);
     SFEM_CUDA(cudaFuncSetAttribute(k_canon_faces, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const unsigned grid = (unsigned)((n_rows - n_edge_rows + kThreadsFaces / 2 - 1) / (kThreadsFaces / 2));
+    const int64_t nblocks = (n_rows - n_edge_rows + kThreadsFaces / 2 - 1) / (kThreadsFaces / 2);
+    const unsigned grid = (unsigned)std::min<int64_t>(nblocks, (int64_t)num_sms * SFEM_FACE_CTAS);
     k_canon_faces<<<grid, kThreadsFaces, smem, st>>>(p);
   }
   SFEM_CUDA(cudaGetLastError());

@@ -22,7 +22,8 @@ constexpr int kCap = 1024;  // candidates per row entity (valence * entities per
 
 template <bool FILL>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
-k_pattern(SpaceView sv, const int64_t* __restrict__ inc_ptr, const int32_t* __restrict__ inc_cell,
+k_pattern(SpaceView sv, const int32_t* __restrict__ cells, const int64_t* __restrict__ inc_ptr,
+          const int32_t* __restrict__ inc_cell,
           const uint8_t* __restrict__ inc_loc, bool canon, int64_t ent_lo, int64_t n_rows, int64_t inc_base,
           int32_t* __restrict__ row_len,
           const int64_t* __restrict__ ent_rowptr, int32_t* __restrict__ ent_cols, uint16_t* __restrict__ pos,
@@ -74,15 +75,21 @@ k_pattern(SpaceView sv, const int64_t* __restrict__ inc_ptr, const int32_t* __re
   }
   const int64_t rp = ent_rowptr[r];
   for (int k = lane; k < nu; k += 32) ent_cols[rp + k] = cand[k];
-  // packed item records (order-2 tets): bytes 0-3 cell, 4 descriptor index into kRingDesc, 5-14 slots, 15 flags.
+  // packed 32-byte item records (order-2 tets): bytes 0-15 the cell's vertex ids in RELABELLED order, 16-19 cell,
+  // 20 descriptor index into kRingDesc, 21 flags, 22-31 slots of the 10 canonical column entities.
   // Face rows are written here (descriptor 12 + local face); edge rows by k_edge_ring in ring order.
   const bool rec_here = rec && g >= sv.E;
   if (rec_here)
     for (int i = lane; i < (int)(i1 - i0); i += 32) {
-      uint8_t* q = rec + (i0 - inc_base + i) * 16;
-      *reinterpret_cast<int32_t*>(q) = inc_cell[i0 + i];
-      q[4] = (uint8_t)(inc_loc[i0 + i] + 6);
-      q[15] = 0;
+      uint8_t* q = rec + (i0 - inc_base + i) * 32;
+      const int64_t c = inc_cell[i0 + i];
+      const int di = inc_loc[i0 + i] + 6;
+      const unsigned long long desc = kRingDesc[di];
+      for (int k = 0; k < 4; ++k)
+        reinterpret_cast<int32_t*>(q)[k] = cells[c * 4 + (int)((desc >> (2 * k)) & 3ull)];
+      reinterpret_cast<int32_t*>(q)[4] = (int32_t)c;
+      q[20] = (uint8_t)di;
+      q[21] = 0;
     }
   // slot of every (incidence, column entity) in the unique list.  Column entities are stored in the order the
   // value kernels visit them: for order-2 tets the CANONICAL order of the cell relabelled around the row entity
@@ -98,7 +105,7 @@ k_pattern(SpaceView sv, const int64_t* __restrict__ inc_ptr, const int32_t* __re
       if (cand[mid] < x) lo = mid + 1; else hi = mid;
     }
     pos[(i0 - inc_base) * nec + idx] = (uint16_t)lo;
-    if (rec_here) rec[(i0 - inc_base + i) * 16 + 5 + u_canon] = (uint8_t)lo;
+    if (rec_here) rec[(i0 - inc_base + i) * 32 + 22 + u_canon] = (uint8_t)lo;
   }
 }
 
@@ -106,8 +113,8 @@ k_pattern(SpaceView sv, const int64_t* __restrict__ inc_ptr, const int32_t* __re
 // Edge rows of order-2 tets: the cells around an edge are re-ordered into RING order (consecutive cells share a
 // face containing the edge), so that the value kernel can carry the contributions two neighbouring cells make to
 // their three common column entities in registers and store every CSR slot exactly once.  One thread per edge.
-// Output: packed records in ring order.  Record byte 4 = 2*t + swap (descriptor index, see canonical_lut.inc: the
-// cell is relabelled (a, b, entry, exit)), byte 15 = flags: 1 has_prev (shares its entry face with the previous
+// Output: packed 32-byte records in ring order.  Descriptor index = 2*t + swap (see canonical_lut.inc: the
+// cell is relabelled (a, b, entry, exit)), flags: 1 has_prev (shares its entry face with the previous
 // record), 2 has_next, 4 wrap (last cell of a closed ring: its exit face is the first cell's entry face).
 constexpr int kMaxRing = 64;
 __global__ void k_edge_ring(SpaceView sv, const int32_t* __restrict__ cells, const int64_t* __restrict__ inc_ptr,
@@ -177,9 +184,11 @@ __global__ void k_edge_ring(SpaceView sv, const int32_t* __restrict__ cells, con
       const int64_t c = inc_cell[i0 + cur];
       const int t = inc_loc[i0 + cur];
       const unsigned long long desc = kRingDesc[2 * t + swap];
-      uint8_t* q = rec + (i0 - inc_base + pos) * 16;
-      *reinterpret_cast<int32_t*>(q) = (int32_t)c;
-      q[4] = (uint8_t)(2 * t + swap);
+      uint8_t* q = rec + (i0 - inc_base + pos) * 32;
+      for (int k = 0; k < 4; ++k)
+        reinterpret_cast<int32_t*>(q)[k] = cells[c * 4 + (int)((desc >> (2 * k)) & 3ull)];
+      reinterpret_cast<int32_t*>(q)[4] = (int32_t)c;
+      q[20] = (uint8_t)(2 * t + swap);
       for (int u = 0; u < 10; ++u) {
         const int32_t x = sv.ent(c, (int)((desc >> (8 + 4 * u)) & 15ull));
         int lo = 0, hi = len - 1;
@@ -187,9 +196,9 @@ __global__ void k_edge_ring(SpaceView sv, const int32_t* __restrict__ cells, con
           const int mid = (lo + hi) >> 1;
           if (ent_cols[a + mid] < x) lo = mid + 1; else hi = mid;
         }
-        q[5 + u] = (uint8_t)lo;
+        q[22 + u] = (uint8_t)lo;
       }
-      q[15] = (uint8_t)flags;
+      q[21] = (uint8_t)flags;
       ++pos;
       if (nxt < 0) break;
       entry = exitv;
@@ -252,7 +261,7 @@ int build_pattern(sfem_pattern_s* pat, cudaStream_t st) {
   SFEM_CUDA(cudaMalloc(&pat->ent_rowptr, (n + 1) * 8));
   const unsigned grid = (unsigned)((n + kWarpsPerBlock - 1) / kWarpsPerBlock);
   if (n > 0)
-    k_pattern<false><<<grid, kWarpsPerBlock * 32, 0, st>>>(sv, sp->inc_ptr, sp->inc_cell, sp->inc_loc, canon, pat->ent_lo, n,
+    k_pattern<false><<<grid, kWarpsPerBlock * 32, 0, st>>>(sv, sp->mesh->cells, sp->inc_ptr, sp->inc_cell, sp->inc_loc, canon, pat->ent_lo, n,
                                                            pat->inc_base, row_len, nullptr, nullptr, nullptr,
                                                            nullptr, overflow);
   k_len_to_i64<<<grid_for(n + 1), 256, 0, st>>>(row_len, len64, n);
@@ -287,9 +296,9 @@ int build_pattern(sfem_pattern_s* pat, cudaStream_t st) {
   pat->max_row_len = std::max(h_max2[0], h_max2[1]);
   SFEM_CUDA(cudaMalloc(&pat->ent_cols, std::max<int64_t>(pat->nnz_ent, 1) * 4));
   SFEM_CUDA(cudaMalloc(&pat->pos, std::max<int64_t>(pat->n_inc_block * sp->n_ent_cell, 1) * 2));
-  if (canon && pat->max_row_len <= 255) SFEM_CUDA(cudaMalloc(&pat->rec, std::max<int64_t>(pat->n_inc_block, 1) * 16));
+  if (canon && pat->max_row_len <= 255) SFEM_CUDA(cudaMalloc(&pat->rec, std::max<int64_t>(pat->n_inc_block, 1) * 32));
   if (n > 0)
-    k_pattern<true><<<grid, kWarpsPerBlock * 32, 0, st>>>(sv, sp->inc_ptr, sp->inc_cell, sp->inc_loc, canon, pat->ent_lo, n,
+    k_pattern<true><<<grid, kWarpsPerBlock * 32, 0, st>>>(sv, sp->mesh->cells, sp->inc_ptr, sp->inc_cell, sp->inc_loc, canon, pat->ent_lo, n,
                                                           pat->inc_base, nullptr, pat->ent_rowptr, pat->ent_cols,
                                                           pat->pos, reinterpret_cast<uint8_t*>(pat->rec), overflow);
   pat->ring_ok = false;

@@ -104,7 +104,8 @@ struct sfem_pattern_s {
   int32_t* ent_cols = nullptr;    // [nnz_ent] global entity ids, ascending within a row
   uint16_t* pos = nullptr;        // [n_inc_block][n_ent_cell]: slot of the cell's u-th column entity in the row
                                   // (u in canonical order when pos_is_canonical(space))
-  uint4* rec = nullptr;           // [n_inc_block] packed {cell, t, 10 uint8 slots} (order-2 tets, rows <= 255 entities)
+  uint4* rec = nullptr;           // [n_inc_block][2] packed 32-byte item records {relabelled vertex ids, cell,
+                                  // descriptor, flags, 10 uint8 slots} (order-2 tets, rows <= 255 entities)
   bool ring_ok = false;           // edge records are in ring order (manifold edges of bounded valence)
   int64_t inc_base = 0;           // = space->inc_ptr[ent_lo]
   int64_t n_inc_block = 0;
