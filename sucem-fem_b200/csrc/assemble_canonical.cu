@@ -59,14 +59,23 @@ struct Item {
   uint32_t w1, w2, w3;  // record bytes 20..31: descriptor index, flags, slots[10]
 };
 
+// the part of an item that outlives its coordinates: slots, flags, descriptor index
+struct Slots {
+  uint32_t w1, w2, w3;
+};
+__device__ __forceinline__ Slots slots_of(const Item& it) {
+  Slots s;
+  s.w1 = it.w1; s.w2 = it.w2; s.w3 = it.w3;
+  return s;
+}
 template <int U>
-__device__ __forceinline__ int slot_of(const Item& it) {
+__device__ __forceinline__ int slot_of(const Slots& it) {
   if constexpr (U < 2) return (it.w1 >> (16 + 8 * U)) & 0xffu;
   else if constexpr (U < 6) return (it.w2 >> (8 * (U - 2))) & 0xffu;
   else return (it.w3 >> (8 * (U - 6))) & 0xffu;
 }
-__device__ __forceinline__ unsigned flags_of(const Item& it) { return (it.w1 >> 8) & 0xffu; }
-__device__ __forceinline__ unsigned desc_index(const Item& it) { return it.w1 & 0xffu; }
+__device__ __forceinline__ unsigned flags_of(const Slots& it) { return (it.w1 >> 8) & 0xffu; }
+__device__ __forceinline__ unsigned desc_index(const Slots& it) { return it.w1 & 0xffu; }
 
 // last hop of the gather chain: coordinates + coefficients, from the record (vertex ids already relabelled)
 __device__ __forceinline__ void gather_item(const CanonArgs& p, uint4 ra, uint4 rb, Item& it) {
@@ -139,6 +148,9 @@ struct Fix {
 // true-frame values of the 2 columns of canonical column entity U, from canonical-frame values (v0, v1)
 template <int U>
 __device__ __forceinline__ double2 fix_columns(const Fix& f, double v0, double v1) {
+#ifdef SFEM_NOFIX  // timing experiment only: wrong results
+  return make_double2(v0, v1);
+#endif
   if constexpr (U < 6) {
     const bool flip = (f.desc >> (48 + U)) & 1ull;
     return flip ? make_double2(-v1, -v0) : make_double2(v0, v1);
@@ -191,8 +203,14 @@ __device__ __forceinline__ void stage_lut(unsigned long long* s_desc, unsigned* 
 #ifndef SFEM_FACE_CTAS
 #define SFEM_FACE_CTAS 2
 #endif
-constexpr int kThreadsEdges = 128;  // 4 warps x 16 edges; CTAs per SM are bounded by the shared-memory tiles
-constexpr int kThreadsFaces = 128;  // 4 warps x 16 faces
+#ifndef SFEM_EDGE_THREADS
+#define SFEM_EDGE_THREADS 128
+#endif
+#ifndef SFEM_FACE_THREADS
+#define SFEM_FACE_THREADS 128
+#endif
+constexpr int kThreadsEdges = SFEM_EDGE_THREADS;  // warps x 16 edges; CTAs per SM are bounded by tiles and registers
+constexpr int kThreadsFaces = SFEM_FACE_THREADS;  // warps x 16 faces
 
 __device__ __forceinline__ double2 shfl_xor1(double2 v) {
   return make_double2(__shfl_xor_sync(0xffffffffu, v.x, 1), __shfl_xor_sync(0xffffffffu, v.y, 1));
@@ -235,7 +253,7 @@ template <bool MASS>
 __device__ __forceinline__ void edge_pass(const CanonArgs& p, const unsigned long long* __restrict__ s_desc,
                                           const unsigned* __restrict__ s_fsel, double2* __restrict__ tile, int lane,
                                           const EdgeMeta& m, int64_t g, int off, int span, int nsteps,
-                                          Item& cur, Item& nxt, uint4& rc1a, uint4& rc1b,
+                                          Item& cur, uint4& rc1a, uint4& rc1b,
                                           int64_t nf, int64_t nf_end, double* __restrict__ out_first) {
   // cur: this lane's first item (loaded or in flight); rc1: record of its second item; [nf, nf_end): this lane's
   // record range in the next pass (nf = first item; nf >= nf_end: none)
@@ -259,30 +277,32 @@ __device__ __forceinline__ void edge_pass(const CanonArgs& p, const unsigned lon
 #pragma unroll 1
   for (int s = 0; s < nsteps; ++s, i += 2) {
     const bool active = valid && i < m.i1;
-    uint4 rc2a = make_uint4(0, 0, 0, 0), rc2b = rc2a;
-    if (s + 1 < nsteps) {
-      // this lane's next item of the pass (record two ahead)
-      if (i + 2 < m.i1) {
-        if (i + 4 < m.i1) { rc2a = rec[2 * (i + 4)]; rc2b = rec[2 * (i + 4) + 1]; }
-        gather_item(p, rc1a, rc1b, nxt);
-      }
-    } else {
-      // last step: the first item of the next pass, and the record of its second item
-      if (nf < nf_end) {
-        if (nf + 2 < nf_end) { rc2a = rec[2 * (nf + 2)]; rc2b = rec[2 * (nf + 2) + 1]; }
-        gather_item(p, rfa, rfb, nxt);
-      }
-    }
-    const unsigned flags = active ? flags_of(cur) : 0u;
+    // everything that is needed from the current item; its buffer is then free for the next one
+    const Slots sl = slots_of(cur);
+    const unsigned flags = active ? flags_of(sl) : 0u;
     const bool has_prev = flags & 1u, has_next = flags & 2u, wrap = flags & 4u;
     double gm[6], o[20];
     Fix fx;
     fx.desc = 0ull; fx.fsel = 0u;
     if (active) {
       canon_geometry<MASS>(cur, gm);
-      fx.desc = s_desc[desc_index(cur)];
-      fx.fsel = s_fsel[desc_index(cur)];
-      if (s == 0 && h == 0) self_slot = slot_of<5>(cur);
+      fx.desc = s_desc[desc_index(sl)];
+      fx.fsel = s_fsel[desc_index(sl)];
+      if (s == 0 && h == 0) self_slot = slot_of<5>(sl);
+    }
+    uint4 rc2a = make_uint4(0, 0, 0, 0), rc2b = rc2a;
+    if (s + 1 < nsteps) {
+      // this lane's next item of the pass (record two ahead)
+      if (i + 2 < m.i1) {
+        if (i + 4 < m.i1) { rc2a = rec[2 * (i + 4)]; rc2b = rec[2 * (i + 4) + 1]; }
+        gather_item(p, rc1a, rc1b, cur);
+      }
+    } else {
+      // last step: the first item of the next pass, and the record of its second item
+      if (nf < nf_end) {
+        if (nf + 2 < nf_end) { rc2a = rec[2 * (nf + 2)]; rc2b = rec[2 * (nf + 2) + 1]; }
+        gather_item(p, rfa, rfb, cur);
+      }
     }
     __syncwarp();
 #define SFEM_RING_ROW(K, FN)                                                                       \
@@ -303,21 +323,21 @@ __device__ __forceinline__ void edge_pass(const CanonArgs& p, const unsigned lon
         double2 r;                                                                                 \
         r = fix_columns<5>(fx, o[10], o[11]); self[K].x += r.x; self[K].y += r.y;                  \
         r = fix_columns<4>(fx, o[8], o[9]);                                                        \
-        if (has_prev) { r.x += c4.x; r.y += c4.y; }                                                \
-        row[slot_of<4>(cur)] = r;                                                                  \
+        r.x += has_prev ? c4.x : 0.0; r.y += has_prev ? c4.y : 0.0;                                \
+        row[slot_of<4>(sl)] = r;                                                                  \
         r = fix_columns<2>(fx, o[4], o[5]);                                                        \
-        if (has_prev) { r.x += c2.x; r.y += c2.y; }                                                \
-        row[slot_of<2>(cur)] = r;                                                                  \
+        r.x += has_prev ? c2.x : 0.0; r.y += has_prev ? c2.y : 0.0;                                \
+        row[slot_of<2>(sl)] = r;                                                                  \
         r = fix_columns<9>(fx, o[18], o[19]);                                                      \
-        if (has_prev) { r.x += c9.x; r.y += c9.y; }                                                \
-        row[slot_of<9>(cur)] = r;                                                                  \
-        row[slot_of<0>(cur)] = fix_columns<0>(fx, o[0], o[1]);                                     \
-        row[slot_of<7>(cur)] = fix_columns<7>(fx, o[14], o[15]);                                   \
-        row[slot_of<6>(cur)] = fix_columns<6>(fx, o[12], o[13]);                                   \
+        r.x += has_prev ? c9.x : 0.0; r.y += has_prev ? c9.y : 0.0;                                \
+        row[slot_of<9>(sl)] = r;                                                                  \
+        row[slot_of<0>(sl)] = fix_columns<0>(fx, o[0], o[1]);                                     \
+        row[slot_of<7>(sl)] = fix_columns<7>(fx, o[14], o[15]);                                   \
+        row[slot_of<6>(sl)] = fix_columns<6>(fx, o[12], o[13]);                                   \
         if (!has_next) {                                                                           \
-          double2* q3 = row + slot_of<3>(cur);                                                     \
-          double2* q1 = row + slot_of<1>(cur);                                                     \
-          double2* q8 = row + slot_of<8>(cur);                                                     \
+          double2* q3 = row + slot_of<3>(sl);                                                     \
+          double2* q1 = row + slot_of<1>(sl);                                                     \
+          double2* q8 = row + slot_of<8>(sl);                                                     \
           if (wrap) {                                                                              \
             const double2 t3 = *q3, t1 = *q1, t8 = *q8;                                            \
             n3.x += t3.x; n3.y += t3.y; n1.x += t1.x; n1.y += t1.y; n8.x += t8.x; n8.y += t8.y;    \
@@ -334,7 +354,6 @@ __device__ __forceinline__ void edge_pass(const CanonArgs& p, const unsigned lon
       SFEM_RING_ROW(1, canon_edge_curl_k1)
     }
 #undef SFEM_RING_ROW
-    cur = nxt;
     rc1a = rc2a; rc1b = rc2b;
   }
   // the row edge's own block: both lanes' partial sums, stored by the even lane
@@ -366,7 +385,7 @@ __global__ void __launch_bounds__(kThreadsEdges, SFEM_EDGE_CTAS) k_canon_edges(C
   if (b >= nb) return;
   // prologue: this lane's first item and the record of its second one
   EdgeMeta m = load_edge_meta(p, b, lane);
-  Item cur, nxt;
+  Item cur;
   uint4 rc1a = make_uint4(0, 0, 0, 0), rc1b = rc1a;
   {
     const int64_t i = m.i0 + h;
@@ -391,9 +410,9 @@ __global__ void __launch_bounds__(kThreadsEdges, SFEM_EDGE_CTAS) k_canon_edges(C
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) nsteps = max(nsteps, __shfl_xor_sync(0xffffffffu, nsteps, o));
     const int64_t g = p.ent_lo + p.r_begin + b * 16 + (lane >> 1);
-    edge_pass<false>(p, s_desc, s_fsel, tile, lane, m, g, off, span, nsteps, cur, nxt, rc1a, rc1b, m.i0 + h, m.i1,
+    edge_pass<false>(p, s_desc, s_fsel, tile, lane, m, g, off, span, nsteps, cur, rc1a, rc1b, m.i0 + h, m.i1,
                      p.S + 4 * a_first);
-    edge_pass<true>(p, s_desc, s_fsel, tile, lane, m, g, off, span, nsteps, cur, nxt, rc1a, rc1b, mn.i0 + h, mn.i1,
+    edge_pass<true>(p, s_desc, s_fsel, tile, lane, m, g, off, span, nsteps, cur, rc1a, rc1b, mn.i0 + h, mn.i1,
                     p.T + 4 * a_first);
     m = mn;
   }
@@ -405,13 +424,12 @@ __global__ void __launch_bounds__(kThreadsEdges, SFEM_EDGE_CTAS) k_canon_edges(C
 // fix-up): the odd lane hands its values over by shuffle and the even lane stores the sums.
 template <bool MASS>
 __device__ __forceinline__ void face_pass(const CanonArgs& p, double2* __restrict__ tile, int lane, bool valid,
-                                          bool active, int64_t g, int len, int off, int span, const Item& it,
-                                          const Fix& fx, double* __restrict__ out_first) {
+                                          bool active, int64_t g, int len, int off, int span, const Slots& it,
+                                          const double (&gm)[6], const Fix& fx, double* __restrict__ out_first) {
   const int h = lane & 1;
   tile_store_wait(lane);
   double2* row0 = tile + off;
-  double gm[6], o[20];
-  if (active) canon_geometry<MASS>(it, gm);
+  double o[20];
 #define SFEM_FACE_ROW(K, FN)                                                                              \
   {                                                                                                       \
     double2 s2 = make_double2(0.0, 0.0), s4 = s2, s5 = s2, s9 = s2;                                       \
@@ -472,7 +490,7 @@ __global__ void __launch_bounds__(kThreadsFaces, SFEM_FACE_CTAS) k_canon_faces(C
   const int64_t W = (int64_t)gridDim.x * (kThreadsFaces / 32);
   int64_t b = blockIdx.x * (int64_t)(kThreadsFaces / 32) + w;
   if (b >= nb) return;
-  Item cur, nxt;
+  Item cur;
   int64_t i0 = face_item_index(p, b, nb, lane);
   int64_t i1 = face_item_index(p, b + W, nb, lane);
   int64_t i2 = face_item_index(p, b + 2 * W, nb, lane);
@@ -485,11 +503,22 @@ __global__ void __launch_bounds__(kThreadsFaces, SFEM_FACE_CTAS) k_canon_faces(C
     const int64_t i3 = face_item_index(p, b + 3 * W, nb, lane);
     uint4 r2a = make_uint4(0, 0, 0, 0), r2b = r2a;
     if (i2 >= 0) { r2a = p.rec[2 * i2]; r2b = p.rec[2 * i2 + 1]; }
-    if (i1 >= 0) gather_item(p, r1a, r1b, nxt);
+    // everything that is needed from the current item, then its buffer receives the next batch's
+    const bool active = i0 >= 0;
+    const Slots sl = slots_of(cur);
+    double gS[6], gT[6];
+    Fix fx;
+    fx.desc = 0ull; fx.fsel = 0u;
+    if (active) {
+      canon_geometry<false>(cur, gS);
+      canon_geometry<true>(cur, gT);
+      fx.desc = s_desc[desc_index(sl)];
+      fx.fsel = s_fsel[desc_index(sl)];
+    }
+    if (i1 >= 0) gather_item(p, r1a, r1b, cur);
     // current batch
     const int64_t r = p.r_begin + b * 16 + (lane >> 1);
     const bool valid = r < p.r_end;
-    const bool active = i0 >= 0;
     int64_t a = 0, a1 = 0;
     if (valid) { a = p.ent_rowptr[r]; a1 = p.ent_rowptr[r + 1]; }
     const int64_t g = p.ent_lo + r;
@@ -500,12 +529,8 @@ __global__ void __launch_bounds__(kThreadsFaces, SFEM_FACE_CTAS) k_canon_faces(C
     const int64_t a_end = __shfl_sync(0xffffffffu, a1, last);
     const int span = (int)(2 * (a_end - a_first));
     const int off = (int)(2 * (a - a_first));
-    Fix fx;
-    fx.desc = 0ull; fx.fsel = 0u;
-    if (active) { fx.desc = s_desc[desc_index(cur)]; fx.fsel = s_fsel[desc_index(cur)]; }
-    face_pass<false>(p, tile, lane, valid, active, g, len, off, span, cur, fx, p.S + 4 * a_first);
-    face_pass<true>(p, tile, lane, valid, active, g, len, off, span, cur, fx, p.T + 4 * a_first);
-    cur = nxt;
+    face_pass<false>(p, tile, lane, valid, active, g, len, off, span, sl, gS, fx, p.S + 4 * a_first);
+    face_pass<true>(p, tile, lane, valid, active, g, len, off, span, sl, gT, fx, p.T + 4 * a_first);
     r1a = r2a; r1b = r2b;
     i0 = i1; i1 = i2; i2 = i3;
   }
