@@ -197,8 +197,12 @@ def main():
     ms_local = ms
     if sampler:
         sampler.stop_flag = True
+    per_rank_ms = [ms_local / K]
     if world > 1:
         t = torch.tensor([ms], dtype=torch.float64, device='cuda')
+        allt = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(allt, t)
+        per_rank_ms = [float(x.item()) / K for x in allt]
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
     ms_step = ms / K
@@ -232,7 +236,8 @@ def main():
                        "partition": "rows by DOF-entity ownership, %d block(s), ghost cells duplicated" % world,
                        "l2": "outputs per step (%.1f GB) exceed L2; no flush needed" % (16e-9 * pat.nnz),
                        "kernel": {0: "auto", 1: "generic", 2: "canonical"}[kernel]},
-            "setup_ms": setup_ms, "roofline": roofline, "gpu_launches": None}
+            "setup_ms": setup_ms, "roofline": roofline, "gpu_launches": None,
+            "per_rank_ms_per_step": [round(x, 3) for x in per_rank_ms]}
 
     # ---- e2e through the public API with HOST buffers (rank-local; N=1 only measures the full pipeline) ---
     if not args.no_e2e and world == 1:

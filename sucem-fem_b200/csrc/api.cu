@@ -127,9 +127,9 @@ __global__ void k_cell_dofs(SpaceView sv, int q, int64_t C, int32_t* __restrict_
 }
 
 // Row partitioning: weight of an entity row = its number of incident cells (proportional to its nnz and to the work
-// of the value kernels), edge rows weighted kEdgeWeight/16 times a face row's incidence (edges visit their cells in a
-// dependent ring and cost measurably more per incidence: 9.3 ms / 6C vs 5.2 ms / 4C on UnitCube(119)).
-constexpr int64_t kEdgeWeight16 = 19;  // 19/16 = 1.19
+// of the value kernels); edge rows can be weighted kEdgeWeight16/16 relative to face rows (edges visit their cells in a
+// dependent ring, faces write more bytes per incidence).
+constexpr int64_t kEdgeWeight16 = 16;  // measured equal per incidence with the current kernels (r1: 1.71 ms / 6C vs 1.13 ms / 4C at n = 70)
 __device__ __forceinline__ __int128 row_weight_prefix(const int64_t* __restrict__ inc_ptr, int64_t E, int64_t g) {
   const __int128 e = (__int128)(inc_ptr[g < E ? g : E] - inc_ptr[0]) * kEdgeWeight16;
   const __int128 f = g > E ? (__int128)(inc_ptr[g] - inc_ptr[E]) * 16 : 0;
