@@ -145,15 +145,17 @@ struct Fix {
   unsigned fsel;
 };
 
-// true-frame values of the 2 columns of canonical column entity U, from canonical-frame values (v0, v1)
-template <int U>
+// true-frame values of the 2 columns of canonical column entity U, from the canonical-frame values the generated row
+// functions produce: (v0, v1) for faces and for edges that are never seen reversed (DM = false); for the other edges
+// (d, m) = ((v0 - v1)/2, (v0 + v1)/2), where a reversed edge only flips the sign of m (tools/gen_canonical.py).
+template <int U, bool DM = false>
 __device__ __forceinline__ double2 fix_columns(const Fix& f, double v0, double v1) {
-#ifdef SFEM_NOFIX  // timing experiment only: wrong results
-  return make_double2(v0, v1);
-#endif
-  if constexpr (U < 6) {
-    const bool flip = (f.desc >> (48 + U)) & 1ull;
-    return flip ? make_double2(-v1, -v0) : make_double2(v0, v1);
+  if constexpr (U < 6 && DM) {
+    const unsigned sign = ((unsigned)(f.desc >> 32) << (15 - U)) & 0x80000000u;  // descriptor bit 48 + U -> bit 31
+    const double sm = __hiloint2double(__double2hiint(v1) ^ (int)sign, __double2loint(v1));
+    return make_double2(sm + v0, sm - v0);
+  } else if constexpr (U < 6) {
+    return make_double2(v0, v1);
   } else {
     const unsigned nib = (f.fsel >> (4 * (U - 6))) & 15u;
     const double w = -(v0 + v1);
@@ -179,10 +181,16 @@ __device__ __forceinline__ void tile_store_wait(int lane) {
   __syncwarp();
 }
 
-__device__ __forceinline__ void pec_overwrite(const CanonArgs& p, double2* __restrict__ row0, int64_t g, int len, int self) {
+// pecbits: bit k set <=> dof row (entity, k) is Dirichlet-constrained (loaded at the start of the batch)
+__device__ __forceinline__ unsigned load_pecbits(const CanonArgs& p, int64_t g, bool valid) {
+  if (!p.pec || !valid) return 0u;
+  const uchar2 f = *reinterpret_cast<const uchar2*>(p.pec + 2 * g);
+  return (f.x ? 1u : 0u) | (f.y ? 2u : 0u);
+}
+__device__ __forceinline__ void pec_overwrite(unsigned pecbits, double2* __restrict__ row0, int len, int self) {
 #pragma unroll
   for (int k = 0; k < 2; ++k)
-    if (p.pec[2 * g + k]) {
+    if ((pecbits >> k) & 1u) {
       double2* row = row0 + k * len;
       for (int s = 0; s < len; ++s) row[s] = make_double2(0.0, 0.0);
       row[self] = k == 0 ? make_double2(1.0, 0.0) : make_double2(0.0, 1.0);
@@ -252,7 +260,7 @@ __device__ __forceinline__ EdgeMeta load_edge_meta(const CanonArgs& p, int64_t b
 template <bool MASS>
 __device__ __forceinline__ void edge_pass(const CanonArgs& p, const unsigned long long* __restrict__ s_desc,
                                           const unsigned* __restrict__ s_fsel, double2* __restrict__ tile, int lane,
-                                          const EdgeMeta& m, int64_t g, int off, int span, int nsteps,
+                                          const EdgeMeta& m, unsigned pecbits, int off, int span, int nsteps,
                                           Item& cur, uint4& rc1a, uint4& rc1b,
                                           int64_t nf, int64_t nf_end, double* __restrict__ out_first) {
   // cur: this lane's first item (loaded or in flight); rc1: record of its second item; [nf, nf_end): this lane's
@@ -310,8 +318,8 @@ __device__ __forceinline__ void edge_pass(const CanonArgs& p, const unsigned lon
       double2 n3 = make_double2(0.0, 0.0), n1 = n3, n8 = n3;                                       \
       if (active) {                                                                                \
         FN(gm, o);                                                                                 \
-        n3 = fix_columns<3>(fx, o[6], o[7]);                                                       \
-        n1 = fix_columns<1>(fx, o[2], o[3]);                                                       \
+        n3 = fix_columns<3, true>(fx, o[6], o[7]);                                                       \
+        n1 = fix_columns<1, true>(fx, o[2], o[3]);                                                       \
         n8 = fix_columns<8>(fx, o[16], o[17]);                                                     \
       }                                                                                            \
       /* hand the next-side blocks to the partner, which owns the next cell of the ring */         \
@@ -322,16 +330,16 @@ __device__ __forceinline__ void edge_pass(const CanonArgs& p, const unsigned lon
         double2* row = row0 + K * len;                                                             \
         double2 r;                                                                                 \
         r = fix_columns<5>(fx, o[10], o[11]); self[K].x += r.x; self[K].y += r.y;                  \
-        r = fix_columns<4>(fx, o[8], o[9]);                                                        \
+        r = fix_columns<4, true>(fx, o[8], o[9]);                                                        \
         r.x += has_prev ? c4.x : 0.0; r.y += has_prev ? c4.y : 0.0;                                \
         row[slot_of<4>(sl)] = r;                                                                  \
-        r = fix_columns<2>(fx, o[4], o[5]);                                                        \
+        r = fix_columns<2, true>(fx, o[4], o[5]);                                                        \
         r.x += has_prev ? c2.x : 0.0; r.y += has_prev ? c2.y : 0.0;                                \
         row[slot_of<2>(sl)] = r;                                                                  \
         r = fix_columns<9>(fx, o[18], o[19]);                                                      \
         r.x += has_prev ? c9.x : 0.0; r.y += has_prev ? c9.y : 0.0;                                \
         row[slot_of<9>(sl)] = r;                                                                  \
-        row[slot_of<0>(sl)] = fix_columns<0>(fx, o[0], o[1]);                                     \
+        row[slot_of<0>(sl)] = fix_columns<0, true>(fx, o[0], o[1]);                                     \
         row[slot_of<7>(sl)] = fix_columns<7>(fx, o[14], o[15]);                                   \
         row[slot_of<6>(sl)] = fix_columns<6>(fx, o[12], o[13]);                                   \
         if (!has_next) {                                                                           \
@@ -367,7 +375,7 @@ __device__ __forceinline__ void edge_pass(const CanonArgs& p, const unsigned lon
   if (valid && h == 0) {
     row0[self_slot] = self[0];
     row0[len + self_slot] = self[1];
-    if (p.pec) pec_overwrite(p, row0, g, len, self_slot);
+    if (pecbits) pec_overwrite(pecbits, row0, len, self_slot);
   }
   tile_store_issue(tile, out_first, (unsigned)span * 16u, lane);
 }
@@ -409,10 +417,10 @@ __global__ void __launch_bounds__(kThreadsEdges, SFEM_EDGE_CTAS) k_canon_edges(C
     int nsteps = valid ? (int)((m.i1 - m.i0 + 1) >> 1) : 0;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) nsteps = max(nsteps, __shfl_xor_sync(0xffffffffu, nsteps, o));
-    const int64_t g = p.ent_lo + p.r_begin + b * 16 + (lane >> 1);
-    edge_pass<false>(p, s_desc, s_fsel, tile, lane, m, g, off, span, nsteps, cur, rc1a, rc1b, m.i0 + h, m.i1,
+    const unsigned pecbits = load_pecbits(p, p.ent_lo + p.r_begin + b * 16 + (lane >> 1), valid);
+    edge_pass<false>(p, s_desc, s_fsel, tile, lane, m, pecbits, off, span, nsteps, cur, rc1a, rc1b, m.i0 + h, m.i1,
                      p.S + 4 * a_first);
-    edge_pass<true>(p, s_desc, s_fsel, tile, lane, m, g, off, span, nsteps, cur, rc1a, rc1b, mn.i0 + h, mn.i1,
+    edge_pass<true>(p, s_desc, s_fsel, tile, lane, m, pecbits, off, span, nsteps, cur, rc1a, rc1b, mn.i0 + h, mn.i1,
                     p.T + 4 * a_first);
     m = mn;
   }
@@ -424,7 +432,7 @@ __global__ void __launch_bounds__(kThreadsEdges, SFEM_EDGE_CTAS) k_canon_edges(C
 // fix-up): the odd lane hands its values over by shuffle and the even lane stores the sums.
 template <bool MASS>
 __device__ __forceinline__ void face_pass(const CanonArgs& p, double2* __restrict__ tile, int lane, bool valid,
-                                          bool active, int64_t g, int len, int off, int span, const Slots& it,
+                                          bool active, unsigned pecbits, int len, int off, int span, const Slots& it,
                                           const double (&gm)[6], const Fix& fx, double* __restrict__ out_first) {
   const int h = lane & 1;
   tile_store_wait(lane);
@@ -441,9 +449,9 @@ __device__ __forceinline__ void face_pass(const CanonArgs& p, double2* __restric
     const double2 t2 = shfl_xor1(s2), t4 = shfl_xor1(s4), t5 = shfl_xor1(s5), t9 = shfl_xor1(s9);         \
     if (active) {                                                                                         \
       double2* row = row0 + K * len;                                                                      \
-      row[slot_of<0>(it)] = fix_columns<0>(fx, o[0], o[1]);                                               \
-      row[slot_of<1>(it)] = fix_columns<1>(fx, o[2], o[3]);                                               \
-      row[slot_of<3>(it)] = fix_columns<3>(fx, o[6], o[7]);                                               \
+      row[slot_of<0>(it)] = fix_columns<0, true>(fx, o[0], o[1]);                                               \
+      row[slot_of<1>(it)] = fix_columns<1, true>(fx, o[2], o[3]);                                               \
+      row[slot_of<3>(it)] = fix_columns<3, true>(fx, o[6], o[7]);                                               \
       row[slot_of<6>(it)] = fix_columns<6>(fx, o[12], o[13]);                                             \
       row[slot_of<7>(it)] = fix_columns<7>(fx, o[14], o[15]);                                             \
       row[slot_of<8>(it)] = fix_columns<8>(fx, o[16], o[17]);                                             \
@@ -464,7 +472,7 @@ __device__ __forceinline__ void face_pass(const CanonArgs& p, double2* __restric
   }
 #undef SFEM_FACE_ROW
   __syncwarp();
-  if (valid && h == 0 && p.pec) pec_overwrite(p, row0, g, len, slot_of<9>(it));  // canonical 9 = the row face
+  if (valid && h == 0 && pecbits) pec_overwrite(pecbits, row0, len, slot_of<9>(it));  // canonical 9 = the row face
   tile_store_issue(tile, out_first, (unsigned)span * 16u, lane);
 }
 
@@ -497,6 +505,12 @@ __global__ void __launch_bounds__(kThreadsFaces, SFEM_FACE_CTAS) k_canon_faces(C
   uint4 r1a = make_uint4(0, 0, 0, 0), r1b = r1a;
   if (i0 >= 0) gather_item(p, p.rec[2 * i0], p.rec[2 * i0 + 1], cur);
   if (i1 >= 0) { r1a = p.rec[2 * i1]; r1b = p.rec[2 * i1 + 1]; }
+  // row pointers of this lane's face, one batch ahead as well
+  int64_t a = 0, a1 = 0;
+  {
+    const int64_t r = p.r_begin + b * 16 + (lane >> 1);
+    if (r < p.r_end) { a = p.ent_rowptr[r]; a1 = p.ent_rowptr[r + 1]; }
+  }
 #pragma unroll 1
   for (; b < nb; b += W) {
     // stage 3 / 2 / 1 of the batches ahead
@@ -519,9 +533,12 @@ __global__ void __launch_bounds__(kThreadsFaces, SFEM_FACE_CTAS) k_canon_faces(C
     // current batch
     const int64_t r = p.r_begin + b * 16 + (lane >> 1);
     const bool valid = r < p.r_end;
-    int64_t a = 0, a1 = 0;
-    if (valid) { a = p.ent_rowptr[r]; a1 = p.ent_rowptr[r + 1]; }
-    const int64_t g = p.ent_lo + r;
+    int64_t an = 0, a1n = 0;
+    {
+      const int64_t rn = r + W * 16;
+      if (b + W < nb && rn < p.r_end) { an = p.ent_rowptr[rn]; a1n = p.ent_rowptr[rn + 1]; }
+    }
+    const unsigned pecbits = load_pecbits(p, p.ent_lo + r, valid);
     const int len = (int)(a1 - a);
     const unsigned vmask = __ballot_sync(0xffffffffu, valid);
     const int last = 31 - __clz((int)vmask);
@@ -529,10 +546,11 @@ __global__ void __launch_bounds__(kThreadsFaces, SFEM_FACE_CTAS) k_canon_faces(C
     const int64_t a_end = __shfl_sync(0xffffffffu, a1, last);
     const int span = (int)(2 * (a_end - a_first));
     const int off = (int)(2 * (a - a_first));
-    face_pass<false>(p, tile, lane, valid, active, g, len, off, span, sl, gS, fx, p.S + 4 * a_first);
-    face_pass<true>(p, tile, lane, valid, active, g, len, off, span, sl, gT, fx, p.T + 4 * a_first);
+    face_pass<false>(p, tile, lane, valid, active, pecbits, len, off, span, sl, gS, fx, p.S + 4 * a_first);
+    face_pass<true>(p, tile, lane, valid, active, pecbits, len, off, span, sl, gT, fx, p.T + 4 * a_first);
     r1a = r2a; r1b = r2b;
     i0 = i1; i1 = i2; i2 = i3;
+    a = an; a1 = a1n;
   }
   tile_store_wait(lane);
 }

@@ -91,13 +91,23 @@ def pack_descriptor(rowtype, t, swap=0):
     return d, hi
 
 
-def emit_rows(name, table, row, coefs):
+# Column EDGE entities that a relabelled cell can see reversed are emitted in the (d, m) = ((v0 - v1)/2, (v0 + v1)/2)
+# basis: reversing an edge maps (v0, v1) -> (-v1, -v0), i.e. d -> d, m -> -m, so the kernel's fix-up is one sign flip
+# and two adds (v0 = m + d, v1 = m - d) instead of a swap-and-negate of two doubles.
+DM_ENTITIES = {'edge': (0, 1, 2, 3, 4), 'face': (0, 1, 3)}
+
+
+def emit_rows(name, table, row, coefs, dm=()):
     """o[j] = sum_p table[row][j][p] * g[p]; coefficients referenced from the __constant__ pool kCanonCoef so that
     they become constant-bank operands of the DFMAs (literals would be materialised through UMOV pairs)."""
     out = '__device__ __forceinline__ void %s(const double (&g)[6], double (&o)[20]) {\n' % name
     nterms = 0
+    tab = np.array(table[row], dtype=np.float64)
+    for u in dm:
+        v0, v1 = tab[2 * u].copy(), tab[2 * u + 1].copy()
+        tab[2 * u], tab[2 * u + 1] = 0.5 * (v0 - v1), 0.5 * (v0 + v1)
     for j in range(20):
-        terms = [(p, table[row, j, p]) for p in range(6) if table[row, j, p] != 0.0]
+        terms = [(p, tab[j, p]) for p in range(6) if tab[j, p] != 0.0]
         nterms += len(terms)
         if not terms:
             out += '  o[%d] = 0.0;\n' % j
@@ -121,7 +131,7 @@ def main():
     for nm, tab in (('mass', mass), ('curl', curl)):
         for rt, rows in (('edge', (10, 11)), ('face', (18, 19))):
             for k, row in enumerate(rows):
-                code, n = emit_rows('canon_%s_%s_k%d' % (rt, nm, k), tab, row, coefs)
+                code, n = emit_rows('canon_%s_%s_k%d' % (rt, nm, k), tab, row, coefs, DM_ENTITIES[rt])
                 body += code
                 stats['%s_%s_k%d' % (rt, nm, k)] = n
     pool = sorted(coefs, key=coefs.get)

@@ -37,10 +37,18 @@ def _sym6(G):
     return np.array([G[0, 0], G[1, 1], G[2, 2], G[0, 1], G[0, 2], G[1, 2]])
 
 
-def _fix(u, desc, fsel, v0, v1):
-    """the kernels' fix_columns<U>"""
+DM = {'edge': (0, 1, 2, 3, 4), 'face': (0, 1, 3)}     # tools/gen_canonical.py DM_ENTITIES
+
+
+def _fix(u, desc, fsel, v0, v1, kind):
+    """the kernels' fix_columns<U, DM>"""
+    if u < 6 and u in DM[kind]:
+        d, m = v0, v1
+        sm = -m if (desc >> (48 + u)) & 1 else m
+        return sm + d, sm - d
     if u < 6:
-        return (-v1, -v0) if (desc >> (48 + u)) & 1 else (v0, v1)
+        assert not (desc >> (48 + u)) & 1           # never seen reversed
+        return v0, v1
     nib = (fsel >> (4 * (u - 6))) & 15
     w = -(v0 + v1)
     sel = lambda c: (v0, v1, w)[c]
@@ -80,7 +88,7 @@ def test_canonical_rows_and_descriptors_reproduce_true_rows():
                     o = fns['canon_%s_%s_k%d' % (kind, nm, k)] @ g
                     got = np.zeros(20)
                     for u in range(10):
-                        got[2 * umap[u]], got[2 * umap[u] + 1] = _fix(u, d, f, o[2 * u], o[2 * u + 1])
+                        got[2 * umap[u]], got[2 * umap[u] + 1] = _fix(u, d, f, o[2 * u], o[2 * u + 1], kind)
                     assert np.allclose(got, A[rows[k]], rtol=1e-11, atol=1e-13 * np.abs(A).max()), (di, nm, k)
 
 
