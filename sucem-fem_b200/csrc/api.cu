@@ -437,7 +437,7 @@ int sfem_assemble_ST(sfem_pattern_t pat, const double* d_eps_r, const double* d_
   DeviceGuard dg(pat->space->mesh->device);
   if (kernel == SFEM_KERNEL_AUTO) kernel = canonical_supported(pat) ? SFEM_KERNEL_CANONICAL : SFEM_KERNEL_GENERIC;
   if (kernel == SFEM_KERNEL_CANONICAL) {
-    SFEM_CHECK(canonical_supported(pat), "canonical kernels support tetrahedra of order 1 and 2 only");
+    SFEM_CHECK(canonical_supported(pat), "canonical kernels are unavailable for this pattern (they need order-2 tetrahedra, manifold edges of at most 64 cells and rows of at most 255 entities); use SFEM_KERNEL_GENERIC or SFEM_KERNEL_AUTO");
     return assemble_canonical_ST(pat, d_eps_r, d_mu_r, d_pec_row_flags, d_S, d_T, (cudaStream_t)stream);
   }
   return assemble_generic(pat, 3, d_eps_r, d_mu_r, nullptr, d_pec_row_flags, d_S, d_T, (cudaStream_t)stream);

@@ -558,7 +558,11 @@ __global__ void __launch_bounds__(kThreadsFaces, SFEM_FACE_CTAS) k_canon_faces(C
 }  // namespace
 
 bool canonical_supported(const sfem_pattern_s* pat) {
-  return pat->space->mesh->gdim == 3 && pat->space->order == 2 && pat->rec != nullptr && pat->ring_ok;
+  // order-2 tets, packed records built (rows <= 255 entities), edges in ring order (manifold, <= 64 cells), faces
+  // between at most two cells, and the edge kernel's tiles (16 edges x 2 rows per warp) must fit in shared memory
+  const size_t edge_smem = (size_t)(kThreadsEdges / 32) * 16 * 2 * pat->max_row_len_edges * sizeof(double2);
+  return pat->space->mesh->gdim == 3 && pat->space->order == 2 && pat->rec != nullptr && pat->ring_ok &&
+         pat->max_row_len_other <= 16 && edge_smem <= 200 * 1024;
 }
 
 int canonical_launches(const sfem_pattern_s* pat) {

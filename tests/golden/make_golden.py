@@ -12,6 +12,9 @@ scalars, loaded with encoding='latin1':
        (generator: sucemfem/PostProcessing/tests/data/power_flux_generate_dofs.py:44-92)
   7    sucemfem/PostProcessing/tests/data/reference_dofs-2-0.149896229-0.0499654096667.pickle
        (generator: sucemfem/PostProcessing/tests/data/ntff_generate_dofs.py:40-85)
+  6    functional_tests/data/meshes/rectangular_prism.xml + rectangular_prism_facet_region.xml (gmsh mesh of the
+       1 x 0.5 x 0.25 cavity and its PEC facet markers, indexed by DOLFIN's face numbering;
+       test: functional_tests/test_EigenProblems.py:69-134)
 """
 import os
 import pickle
@@ -43,5 +46,25 @@ def main():
     np.savez_compressed(os.path.join(HERE, 'driven_order2_unitcube5.npz'), **{k: np.asarray(v) for k, v in d.items()})
 
 
+def prism():
+    import xml.etree.ElementTree as ET
+    base = '/root/reference/functional_tests/data/meshes/rectangular_prism'
+    mesh = ET.parse(base + '.xml').getroot().find('mesh')
+    vs, cs = mesh.find('vertices'), mesh.find('cells')
+    co = np.zeros((int(vs.get('size')), 3))
+    for v in vs:
+        co[int(v.get('index'))] = [float(v.get(a)) for a in 'xyz']
+    ce = np.zeros((int(cs.get('size')), 4), np.int32)
+    for c in cs:
+        ce[int(c.get('index'))] = [int(c.get('v%d' % i)) for i in range(4)]
+    mf = ET.parse(base + '_facet_region.xml').getroot().find('meshfunction')
+    mk = np.zeros(int(mf.get('size')), np.uint32)
+    for e in mf:
+        mk[int(e.get('index'))] = int(e.get('value'))
+    np.savez_compressed(os.path.join(HERE, 'rectangular_prism_gmsh.npz'), coordinates=co, cells=ce,
+                        facet_markers=mk, facet_dim=int(mf.get('dim')))
+
+
 if __name__ == '__main__':
+    prism()
     main()

@@ -136,3 +136,77 @@ def test_get_centred_cube_matches_reference_fixture_mesh():
     co, ce = meshes.centred_cube(np.array([lam] * 3) * 0.5, lam / 6)
     assert np.array_equal(mesh.cells(), ce)
     assert np.allclose(mesh.coordinates(), co - co[ce[372]].mean(axis=0), rtol=0, atol=1e-17)
+
+
+def test_gmsh_prism_pec_markers_and_cavity_modes():
+    """/root/reference/functional_tests/test_EigenProblems.py:69-134 on the reference's gmsh mesh with its PEC
+    facet-marker file (converted to tests/golden/rectangular_prism_gmsh.npz), at order 2 (the reference runs order 4
+    to 4 decimals; order 2 on this coarse mesh gives the lowest modes of the 1 x 0.5 x 0.25 cavity to 0.3 %)."""
+    import torch
+    from oracle import fem
+    from sucemfem import dolfin_compat as dolfin
+    from sucemfem.BoundaryConditions import PECWallsBoundaryCondition
+    from sucemfem.ProblemConfigurations.EMVectorWaveEigenproblem import EigenProblem, DefaultEigenSolver
+    g = np.load(os.path.join(GOLDEN, 'rectangular_prism_gmsh.npz'))
+    mesh = dolfin.Mesh(coordinates=g['coordinates'], cells=g['cells'])
+    pec_mesh_function = dolfin.MeshFunction('uint', mesh, 2)
+    assert len(pec_mesh_function.array()) == len(g['facet_markers'])      # same number of faces
+    pec_mesh_function.array()[:] = g['facet_markers']
+    # the device's exterior-facet marking reproduces the reference's marker file exactly
+    chk = dolfin.MeshFunction('uint', mesh, 2)
+    dolfin.DomainBoundary().mark(chk, 1)
+    assert np.array_equal(chk.array(), g['facet_markers'])
+    pec_walls = PECWallsBoundaryCondition()
+    pec_walls.init_with_meshfunction(pec_mesh_function, 1)
+    ep = EigenProblem()
+    ep.set_mesh(mesh)
+    ep.set_basis_order(2)
+    ep.set_boundary_conditions(pec_walls)
+    ep.init_problem()
+    # matrices against the oracle on this unstructured mesh (canonical kernels, ring order on a real gmsh mesh)
+    num = fem.number_entities(g['cells'])
+    ref = fem.assemble_system(g['coordinates'], g['cells'], 2, pec_facet_mask=g['facet_markers'] == 1)
+    ref0 = fem.assemble_system(g['coordinates'], g['cells'], 2)
+    for name, key in (('S', 'S'), ('M', 'M')):
+        rp, cl, v = ep.system_matrices[name].data()
+        assert np.array_equal(rp, ref['rowptr']) and np.array_equal(cl, ref['cols'])
+        assert np.all(np.abs(v - ref[key]) <= 1e-12 * np.abs(ref[key]) + 1e-15 * np.abs(ref0[key]).max())
+    es = DefaultEigenSolver()
+    es.set_eigenproblem(ep)
+    es.set_sigma(1.1)
+    eigs_w, _ = es.solve_problem(4)
+    res = np.sqrt(np.array(sorted(eigs_w))) / np.pi
+    a, b, d = 1.0, 0.5, 0.25
+    k = lambda m, n, l: np.sqrt((m / a) ** 2 + (n / b) ** 2 + (l / d) ** 2)
+    analytic = sorted([k(1, 1, 0), k(2, 1, 0), k(3, 1, 0), k(1, 0, 1), k(0, 1, 1), k(1, 2, 0)])[:4]
+    assert np.allclose(res, analytic, rtol=5e-3)
+
+
+def test_high_valence_edge_falls_back_to_generic_kernel():
+    """Edges shared by 70 / 40 cells exceed the ring builder's bound / the shared-memory tile of the canonical
+    kernels: the AUTO kernel must fall back to the generic kernel (same results), the canonical kernel must refuse
+    loudly; a closed ring of 12 cells goes through the canonical kernels (wrap-around path)."""
+    import torch
+    from oracle import fem
+    from sucemfem import device, _native as N
+    for m in (70, 40):
+        ang = 2 * np.pi * np.arange(m) / m
+        co = np.concatenate([[[0, 0, -1.0], [0, 0, 1.0]], np.stack([np.cos(ang), np.sin(ang), 0 * ang], 1)])
+        ce = np.sort(np.array([[0, 1, 2 + i, 2 + (i + 1) % m] for i in range(m)]), axis=1)
+        ref = fem.assemble_system(co, ce, 2)
+        sp = device.DeviceSpace(device.DeviceMesh(co, ce), 2)
+        pat = sp.pattern()
+        S, T = pat.assemble_ST(kernel=N.KERNEL_AUTO)
+        assert np.all(np.abs(S.cpu().numpy() - ref['S']) <= 1e-12 * np.abs(ref['S']) + 1e-15 * np.abs(ref['S']).max())
+        assert np.all(np.abs(T.cpu().numpy() - ref['M']) <= 1e-12 * np.abs(ref['M']) + 1e-15 * np.abs(ref['M']).max())
+        with pytest.raises(N.NativeError, match='canonical'):
+            pat.assemble_ST(kernel=N.KERNEL_CANONICAL)
+    m = 12
+    ang = 2 * np.pi * np.arange(m) / m
+    co = np.concatenate([[[0, 0, -1.0], [0, 0, 1.0]], np.stack([np.cos(ang), np.sin(ang), 0 * ang], 1)])
+    ce = np.sort(np.array([[0, 1, 2 + i, 2 + (i + 1) % m] for i in range(m)]), axis=1)
+    ref = fem.assemble_system(co, ce, 2)
+    pat = device.DeviceSpace(device.DeviceMesh(co, ce), 2).pattern()
+    S, T = pat.assemble_ST(kernel=N.KERNEL_CANONICAL)
+    assert np.all(np.abs(S.cpu().numpy() - ref['S']) <= 1e-12 * np.abs(ref['S']) + 1e-15 * np.abs(ref['S']).max())
+    assert np.all(np.abs(T.cpu().numpy() - ref['M']) <= 1e-12 * np.abs(ref['M']) + 1e-15 * np.abs(ref['M']).max())

@@ -138,3 +138,15 @@ def test_pec_cavity_eigenvalues_order2():
     # PEC rows of the ident-applied matrices are unit rows
     Sp = fem.to_scipy(r['rowptr'], r['cols'], r['S'], r['ndof']).toarray()
     assert np.all(Sp[r['pec_dofs']] == np.eye(r['ndof'])[r['pec_dofs']])
+
+
+def test_fixture6_face_numbering_on_gmsh_prism():
+    """The reference's facet-marker file for its gmsh prism (functional_tests/test_EigenProblems.py:79-84) is indexed
+    by DOLFIN's face numbering: all 92 PEC markers must land exactly on the 92 boundary faces of OUR numbering."""
+    g = np.load(os.path.join(GOLDEN, 'rectangular_prism_gmsh.npz'))
+    co, ce = g['coordinates'], g['cells']
+    assert np.all(np.diff(ce, axis=1) > 0)
+    num = fem.number_entities(ce)
+    assert num['F'] == len(g['facet_markers']) == 362
+    assert np.array_equal(fem.exterior_facet_mask(ce, num), g['facet_markers'] == 1)
+    assert (g['facet_markers'] == 1).sum() == 92
