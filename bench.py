@@ -132,6 +132,7 @@ def main():
     ap.add_argument('--impl', default='b200')
     ap.add_argument('--n', type=int, default=0, help='override the cube size (debug; not a bench line)')
     ap.add_argument('--kernel', type=int, default=0, help='0 auto, 1 generic, 2 canonical')
+    ap.add_argument('--order', type=int, default=2, help='basis order (debug; the bench line is order 2)')
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--no-cpu', action='store_true')
     args = ap.parse_args()
@@ -158,7 +159,7 @@ def main():
     # ---- one-time set-up (not timed as part of a step): mesh, numbering, this rank's row block ----------
     t_setup = time.perf_counter()
     mesh = device.DeviceMesh.unit(n, n, n)
-    space = device.DeviceSpace(mesh, 2)
+    space = device.DeviceSpace(mesh, args.order)
     bounds = space.partition(world)
     pat = device.DevicePattern(space, bounds[rank], bounds[rank + 1])
     markers = torch.zeros(space.n_facets, dtype=torch.int32, device='cuda')
