@@ -135,8 +135,19 @@ __device__ __forceinline__ void canon_geometry(const Item& it, double (&g)[6]) {
   }
 }
 
-__device__ __forceinline__ double sel3(unsigned code, double v0, double v1, double w) {
-  return code == 0 ? v0 : (code == 1 ? v1 : w);
+// branch-free select on one bit of a word: (word >> BIT) & 1 ? a : b   (the compiler turns the equivalent ?: on
+// doubles into short divergent branches with predicated moves; selp.f64 is two SEL and no BSSY/BSYNC)
+template <int BIT>
+__device__ __forceinline__ double sel_bit(unsigned word, double a, double b) {
+  double r;
+  asm("{ .reg .pred q; .reg .b32 t; and.b32 t, %3, %4; setp.ne.u32 q, t, 0; selp.f64 %0, %1, %2, q; }"
+      : "=d"(r) : "d"(a), "d"(b), "r"(word), "n"(1u << BIT));
+  return r;
+}
+__device__ __forceinline__ double sel_flag(bool p, double a, double b) {
+  double r;
+  asm("{ .reg .pred q; setp.ne.u32 q, %3, 0; selp.f64 %0, %1, %2, q; }" : "=d"(r) : "d"(a), "d"(b), "r"((unsigned)p));
+  return r;
 }
 
 // orientation fix-up context of one item (generated/canonical_lut.inc)
@@ -148,6 +159,7 @@ struct Fix {
 // true-frame values of the 2 columns of canonical column entity U, from the canonical-frame values the generated row
 // functions produce: (v0, v1) for faces and for edges that are never seen reversed (DM = false); for the other edges
 // (d, m) = ((v0 - v1)/2, (v0 + v1)/2), where a reversed edge only flips the sign of m (tools/gen_canonical.py).
+// Faces: an ordered pair out of (v0, v1, w = -(v0 + v1)), three selector bits per face (swap, w0, w1).
 template <int U, bool DM = false>
 __device__ __forceinline__ double2 fix_columns(const Fix& f, double v0, double v1) {
   if constexpr (U < 6 && DM) {
@@ -157,9 +169,10 @@ __device__ __forceinline__ double2 fix_columns(const Fix& f, double v0, double v
   } else if constexpr (U < 6) {
     return make_double2(v0, v1);
   } else {
-    const unsigned nib = (f.fsel >> (4 * (U - 6))) & 15u;
     const double w = -(v0 + v1);
-    return make_double2(sel3(nib & 3u, v0, v1, w), sel3(nib >> 2, v0, v1, w));
+    const double u0 = sel_bit<4 * (U - 6)>(f.fsel, v1, v0);
+    const double u1 = sel_bit<4 * (U - 6)>(f.fsel, v0, v1);
+    return make_double2(sel_bit<4 * (U - 6) + 1>(f.fsel, w, u0), sel_bit<4 * (U - 6) + 2>(f.fsel, w, u1));
   }
 }
 
@@ -331,13 +344,13 @@ __device__ __forceinline__ void edge_pass(const CanonArgs& p, const unsigned lon
         double2 r;                                                                                 \
         r = fix_columns<5>(fx, o[10], o[11]); self[K].x += r.x; self[K].y += r.y;                  \
         r = fix_columns<4, true>(fx, o[8], o[9]);                                                        \
-        r.x += has_prev ? c4.x : 0.0; r.y += has_prev ? c4.y : 0.0;                                \
+        r.x += sel_flag(has_prev, c4.x, 0.0); r.y += sel_flag(has_prev, c4.y, 0.0);                \
         row[slot_of<4>(sl)] = r;                                                                  \
         r = fix_columns<2, true>(fx, o[4], o[5]);                                                        \
-        r.x += has_prev ? c2.x : 0.0; r.y += has_prev ? c2.y : 0.0;                                \
+        r.x += sel_flag(has_prev, c2.x, 0.0); r.y += sel_flag(has_prev, c2.y, 0.0);                \
         row[slot_of<2>(sl)] = r;                                                                  \
         r = fix_columns<9>(fx, o[18], o[19]);                                                      \
-        r.x += has_prev ? c9.x : 0.0; r.y += has_prev ? c9.y : 0.0;                                \
+        r.x += sel_flag(has_prev, c9.x, 0.0); r.y += sel_flag(has_prev, c9.y, 0.0);                \
         row[slot_of<9>(sl)] = r;                                                                  \
         row[slot_of<0>(sl)] = fix_columns<0, true>(fx, o[0], o[1]);                                     \
         row[slot_of<7>(sl)] = fix_columns<7>(fx, o[14], o[15]);                                   \

@@ -66,13 +66,22 @@ def relabel_lut(rowtype, t, swap=0):
     return sigma, umap, Q
 
 
-# a face fix-up is two 3-way selections among (v0, v1, w = -(v0+v1)): codes 0,1,2
+# a face fix-up selects an ordered pair out of (v0, v1, w = -(v0+v1)).  Rows of Q -> codes 0,1,2; the kernel gets
+# three bits per face: swap (u = (v1, v0) instead of (v0, v1)), w0 (out0 = w instead of u0), w1 (out1 = w instead of u1)
 SEL = {(1, 0): 0, (0, 1): 1, (-1, -1): 2}
+
+
+def face_bits(s0, s1):
+    swap = int(s0 == 1 or s1 == 0)
+    w0, w1 = int(s0 == 2), int(s1 == 2)
+    u = (1, 0) if swap else (0, 1)
+    assert (2 if w0 else u[0], 2 if w1 else u[1]) == (s0, s1)
+    return swap | (w0 << 1) | (w1 << 2)
 
 
 def pack_descriptor(rowtype, t, swap=0):
     """64-bit descriptor: bits 0-7 sigma (2 bits each), 8-47 umap (4 bits each), 48-53 edge flips,
-    54-61 (or up to 63) face selectors: per canonical face f: 2 bits out0, 2 bits out1 -> 16 bits starting at 48+6."""
+    separate 16-bit word of face selectors: per canonical face f a nibble (swap, w0, w1), see face_bits."""
     sigma, umap, Q = relabel_lut(rowtype, t, swap)
     d = 0
     for i, s in enumerate(sigma):
@@ -87,7 +96,7 @@ def pack_descriptor(rowtype, t, swap=0):
         q = Q[6 + f]
         s0 = SEL[(int(q[0, 0]), int(q[0, 1]))]
         s1 = SEL[(int(q[1, 0]), int(q[1, 1]))]
-        hi |= (s0 | (s1 << 2)) << (4 * f)
+        hi |= face_bits(s0, s1) << (4 * f)
     return d, hi
 
 

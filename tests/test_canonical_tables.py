@@ -51,8 +51,8 @@ def _fix(u, desc, fsel, v0, v1, kind):
         return v0, v1
     nib = (fsel >> (4 * (u - 6))) & 15
     w = -(v0 + v1)
-    sel = lambda c: (v0, v1, w)[c]
-    return sel(nib & 3), sel(nib >> 2)
+    u0, u1 = (v1, v0) if nib & 1 else (v0, v1)
+    return (w if nib & 2 else u0), (w if nib & 4 else u1)
 
 
 def test_canonical_rows_and_descriptors_reproduce_true_rows():
