@@ -337,7 +337,9 @@ __device__ __forceinline__ void edge_pass(const CanonArgs& p, const unsigned lon
       }                                                                                            \
       /* hand the next-side blocks to the partner, which owns the next cell of the ring */         \
       const double2 g3 = shfl_xor1(n3), g1 = shfl_xor1(n1), g8 = shfl_xor1(n8);                    \
-      const double2 c4 = h ? g3 : saved[K][0], c2 = h ? g1 : saved[K][1], c9 = h ? g8 : saved[K][2]; \
+      const double2 c4 = make_double2(sel_flag(h, g3.x, saved[K][0].x), sel_flag(h, g3.y, saved[K][0].y)); \
+      const double2 c2 = make_double2(sel_flag(h, g1.x, saved[K][1].x), sel_flag(h, g1.y, saved[K][1].y)); \
+      const double2 c9 = make_double2(sel_flag(h, g8.x, saved[K][2].x), sel_flag(h, g8.y, saved[K][2].y)); \
       saved[K][0] = g3; saved[K][1] = g1; saved[K][2] = g8;                                        \
       if (active) {                                                                                \
         double2* row = row0 + K * len;                                                             \
