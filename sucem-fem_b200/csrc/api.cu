@@ -253,6 +253,7 @@ int sfem_space_destroy(sfem_space_t sp) {
   cudaFree(sp->facet_first_loc);
   cudaFree(sp->cell_extmask);
   cudaFree(sp->coords4);
+  cudaFree(sp->ones);
   delete sp;
   return 0;
 }

@@ -89,8 +89,8 @@ __device__ __forceinline__ void gather_item(const CanonArgs& p, uint4 ra, uint4 
     it.X[3 * k + 1] = xy.y;
     it.X[3 * k + 2] = z.x;
   }
-  it.cmu = p.mu ? p.mu[(int)rb.x] : 1.0;
-  it.ceps = p.eps ? p.eps[(int)rb.x] : 1.0;
+  it.cmu = p.mu[(int)rb.x];
+  it.ceps = p.eps[(int)rb.x];
 }
 
 // geometry factors of the relabelled cell in symmetric order (00,11,22,01,02,12):
@@ -585,10 +585,23 @@ int canonical_launches(const sfem_pattern_s* pat) {
   return (pat->ent_lo < E ? 1 : 0) + (pat->ent_hi > E ? 1 : 0);
 }
 
+__global__ void k_fill_ones(double* a, int64_t n) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < n) a[i] = 1.0;
+}
+
 int assemble_canonical_ST(const sfem_pattern_s* pat, const double* eps, const double* mu, const uint8_t* pec,
                           double* S, double* T, cudaStream_t st) {
-  const sfem_space_s* sp = pat->space;
+  sfem_space_s* sp = pat->space;
   const sfem_mesh_s* m = sp->mesh;
+  if (!eps || !mu) {  // default coefficients: the kernels always read a per-cell array
+    if (!sp->ones) {
+      SFEM_CUDA(cudaMalloc(&sp->ones, m->C * sizeof(double)));
+      k_fill_ones<<<(unsigned)((m->C + 255) / 256), 256, 0, st>>>(sp->ones, m->C);
+    }
+    if (!eps) eps = sp->ones;
+    if (!mu) mu = sp->ones;
+  }
   CanonArgs p;
   p.coords4 = sp->coords4; p.cells = m->cells; p.eps = eps; p.mu = mu;
   p.inc_ptr = sp->inc_ptr; p.ent_rowptr = pat->ent_rowptr; p.rec = pat->rec; p.pec = pec; p.S = S; p.T = T;

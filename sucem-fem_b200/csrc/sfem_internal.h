@@ -92,6 +92,7 @@ struct sfem_space_s {
   uint8_t* facet_first_loc = nullptr; // [n_facets]
   uint8_t* cell_extmask = nullptr;    // [C] bit lf set <=> local facet lf is exterior
   double* coords4 = nullptr;          // [V][4] 32-byte padded copy of the coordinates (3-D; vector gathers)
+  double* ones = nullptr;             // [C] 1.0, the default eps_r / mu_r (allocated on first use)
 };
 
 struct sfem_pattern_s {
