@@ -491,13 +491,26 @@ __device__ __forceinline__ void face_pass(const CanonArgs& p, double2* __restric
   tile_store_issue(tile, out_first, (unsigned)span * 16u, lane);
 }
 
-// record index of this lane's cell in batch `batch` (or -1), block-relative
-__device__ __forceinline__ int64_t face_item_index(const CanonArgs& p, int64_t batch, int64_t nb, int lane) {
+// incidence range of this lane's face in batch `batch`, RAW: an instruction that consumes a load stalls the in-order
+// warp until it lands, so the range is only turned into a record index one iteration later (face_item_index)
+struct FaceRange {
+  int64_t ip0, ip1;
+};
+__device__ __forceinline__ FaceRange load_face_range(const CanonArgs& p, int64_t batch, int64_t nb, int lane) {
+  FaceRange f;
+  f.ip0 = 0; f.ip1 = 0;
   const int64_t r = p.r_begin + batch * 16 + (lane >> 1);
-  if (batch >= nb || r >= p.r_end) return -1;
-  const int64_t g = p.ent_lo + r;
-  const int64_t i = p.inc_ptr[g] + (lane & 1);
-  return i < p.inc_ptr[g + 1] ? i - p.inc_base : -1;
+  if (batch < nb && r < p.r_end) {
+    const int64_t g = p.ent_lo + r;
+    f.ip0 = p.inc_ptr[g];
+    f.ip1 = p.inc_ptr[g + 1];
+  }
+  return f;
+}
+// record index of this lane's cell (or -1), block-relative
+__device__ __forceinline__ int64_t face_item_index(const CanonArgs& p, const FaceRange& f, int lane) {
+  const int64_t i = f.ip0 + (lane & 1);
+  return i < f.ip1 ? i - p.inc_base : -1;
 }
 
 // Persistent warps over batches of 16 faces; the gather chain (incidence pointer -> record -> coordinates) of the
@@ -514,9 +527,10 @@ __global__ void __launch_bounds__(kThreadsFaces, SFEM_FACE_CTAS) k_canon_faces(C
   int64_t b = blockIdx.x * (int64_t)(kThreadsFaces / 32) + w;
   if (b >= nb) return;
   Item cur;
-  int64_t i0 = face_item_index(p, b, nb, lane);
-  int64_t i1 = face_item_index(p, b + W, nb, lane);
-  int64_t i2 = face_item_index(p, b + 2 * W, nb, lane);
+  int64_t i0 = face_item_index(p, load_face_range(p, b, nb, lane), lane);
+  int64_t i1 = face_item_index(p, load_face_range(p, b + W, nb, lane), lane);
+  int64_t i2 = face_item_index(p, load_face_range(p, b + 2 * W, nb, lane), lane);
+  FaceRange f3 = load_face_range(p, b + 3 * W, nb, lane);
   uint4 r1a = make_uint4(0, 0, 0, 0), r1b = r1a;
   if (i0 >= 0) gather_item(p, p.rec[2 * i0], p.rec[2 * i0 + 1], cur);
   if (i1 >= 0) { r1a = p.rec[2 * i1]; r1b = p.rec[2 * i1 + 1]; }
@@ -529,7 +543,8 @@ __global__ void __launch_bounds__(kThreadsFaces, SFEM_FACE_CTAS) k_canon_faces(C
 #pragma unroll 1
   for (; b < nb; b += W) {
     // stage 3 / 2 / 1 of the batches ahead
-    const int64_t i3 = face_item_index(p, b + 3 * W, nb, lane);
+    const int64_t i3 = face_item_index(p, f3, lane);        // loaded one iteration ago
+    f3 = load_face_range(p, b + 4 * W, nb, lane);
     uint4 r2a = make_uint4(0, 0, 0, 0), r2b = r2a;
     if (i2 >= 0) { r2a = p.rec[2 * i2]; r2b = p.rec[2 * i2 + 1]; }
     // everything that is needed from the current item, then its buffer receives the next batch's
