@@ -242,7 +242,7 @@ def main():
 
     # ---- e2e through the public API with HOST buffers (rank-local; N=1 only measures the full pipeline) ---
     if not args.no_e2e and world == 1:
-        line["e2e"] = e2e_run(n, min(K, 2))
+        line["e2e"] = e2e_run(n, min(K, 3))
     # ---- CPU baseline (rank 0, N=1): bounded sample, 1 thread = what sucemfem + DOLFIN 1.0 run ------------
     if rank == 0 and world == 1 and not args.no_cpu:
         v1, dt1, cells, A = cpu_port_run(24, 1, 2)
@@ -306,11 +306,12 @@ def e2e_run(n, steps):
         if it > 0:
             times.append(time.perf_counter() - t0)
         del S, T, rp, cl, pat, space, mesh
-    dt = sum(times) / len(times)
+    dt = sorted(times)[len(times) // 2]      # median step
     h2d = sum(x.numel() * x.element_size() for x in (h_co, h_ce, h_eps, h_mu))
     d2h = sum(x.numel() * x.element_size() for x in out.values())
     return {"value": len(ce) / dt, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-            "ms_per_step": dt * 1e3, "includes": "H2D mesh+materials, numbering, pattern, S+T values, PEC, D2H CSR"}
+            "ms_per_step": dt * 1e3, "steps_ms": [round(t * 1e3, 1) for t in times],
+            "includes": "H2D mesh+materials, numbering, pattern, S+T values, PEC, D2H CSR"}
 
 
 if __name__ == '__main__':
