@@ -585,9 +585,185 @@ __global__ void __launch_bounds__(kThreadsFaces, SFEM_FACE_CTAS) k_canon_faces(C
   tile_store_wait(lane);
 }
 
+// ---- order 1 (Whitney elements): one CSR row per edge, one function per column edge ----------------------------
+// Same decomposition as the order-2 edge kernel (lane pair per edge, ring order, carries by shuffle, every slot stored
+// once), but a row is short (1 + 3 m values), so S and T are assembled in ONE sweep into two small tiles and written
+// out with coalesced 8-byte streaming stores.  A reversed column edge only changes the sign of its function.
+__device__ __forceinline__ double flip_sign(const Fix& f, int u, double v) {
+  const unsigned sign = ((unsigned)(f.desc >> 32) << (15 - u)) & 0x80000000u;  // descriptor bit 48 + u -> bit 31
+  return __hiloint2double(__double2hiint(v) ^ (int)sign, __double2loint(v));
+}
+
+__device__ __forceinline__ void canon_geometry_both(const Item& it, double (&gT)[6], double (&gS)[6]) {
+  double J[3][3];
+#pragma unroll
+  for (int a = 0; a < 3; ++a)
+#pragma unroll
+    for (int d = 0; d < 3; ++d) J[d][a] = it.X[3 * (a + 1) + d] - it.X[d];
+  double A[3][3];  // adj(J) = det J^-1
+  A[0][0] = J[1][1] * J[2][2] - J[1][2] * J[2][1];
+  A[1][0] = J[1][2] * J[2][0] - J[1][0] * J[2][2];
+  A[2][0] = J[1][0] * J[2][1] - J[1][1] * J[2][0];
+  A[0][1] = J[0][2] * J[2][1] - J[0][1] * J[2][2];
+  A[1][1] = J[0][0] * J[2][2] - J[0][2] * J[2][0];
+  A[2][1] = J[0][1] * J[2][0] - J[0][0] * J[2][1];
+  A[0][2] = J[0][1] * J[1][2] - J[0][2] * J[1][1];
+  A[1][2] = J[0][2] * J[1][0] - J[0][0] * J[1][2];
+  A[2][2] = J[0][0] * J[1][1] - J[0][1] * J[1][0];
+  const double det = J[0][0] * A[0][0] + J[0][1] * A[1][0] + J[0][2] * A[2][0];
+  const double ad = fabs(det);
+  const double st = it.ceps / ad, ss = 1.0 / (ad * it.cmu);
+  const int pa[6] = {0, 1, 2, 0, 0, 1}, pb[6] = {0, 1, 2, 1, 2, 2};
+#pragma unroll
+  for (int q = 0; q < 6; ++q) {
+    const int a = pa[q], b = pb[q];
+    gT[q] = (A[a][0] * A[b][0] + A[a][1] * A[b][1] + A[a][2] * A[b][2]) * st;
+    gS[q] = (J[0][a] * J[0][b] + J[1][a] * J[1][b] + J[2][a] * J[2][b]) * ss;
+  }
+}
+
+constexpr int kThreadsEdges1 = 128;
+
+__global__ void __launch_bounds__(kThreadsEdges1, 3) k_canon1_edges(CanonArgs p) {
+  extern __shared__ double2 smem[];
+  __shared__ unsigned long long s_desc[16];
+  __shared__ unsigned s_fsel[16];
+  stage_lut(s_desc, s_fsel);
+  (void)s_fsel;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, h = lane & 1;
+  double* tileS = reinterpret_cast<double*>(smem) + (size_t)w * 2 * p.tile_chunks;  // tile_chunks = doubles per matrix tile
+  double* tileT = tileS + p.tile_chunks;
+  const int64_t nb = (p.r_end - p.r_begin + 15) / 16;
+  const int64_t W = (int64_t)gridDim.x * (kThreadsEdges1 / 32);
+  int64_t b = blockIdx.x * (int64_t)(kThreadsEdges1 / 32) + w;
+  if (b >= nb) return;
+  const uint4* __restrict__ rec = p.rec;
+  EdgeMeta m = load_edge_meta(p, b, lane);
+  Item cur;
+  uint4 rc1a = make_uint4(0, 0, 0, 0), rc1b = rc1a;
+  {
+    const int64_t i = m.i0 + h;
+    if (i < m.i1) {
+      const uint4 ra = rec[2 * i], rb = rec[2 * i + 1];
+      if (i + 2 < m.i1) { rc1a = rec[2 * (i + 2)]; rc1b = rec[2 * (i + 2) + 1]; }
+      gather_item(p, ra, rb, cur);
+    }
+  }
+#pragma unroll 1
+  for (; b < nb; b += W) {
+    const EdgeMeta mn = load_edge_meta(p, b + W, lane);  // beyond the end: empty
+    const bool valid = m.i0 <= m.i1 && m.a1 > m.a;
+    const int len = (int)(m.a1 - m.a);
+    const unsigned vmask = __ballot_sync(0xffffffffu, valid);
+    const int last = 31 - __clz((int)vmask);
+    const int64_t a_first = __shfl_sync(0xffffffffu, m.a, 0);
+    const int64_t a_end = __shfl_sync(0xffffffffu, m.a1, last);
+    const int span = (int)(a_end - a_first);
+    const int off = (int)(m.a - a_first);
+    int nsteps = valid ? (int)((m.i1 - m.i0 + 1) >> 1) : 0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) nsteps = max(nsteps, __shfl_xor_sync(0xffffffffu, nsteps, o));
+    const int64_t g = p.ent_lo + p.r_begin + b * 16 + (lane >> 1);
+    const bool pecrow = valid && p.pec && p.pec[g];
+    const int64_t nf = mn.i0 + h, nf_end = mn.i1;
+    uint4 rfa = make_uint4(0, 0, 0, 0), rfb = rfa;
+    if (nf < nf_end) { rfa = rec[2 * nf]; rfb = rec[2 * nf + 1]; }
+    double* rowS = tileS + off;
+    double* rowT = tileT + off;
+    double selfS = 0.0, selfT = 0.0;
+    double savedS[2] = {0.0, 0.0}, savedT[2] = {0.0, 0.0};
+    int self_slot = 0;
+    int64_t i = m.i0 + h;
+    __syncwarp();  // the previous batch's write-out has finished reading the tiles
+#pragma unroll 1
+    for (int s = 0; s < nsteps; ++s, i += 2) {
+      const bool active = valid && i < m.i1;
+      const Slots sl = slots_of(cur);
+      const unsigned flags = active ? flags_of(sl) : 0u;
+      const bool has_prev = flags & 1u, has_next = flags & 2u, wrap = flags & 4u;
+      double gT[6], gS[6];
+      Fix fx;
+      fx.desc = 0ull; fx.fsel = 0u;
+      if (active) {
+        canon_geometry_both(cur, gT, gS);
+        fx.desc = s_desc[desc_index(sl)];
+        if (s == 0 && h == 0) self_slot = slot_of<5>(sl);
+      }
+      uint4 rc2a = make_uint4(0, 0, 0, 0), rc2b = rc2a;
+      if (s + 1 < nsteps) {
+        if (i + 2 < m.i1) {
+          if (i + 4 < m.i1) { rc2a = rec[2 * (i + 4)]; rc2b = rec[2 * (i + 4) + 1]; }
+          gather_item(p, rc1a, rc1b, cur);
+        }
+      } else if (nf < nf_end) {
+        if (nf + 2 < nf_end) { rc2a = rec[2 * (nf + 2)]; rc2b = rec[2 * (nf + 2) + 1]; }
+        gather_item(p, rfa, rfb, cur);
+      }
+      double oS[6], oT[6];
+#pragma unroll
+      for (int u = 0; u < 6; ++u) { oS[u] = 0.0; oT[u] = 0.0; }
+      if (active) {
+        canon1_edge_curl(gS, oS);
+        canon1_edge_mass(gT, oT);
+#pragma unroll
+        for (int u = 0; u < 5; ++u) { oS[u] = flip_sign(fx, u, oS[u]); oT[u] = flip_sign(fx, u, oT[u]); }
+      }
+      // next-side edges (3 = (0,3), 1 = (1,3)) go to the partner lane, which owns the next cell of the ring
+      const double gS3 = __shfl_xor_sync(0xffffffffu, oS[3], 1), gS1 = __shfl_xor_sync(0xffffffffu, oS[1], 1);
+      const double gT3 = __shfl_xor_sync(0xffffffffu, oT[3], 1), gT1 = __shfl_xor_sync(0xffffffffu, oT[1], 1);
+      const double cS4 = sel_flag(h, gS3, savedS[0]), cS2 = sel_flag(h, gS1, savedS[1]);
+      const double cT4 = sel_flag(h, gT3, savedT[0]), cT2 = sel_flag(h, gT1, savedT[1]);
+      savedS[0] = gS3; savedS[1] = gS1; savedT[0] = gT3; savedT[1] = gT1;
+      __syncwarp();
+      if (active) {
+        selfS += oS[5];
+        selfT += oT[5];
+        const int s4 = slot_of<4>(sl), s2 = slot_of<2>(sl), s0 = slot_of<0>(sl);
+        rowS[s4] = oS[4] + sel_flag(has_prev, cS4, 0.0);
+        rowT[s4] = oT[4] + sel_flag(has_prev, cT4, 0.0);
+        rowS[s2] = oS[2] + sel_flag(has_prev, cS2, 0.0);
+        rowT[s2] = oT[2] + sel_flag(has_prev, cT2, 0.0);
+        rowS[s0] = oS[0];
+        rowT[s0] = oT[0];
+        if (!has_next) {
+          const int s3 = slot_of<3>(sl), s1 = slot_of<1>(sl);
+          double a3 = oS[3], a1 = oS[1], b3 = oT[3], b1 = oT[1];
+          if (wrap) { a3 += rowS[s3]; a1 += rowS[s1]; b3 += rowT[s3]; b1 += rowT[s1]; }
+          rowS[s3] = a3; rowS[s1] = a1; rowT[s3] = b3; rowT[s1] = b1;
+        }
+      }
+      rc1a = rc2a; rc1b = rc2b;
+    }
+    selfS += __shfl_xor_sync(0xffffffffu, selfS, 1);
+    selfT += __shfl_xor_sync(0xffffffffu, selfT, 1);
+    __syncwarp();
+    if (valid && h == 0) {
+      rowS[self_slot] = selfS;
+      rowT[self_slot] = selfT;
+      if (pecrow) {  // row-only ident fused: unit row
+        for (int k = 0; k < len; ++k) { rowS[k] = 0.0; rowT[k] = 0.0; }
+        rowS[self_slot] = 1.0;
+        rowT[self_slot] = 1.0;
+      }
+    }
+    __syncwarp();
+    for (int j = lane; j < span; j += 32) {
+      __stcs(p.S + a_first + j, tileS[j]);
+      __stcs(p.T + a_first + j, tileT[j]);
+    }
+    m = mn;
+  }
+}
+
 }  // namespace
 
+static bool canonical1_supported(const sfem_pattern_s* pat) {
+  return pat->space->mesh->gdim == 3 && pat->space->order == 1 && pat->rec != nullptr && pat->ring_ok &&
+         (size_t)(kThreadsEdges1 / 32) * 2 * 16 * pat->max_row_len_edges * sizeof(double) <= 64 * 1024;
+}
+
 bool canonical_supported(const sfem_pattern_s* pat) {
+  if (pat->space->order == 1) return canonical1_supported(pat);
   // order-2 tets, packed records built (rows <= 255 entities), edges in ring order (manifold, <= 64 cells), faces
   // between at most two cells, and the edge kernel's tiles (16 edges x 2 rows per warp) must fit in shared memory
   const size_t edge_smem = (size_t)(kThreadsEdges / 32) * 16 * 2 * pat->max_row_len_edges * sizeof(double2);
@@ -596,6 +772,7 @@ bool canonical_supported(const sfem_pattern_s* pat) {
 }
 
 int canonical_launches(const sfem_pattern_s* pat) {
+  if (pat->space->order == 1) return 1;
   const int64_t E = pat->space->E;
   return (pat->ent_lo < E ? 1 : 0) + (pat->ent_hi > E ? 1 : 0);
 }
@@ -626,6 +803,18 @@ int assemble_canonical_ST(const sfem_pattern_s* pat, const double* eps, const do
   const int64_t n_rows = pat->n_rows_ent;
   int num_sms = 148;
   SFEM_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, sp->device));
+  if (sp->order == 1) {
+    if (n_rows == 0) return 0;
+    p.r_begin = 0; p.r_end = n_rows;
+    p.tile_chunks = 16 * pat->max_row_len_edges;  // doubles per matrix tile
+    const size_t smem = (size_t)(kThreadsEdges1 / 32) * 2 * p.tile_chunks * sizeof(double);
+    SFEM_CUDA(cudaFuncSetAttribute(k_canon1_edges, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int64_t nblocks = (n_rows + kThreadsEdges1 / 2 - 1) / (kThreadsEdges1 / 2);
+    const unsigned grid = (unsigned)std::min<int64_t>(nblocks, (int64_t)num_sms * 3);
+    k_canon1_edges<<<grid, kThreadsEdges1, smem, st>>>(p);
+    SFEM_CUDA(cudaGetLastError());
+    return 0;
+  }
   if (n_edge_rows > 0) {
     p.r_begin = 0; p.r_end = n_edge_rows;
     p.tile_chunks = 16 * 2 * pat->max_row_len_edges;

@@ -189,7 +189,7 @@ __global__ void k_edge_ring(SpaceView sv, const int32_t* __restrict__ cells, con
         reinterpret_cast<int32_t*>(q)[k] = cells[c * 4 + (int)((desc >> (2 * k)) & 3ull)];
       reinterpret_cast<int32_t*>(q)[4] = (int32_t)c;
       q[20] = (uint8_t)(2 * t + swap);
-      for (int u = 0; u < 10; ++u) {
+      for (int u = 0; u < sv.n_ent_cell; ++u) {  // 10 at order 2, the 6 edges at order 1
         const int32_t x = sv.ent(c, (int)((desc >> (8 + 4 * u)) & 15ull));
         int lo = 0, hi = len - 1;
         while (lo < hi) {

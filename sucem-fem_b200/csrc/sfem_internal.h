@@ -138,8 +138,8 @@ inline SpaceView make_view(const sfem_space_s* s) {
   return v;
 }
 
-// order-2 tets: the slot table is stored in canonical column order (see pattern.cu / assemble_canonical.cu)
-inline bool pos_is_canonical(const sfem_space_s* s) { return s->mesh->gdim == 3 && s->order == 2; }
+// tets: the slot table is stored in canonical column order (see pattern.cu / assemble_canonical.cu)
+inline bool pos_is_canonical(const sfem_space_s* s) { return s->mesh->gdim == 3; }
 
 int build_numbering(sfem_space_s* sp, cudaStream_t st);
 int build_pattern(sfem_pattern_s* pat, cudaStream_t st);

@@ -106,16 +106,16 @@ def pack_descriptor(rowtype, t, swap=0):
 DM_ENTITIES = {'edge': (0, 1, 2, 3, 4), 'face': (0, 1, 3)}
 
 
-def emit_rows(name, table, row, coefs, dm=()):
+def emit_rows(name, table, row, coefs, dm=(), ncols=20):
     """o[j] = sum_p table[row][j][p] * g[p]; coefficients referenced from the __constant__ pool kCanonCoef so that
     they become constant-bank operands of the DFMAs (literals would be materialised through UMOV pairs)."""
-    out = '__device__ __forceinline__ void %s(const double (&g)[6], double (&o)[20]) {\n' % name
+    out = '__device__ __forceinline__ void %s(const double (&g)[6], double (&o)[%d]) {\n' % (name, ncols)
     nterms = 0
     tab = np.array(table[row], dtype=np.float64)
     for u in dm:
         v0, v1 = tab[2 * u].copy(), tab[2 * u + 1].copy()
         tab[2 * u], tab[2 * u + 1] = 0.5 * (v0 - v1), 0.5 * (v0 + v1)
-    for j in range(20):
+    for j in range(ncols):
         terms = [(p, tab[j, p]) for p in range(6) if tab[j, p] != 0.0]
         nterms += len(terms)
         if not terms:
@@ -143,6 +143,13 @@ def main():
                 code, n = emit_rows('canon_%s_%s_k%d' % (rt, nm, k), tab, row, coefs, DM_ENTITIES[rt])
                 body += code
                 stats['%s_%s_k%d' % (rt, nm, k)] = n
+    # order 1 (Whitney): one function per edge, one row (the canonical edge e5 = local dof 5), 6 columns; a reversed
+    # column edge only changes sign, so no change of basis is needed
+    mass1, curl1 = load_table('kMassTet1'), load_table('kCurlTet1')
+    for nm, tab in (('mass', mass1), ('curl', curl1)):
+        code, n = emit_rows('canon1_edge_%s' % nm, tab, 5, coefs, ncols=6)
+        body += code
+        stats['order1_edge_%s' % nm] = n
     pool = sorted(coefs, key=coefs.get)
     src += '__constant__ double kCanonCoef[%d] = {%s};\n' % (len(pool), ', '.join(repr(c) for c in pool))
     src += body

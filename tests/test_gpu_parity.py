@@ -166,9 +166,10 @@ def test_unsorted_cells_rejected(dev):
 TET_MESHES = [k for k in sorted(MESHES) if MESHES[k][0].shape[1] == 3]
 
 
+@pytest.mark.parametrize('order', [1, 2])
 @pytest.mark.parametrize('name', TET_MESHES)
-def test_values_canonical_vs_oracle(dev, name):
-    """The benchmarked kernels (canonical frame, order-2 tets) against the oracle and the generic kernel."""
+def test_values_canonical_vs_oracle(dev, name, order):
+    """The benchmarked kernels (canonical frame, tets of order 2 and 1) against the oracle and the generic kernel."""
     import torch
     from sucemfem import _native as N
     co, ce = MESHES[name]
@@ -177,10 +178,10 @@ def test_values_canonical_vs_oracle(dev, name):
     mu = rng.uniform(1, 2, ce.shape[0])
     num = fem.number_entities(ce)
     pecmask = fem.exterior_facet_mask(ce, num)
-    ref = fem.assemble_system(co, ce, 2, eps_r=eps, mu_r=mu)
-    refp = fem.assemble_system(co, ce, 2, eps_r=eps, mu_r=mu, pec_facet_mask=pecmask)
+    ref = fem.assemble_system(co, ce, order, eps_r=eps, mu_r=mu)
+    refp = fem.assemble_system(co, ce, order, eps_r=eps, mu_r=mu, pec_facet_mask=pecmask)
     m = dev.DeviceMesh(co, ce)
-    sp = dev.DeviceSpace(m, 2)
+    sp = dev.DeviceSpace(m, order)
     pat = sp.pattern()
     d_eps, d_mu = torch.from_numpy(eps).cuda(), torch.from_numpy(mu).cuda()
     S, T = pat.assemble_ST(d_eps, d_mu, kernel=N.KERNEL_CANONICAL)
@@ -189,7 +190,7 @@ def test_values_canonical_vs_oracle(dev, name):
     assert close(S.cpu().numpy(), Sg.cpu().numpy()) and close(T.cpu().numpy(), Tg.cpu().numpy())
     # homogeneous default coefficients (NULL pointers) and fused PEC
     S1, T1 = pat.assemble_ST(kernel=N.KERNEL_CANONICAL)
-    ref1 = fem.assemble_system(co, ce, 2)
+    ref1 = fem.assemble_system(co, ce, order)
     assert close(S1.cpu().numpy(), ref1['S']) and close(T1.cpu().numpy(), ref1['M'])
     markers = torch.zeros(sp.n_facets, dtype=torch.int32, device='cuda')
     sp.mark_exterior_facets(markers, 999)
