@@ -371,6 +371,7 @@ int sfem_pattern_destroy(sfem_pattern_t pat) {
   cudaFree(pat->ent_cols);
   cudaFree(pat->pos);
   cudaFree(pat->rec);
+  cudaFree(pat->abc_rows);
   delete pat;
   return 0;
 }

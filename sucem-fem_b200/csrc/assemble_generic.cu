@@ -9,6 +9,8 @@
 // geometry factors with the full pre-integrated reference tensor.  Every CSR value is written exactly once,
 // coalesced, without atomics: results are bit-reproducible.  Works for any dim/order and any local position;
 // it is the cross-check for the canonical-frame kernels in assemble_canonical.cu.
+#include <cub/cub.cuh>
+
 #include "sfem_internal.h"
 
 #define SFEM_TABLE static __device__ const
@@ -187,6 +189,8 @@ struct PatView {
   int64_t ent_lo, n_rows, inc_base;
   int nec;
   bool canon;  // slot table in canonical column order
+  const int64_t* row_list;  // optional: only these block-relative row entities are assembled (ABC: boundary rows)
+  int64_t n_list;
 };
 
 constexpr int kWarps = 8;
@@ -201,7 +205,11 @@ k_values_generic(PatView pv, const double* __restrict__ geo, const double* __res
   using El = Elem<DIM, ORDER>;
   constexpr int Q = ORDER, NP = El::NP, NFAC = DIM + 1;
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int64_t r = blockIdx.x * (int64_t)kWarps + w;
+  int64_t r = blockIdx.x * (int64_t)kWarps + w;
+  if (pv.row_list) {
+    if (r >= pv.n_list) return;
+    r = pv.row_list[r];
+  }
   if (r >= pv.n_rows) return;
   const int64_t g = pv.ent_lo + r;
   const int64_t a = pv.ent_rowptr[r];
@@ -266,6 +274,63 @@ k_values_generic(PatView pv, const double* __restrict__ geo, const double* __res
   }
 }
 
+// rows that can carry ABC contributions: row entities with an incident cell that has an exterior facet
+__global__ void k_abc_row_flags(const int64_t* __restrict__ inc_ptr, const int32_t* __restrict__ inc_cell,
+                                const uint8_t* __restrict__ cell_extmask, int64_t ent_lo, int64_t n_rows,
+                                uint8_t* __restrict__ flags) {
+  const int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (r >= n_rows) return;
+  const int64_t g = ent_lo + r;
+  uint8_t f = 0;
+  for (int64_t i = inc_ptr[g]; i < inc_ptr[g + 1]; ++i)
+    if (cell_extmask[inc_cell[i]]) f = 1;
+  flags[r] = f;
+}
+
+__global__ void k_ident_rows(const int64_t* __restrict__ ent_rowptr, const int32_t* __restrict__ ent_cols, int q,
+                             int64_t ent_lo, int64_t n_rows, const uint8_t* __restrict__ flags,
+                             double* __restrict__ vals) {
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t r = blockIdx.x * (int64_t)(blockDim.x >> 5) + w;
+  if (r >= n_rows) return;
+  const int64_t g = ent_lo + r;
+  const int64_t a = ent_rowptr[r];
+  const int len = (int)(ent_rowptr[r + 1] - a);
+  for (int k = 0; k < q; ++k) {
+    if (!flags[q * g + k]) continue;
+    const int64_t rs = (int64_t)q * q * a + (int64_t)k * q * len;
+    for (int idx = lane; idx < q * len; idx += 32) {
+      int s = idx / q, kp = idx - s * q;
+      vals[rs + idx] = (ent_cols[a + s] == g && kp == k) ? 1.0 : 0.0;
+    }
+  }
+}
+
+static int build_abc_rows(sfem_pattern_s* pat, cudaStream_t st) {
+  if (pat->n_abc_rows >= 0) return 0;
+  const sfem_space_s* sp = pat->space;
+  const int64_t n = pat->n_rows_ent;
+  uint8_t* flags = nullptr;
+  int64_t* d_count = nullptr;
+  SFEM_CUDA(cudaMalloc(&flags, std::max<int64_t>(n, 1)));
+  SFEM_CUDA(cudaMalloc(&d_count, 8));
+  SFEM_CUDA(cudaMalloc(&pat->abc_rows, std::max<int64_t>(n, 1) * 8));
+  k_abc_row_flags<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(sp->inc_ptr, sp->inc_cell, sp->cell_extmask,
+                                                            pat->ent_lo, n, flags);
+  cub::CountingInputIterator<int64_t> it(0);
+  size_t tb = 0;
+  SFEM_CUDA(cub::DeviceSelect::Flagged(nullptr, tb, it, flags, pat->abc_rows, d_count, (int)n, st));
+  void* tmp = nullptr;
+  SFEM_CUDA(cudaMalloc(&tmp, tb + 16));
+  SFEM_CUDA(cub::DeviceSelect::Flagged(tmp, tb, it, flags, pat->abc_rows, d_count, (int)n, st));
+  int64_t h = 0;
+  SFEM_CUDA(cudaMemcpyAsync(&h, d_count, 8, cudaMemcpyDeviceToHost, st));
+  SFEM_CUDA(cudaStreamSynchronize(st));
+  cudaFree(tmp); cudaFree(flags); cudaFree(d_count);
+  pat->n_abc_rows = h;
+  return 0;
+}
+
 template <int DIM, int ORDER>
 int launch_generic(const sfem_pattern_s* pat, int form, const double* coef_a, const double* coef_b,
                    const uint8_t* facet_mask, const uint8_t* pec, double* out_a, double* out_b,
@@ -273,9 +338,19 @@ int launch_generic(const sfem_pattern_s* pat, int form, const double* coef_a, co
   const sfem_space_s* sp = pat->space;
   const sfem_mesh_s* m = sp->mesh;
   PatView pv{sp->inc_ptr, sp->inc_cell, sp->inc_loc, pat->ent_rowptr, pat->ent_cols, pat->pos,
-             pat->ent_lo, pat->n_rows_ent, pat->inc_base, sp->n_ent_cell, pos_is_canonical(sp)};
+             pat->ent_lo, pat->n_rows_ent, pat->inc_base, sp->n_ent_cell, pos_is_canonical(sp), nullptr, 0};
   if (pat->n_rows_ent == 0) return 0;
-  const unsigned grid = (unsigned)((pat->n_rows_ent + kWarps - 1) / kWarps);
+  unsigned grid = (unsigned)((pat->n_rows_ent + kWarps - 1) / kWarps);
+  if (form == SFEM_FORM_ABC) {
+    // S_0 lives on the S/M pattern but only rows next to the boundary are non-zero: clear everything at memset
+    // speed, assemble the boundary rows, then write the unit rows of Dirichlet dofs (which may be interior)
+    SFEM_TRY(build_abc_rows(const_cast<sfem_pattern_s*>(pat), st));
+    const int64_t nnz = (int64_t)ORDER * ORDER * pat->nnz_ent;
+    SFEM_CUDA(cudaMemsetAsync(out_a, 0, nnz * sizeof(double), st));
+    pv.row_list = pat->abc_rows;
+    pv.n_list = pat->n_abc_rows;
+    grid = (unsigned)((pat->n_abc_rows + kWarps - 1) / kWarps);
+  }
   const int32_t* cell_facets = DIM == 3 ? sp->cell_faces : sp->cell_edges;
   double* geo = nullptr;
   if (form != SFEM_FORM_ABC) {
@@ -293,8 +368,12 @@ int launch_generic(const sfem_pattern_s* pat, int form, const double* coef_a, co
                                                                    sp->cell_extmask, facet_mask, pec, out_a, nullptr);
       break;
     case SFEM_FORM_ABC:
-      k_values_generic<DIM, ORDER, 2><<<grid, kWarps * 32, 0, st>>>(pv, geo, m->coords, m->cells, cell_facets,
-                                                                   sp->cell_extmask, facet_mask, pec, out_a, nullptr);
+      if (grid > 0)
+        k_values_generic<DIM, ORDER, 2><<<grid, kWarps * 32, 0, st>>>(pv, geo, m->coords, m->cells, cell_facets,
+                                                                     sp->cell_extmask, facet_mask, nullptr, out_a, nullptr);
+      if (pec)
+        k_ident_rows<<<(unsigned)((pat->n_rows_ent + 7) / 8), 256, 0, st>>>(pat->ent_rowptr, pat->ent_cols, ORDER,
+                                                                          pat->ent_lo, pat->n_rows_ent, pec, out_a);
       break;
     default:  // 3: fused S (out_a) and M (out_b)
       k_values_generic<DIM, ORDER, 3><<<grid, kWarps * 32, 0, st>>>(pv, geo, m->coords, m->cells, cell_facets,
