@@ -1,30 +1,33 @@
-// K3 (canonical-frame variant, tetrahedra order 2): the benchmarked S + M(=T) value kernels.
-// Replaces the cell loop of dolfin.assemble + DirichletBC.apply called from
+// K3 (canonical-frame variant, tetrahedra): the benchmarked S + M(=T) value kernels (order 2: k_canon_edges +
+// k_canon_faces; order 1: k_canon1_edges).  Replaces the cell loop of dolfin.assemble + DirichletBC.apply called from
 // /root/reference/sucemfem/SystemMatrices.py:54-55 for the forms of /root/reference/sucemfem/Forms.py:76,84.
 //
 // Work decomposition (row-owner gather, no atomics, bit-reproducible):
 //   * a PAIR of lanes owns one row entity (edge or face) = 2 CSR rows of S and 2 of T, and splits the entity's
 //     incident cells between its two lanes; a warp owns 16 consecutive entities, i.e. one contiguous span of the
-//     value arrays.
-//   * for every incident cell the thread relabels the cell's vertices so that its entity sits at the canonical
-//     position (edge (v0,v1) / face (v0,v1,v2)).  The two element-matrix rows are then straight-line DFMAs whose
-//     reference-tensor coefficients are constant-bank operands (generated/canonical_rows.inc), identical for all
-//     lanes; structural zeros are gone at compile time.  A 64-bit descriptor per local position maps canonical
-//     column entities back to the true ones (orientation fix-up); the slots they land in come precomputed, in
-//     canonical order, in one packed 16-byte record per (entity, cell) (pattern.cu).
+//     value arrays.  Warps are persistent over batches of 16 entities.
+//   * every incident cell is seen RELABELLED so that the row entity sits at the canonical position (edge (v0,v1) /
+//     face (v0,v1,v2)).  The two element-matrix rows are then straight-line DFMAs whose reference-tensor
+//     coefficients are constant-bank operands (generated/canonical_rows.inc), identical for all lanes; structural
+//     zeros are gone at generation time.  A 64-bit descriptor per relabelling maps canonical column entities back to
+//     the true ones (orientation fix-up, branch-free: a sign flip + two adds for edges in the (d, m) basis, two-level
+//     selp.f64 for faces); relabelled vertex ids, slots, descriptor index and ring flags come precomputed in one packed
+//     32-byte record per (entity, cell) (pattern.cu).
 //   * contributions are staged in a per-warp shared-memory tile that is the warp's output span in its FINAL
 //     layout; the span leaves the SM as ONE bulk asynchronous copy (cp.async.bulk shared -> global, the TMA
-//     engine), so global stores cost no LSU wavefronts and are perfectly coalesced.  Faces (<= 2 cells; the 4
-//     shared entities are summed in registers) only store into the tile.  Edges visit their cells in RING order
-//     (consecutive cells share a face through the edge; order precomputed in pattern.cu), carry the three column
-//     entities two neighbouring cells have in common in registers and therefore also store every slot exactly once
-//     (the one exception: where a closed ring closes, three chunks per row are added to the first cell's).
-//   * gathers are the other LSU consumer: one 16-byte record, one 16-byte vertex quadruple, four 32-byte padded
-//     coordinates and one coefficient per (entity, cell); for edges the three dependent hops are software-pipelined
-//     three items deep because the tile limits residency to a few warps per SM.
+//     engine), so global stores cost no LSU wavefronts and are perfectly coalesced.  Faces: one lane per cell, the 4
+//     entities of the shared face are exchanged by shuffle and summed in registers.  Edges visit their cells in RING
+//     order (consecutive cells share a face through the edge; order precomputed in pattern.cu), alternate cells
+//     between the two lanes, hand the three column entities two neighbouring cells have in common over by shuffle and
+//     therefore store every slot exactly once (the one exception: where a closed ring closes, three chunks per row
+//     are added to the first cell's).
+//   * gathers are the other LSU consumer: the record (2 x 16 B), four 32-byte padded coordinates and two
+//     coefficients per (entity, cell).  The chain record -> coordinates is issued two / one items ahead, straight
+//     into the single item buffer once the current item's geometry has been computed; at the last step of a pass the
+//     buffer receives the first item of the NEXT pass (S -> T: same batch, T -> S: next batch).
 //   * PEC rows are overwritten with unit rows in the tile before it is stored (row-only ident fused).
 // Geometry (J, detJ, J^-1 J^-T, J^T J) is recomputed per (entity, cell) from the gathered coordinates: ~70 flops
-// against ~170 DFMAs of tensor contraction per matrix, cheaper than staging per-cell geometry through HBM.
+// against ~160 DFMAs of tensor contraction per matrix, cheaper than staging per-cell geometry through HBM.
 #include "sfem_internal.h"
 
 #define SFEM_TABLE static __device__ const

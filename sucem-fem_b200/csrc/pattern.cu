@@ -7,6 +7,8 @@
 //   one warp per row entity: gather the entities of its incident cells, rank-sort + unique in shared
 //   memory, count -> scan (int64) -> fill; the same pass records pos[incidence][u] = slot of the cell's
 //   u-th entity in the row (the "precomputed CSR value slots" the value kernels scatter into).
+// For tetrahedra it also writes the packed 32-byte item records the canonical-frame kernels stream (faces here,
+// edges -- in ring order -- in k_edge_ring).
 #include <cub/cub.cuh>
 
 #include "sfem_internal.h"
