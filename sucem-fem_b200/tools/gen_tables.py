@@ -160,8 +160,31 @@ def tables_for(dim, order):
     return out
 
 
+def basis_module():
+    """sucemfem/_generated_basis.py: monomial coefficients of the nodal basis functions on the reference tetrahedron
+    (orders 1, 2), for point evaluation on the host (sources)."""
+    out = '"""GENERATED by tools/gen_tables.py -- do not edit.  BASIS[order] = (exponents [n_mono][3], coefficients\n'
+    out += '[ndof][3][n_mono]): reference basis function j, component d = sum_m coef[j][d][m] * x^e0 y^e1 z^e2."""\n'
+    out += 'BASIS = {}\n'
+    for order in (1, 2):
+        X, verts, basis = build_basis(3, order)
+        monos = sorted({m for phi in basis for d in range(3) for m in sp.Poly(phi[d], *X).monoms()})
+        out += 'BASIS[%d] = (%r,\n [' % (order, [list(m) for m in monos])
+        for phi in basis:
+            rows = []
+            for d in range(3):
+                poly = sp.Poly(phi[d], *X)
+                cd = dict(zip(poly.monoms(), poly.coeffs()))
+                rows.append([float(cd.get(m, 0)) for m in monos])
+            out += repr(rows) + ',\n  '
+        out += '])\n'
+    return out
+
+
 def main():
     here = os.path.dirname(os.path.abspath(__file__))
+    with open(os.path.join(here, '..', 'sucemfem', '_generated_basis.py'), 'w') as f:
+        f.write(basis_module())
     dst = os.path.join(here, '..', 'csrc', 'generated', 'n1curl_tables.inc')
     out = '// GENERATED by tools/gen_tables.py -- do not edit.  See that file for definitions.\n'
     for dim in (3, 2):

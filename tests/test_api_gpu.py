@@ -210,3 +210,113 @@ def test_high_valence_edge_falls_back_to_generic_kernel():
     S, T = pat.assemble_ST(kernel=N.KERNEL_CANONICAL)
     assert np.all(np.abs(S.cpu().numpy() - ref['S']) <= 1e-12 * np.abs(ref['S']) + 1e-15 * np.abs(ref['S']).max())
     assert np.all(np.abs(T.cpu().numpy() - ref['M']) <= 1e-12 * np.abs(ref['M']) + 1e-15 * np.abs(ref['M']).max())
+
+
+def _driven_problem(mesh, order, sources, freq):
+    from sucemfem import dolfin_compat as dolfin
+    from sucemfem.BoundaryConditions import ABCBoundaryCondition, BoundaryConditions
+    from sucemfem.ProblemConfigurations.EMDrivenProblem import DrivenProblemABC
+    material_mesh_func = dolfin.MeshFunction('uint', mesh, 3)
+    material_mesh_func.set_all(0)
+    abc = ABCBoundaryCondition()
+    abc.set_region_number(1)
+    bcs = BoundaryConditions()
+    bcs.add_boundary_condition(abc)
+    dp = DrivenProblemABC()
+    dp.set_mesh(mesh)
+    dp.set_basis_order(order)
+    dp.set_material_regions({0: dict(eps_r=1, mu_r=1)})
+    dp.set_region_meshfunction(material_mesh_func)
+    dp.set_boundary_conditions(bcs)
+    dp.set_sources(sources)
+    dp.init_problem()
+    dp.set_frequency(freq)
+    return dp
+
+
+def test_get_RHS_reference_fixture():
+    """/root/reference/sucemfem/ProblemConfigurations/tests/test_EMDrivenProblem.py:74-82: point dipole [2,-1,3] at the
+    origin of InscribedTet, order 1; RHS vs RHS_vector.pickle with the reference's rtol=1e-12, atol=1e-16."""
+    from sucemfem.Testing import Meshes
+    from sucemfem.Sources import point_source, current_source
+    g = np.load(os.path.join(GOLDEN, 'driven_order1_inscribedtet.npz'))
+    srcs = current_source.CurrentSources()
+    dipole = point_source.PointCurrentSource()
+    dipole.set_position(np.array([0, 0, 0.]))
+    dipole.set_value(np.array([2, -1, 3.]))
+    srcs.add_source(dipole)
+    dp = _driven_problem(Meshes.InscribedTet().get_dolfin_mesh(), 1, srcs, 1e8)
+    assert np.allclose(dp.get_RHS(), g['RHS'], rtol=1e-12, atol=1e-16)
+
+
+def test_fillament_source_reference_fixture():
+    """/root/reference/sucemfem/Sources/tests/test_fillament_source.py:45-82: order-2 dof numbers and values of a
+    20-point current filament on get_centred_cube(lambda/2, lambda/3); the 26 significant entries of the fixture (the
+    rest is round-off on a shared face where DOLFIN's point location picked the other cell)."""
+    from sucemfem import dolfin_compat as dolfin
+    from sucemfem.Utilities.MeshGenerators import get_centred_cube
+    from sucemfem.Sources.fillament_current_source import FillamentCurrentSource
+    g = np.load(os.path.join(GOLDEN, 'fillament_source_order2.npz'))
+    mesh = get_centred_cube(g['domain_size'], float(g['max_edge_len']))
+    V = dolfin.FunctionSpace(mesh, "Nedelec 1st kind H(curl)", int(g['order']))
+    DUT = FillamentCurrentSource()
+    DUT.set_function_space(V)
+    DUT.set_no_integration_points(int(g['no_integration_points']))
+    DUT.set_source_endpoints(g['source_endpoints'])
+    DUT.set_value(float(g['I']))
+    dofnos, rhs = DUT.get_contribution()
+    sig = np.abs(g['rhs_contribs']) > 1e-12
+    mine = dict(zip(dofnos.tolist(), rhs))
+    assert sorted(k for k, v in mine.items() if abs(v) > 1e-12) == sorted(g['dofnos'][sig].tolist())
+    got = np.array([mine[k] for k in g['dofnos'][sig].tolist()])
+    assert np.allclose(got, g['rhs_contribs'][sig], rtol=1e-10, atol=1e-12)
+    # test_negative_direction (:71-82)
+    DUT.set_source_endpoints(-g['source_endpoints'])
+    dn2, rhs2 = DUT.get_contribution()
+    m2 = dict(zip(dn2.tolist(), rhs2))
+    assert all(abs(mine[k] + m2[k]) < 1e-12 for k in mine if abs(mine[k]) > 1e-12)
+
+
+def test_driven_solution_reference_fixture_order2():
+    """The reference's shipped order-2 solution vector (power_flux_reference_dofs..., generated by
+    sucemfem/PostProcessing/tests/data/power_flux_generate_dofs.py:44-92: lambda/4 cube, lambda/6 edges, 100-point
+    filament, UMFPACK) is reproduced by the PRODUCT path end to end: device S, M, S_0 + host sources + sparse solve."""
+    import scipy.sparse.linalg as spla
+    from sucemfem.Utilities.MeshGenerators import get_centred_cube
+    from sucemfem.Sources import current_source
+    from sucemfem.Sources.fillament_current_source import FillamentCurrentSource
+    g = np.load(os.path.join(GOLDEN, 'driven_order2_unitcube3.npz'))
+    freq = float(g['freq'])
+    lam = c0 / freq
+    mesh = get_centred_cube(np.array([lam] * 3) * 0.25, lam / 6)
+    srcs = current_source.CurrentSources()
+    fil = FillamentCurrentSource()
+    fil.set_source_endpoints(g['source_endpoints'])
+    fil.set_value(float(g['I']))
+    srcs.add_source(fil)
+    dp = _driven_problem(mesh, 2, srcs, freq)
+    assert dp.get_global_dimension() == 1314
+    A, b = dp.get_LHS_matrix(), dp.get_RHS()
+    x = spla.spsolve(A.tocsc(), b)
+    assert np.linalg.norm(x - g['x']) / np.linalg.norm(g['x']) < 1e-11
+
+
+def test_driven_residual_reference_fixture_unitcube5():
+    """reference_dofs-2-... (sucemfem/PostProcessing/tests/data/ntff_generate_dofs.py:40-85: UnitCube(5) recentred on
+    the dipole, order 2, ABC): the shipped solution satisfies the product's A x = b to 1e-11."""
+    from sucemfem.Utilities.MeshGenerators import get_centred_cube
+    from sucemfem.Sources import current_source, point_source
+    g = np.load(os.path.join(GOLDEN, 'driven_order2_unitcube5.npz'))
+    freq = float(g['freq'])
+    lam = c0 / freq
+    source_coord = np.array([0, 0, 0.])
+    mesh = get_centred_cube(g['domain_size'], float(g['max_edge_len']), source_coord)
+    srcs = current_source.CurrentSources()
+    dipole = point_source.PointCurrentSource()
+    dipole.set_position(source_coord)
+    dipole.set_value(np.array([0, 0, 1.]) * lam / 1000)
+    srcs.add_source(dipole)
+    dp = _driven_problem(mesh, 2, srcs, freq)
+    assert dp.get_global_dimension() == 5530
+    A, b = dp.get_LHS_matrix(), dp.get_RHS()
+    assert np.linalg.norm(A @ g['x'] - b) / np.linalg.norm(b) < 1e-11
