@@ -25,6 +25,7 @@
 #ifndef SUCEM_B200_H
 #define SUCEM_B200_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #if defined(__GNUC__)
@@ -40,6 +41,7 @@ extern "C" {
 typedef struct sfem_mesh_s* sfem_mesh_t;
 typedef struct sfem_space_s* sfem_space_t;
 typedef struct sfem_pattern_s* sfem_pattern_t;
+typedef struct sfem_host_job_s* sfem_host_job_t;
 
 /* forms: which bilinear form a value array is assembled for */
 enum {
@@ -58,6 +60,11 @@ enum {
 SFEM_API const char* sfem_last_error(void);
 /* "sucem_b200 <version> sm_100a" */
 SFEM_API const char* sfem_version(void);
+
+/* Library-owned device buffers are stream-ordered allocations from the current device's default memory pool, kept
+ * cached when handles are destroyed (repeated set-ups reuse them).  This returns the cached memory to the driver
+ * (synchronises the device).  Buffers of a handle are freed in the order of the stream the handle was created on. */
+SFEM_API int sfem_release_cached_memory(void);
 
 /* ---- mesh: replaces dolfin.Mesh / UnitCube / UnitSquare as inputs of the path -------------------
  * (examples/resonant_cavity/driver.py:34, sucemfem/Utilities/MeshGenerators.py:32-36).
@@ -115,6 +122,12 @@ SFEM_API int sfem_pattern_info(sfem_pattern_t pat, int64_t* row_begin, int64_t* 
 SFEM_API int sfem_pattern_export(sfem_pattern_t pat, int64_t* d_rowptr, int32_t* d_cols, void* stream);
 /* Split [0, n_entities) into nparts contiguous entity ranges of (nearly) equal nnz; host int64 [nparts+1]. */
 SFEM_API int sfem_partition_rows(sfem_space_t space, int nparts, int64_t* ent_bounds, void* stream);
+/* The same split inside each entity class: edge_bounds[p..p+1] is a range of [0, n_edges), other_bounds[p..p+1]
+ * a range of [n_edges, n_entities) (faces in 3-D, cell interiors in 2-D at order 2; empty at order 1), each
+ * balanced by incidence count; host int64 [nparts+1] each.  A rank that owns one range of each class (two
+ * patterns) runs the same mix of edge-row and face-row work as every other rank. */
+SFEM_API int sfem_partition_rows_by_class(sfem_space_t space, int nparts, int64_t* edge_bounds, int64_t* other_bounds,
+                                 void* stream);
 
 /* ---- values: replaces dolfin.assemble(form, tensor=mat) + apply_essential(mat)
  * (sucemfem/SystemMatrices.py:54-55).  d_coef: per-cell double [n_cells] (eps_r for MASS, mu_r for
@@ -135,6 +148,40 @@ SFEM_API int sfem_launches_per_assemble_ST(sfem_pattern_t pat, int kernel);
  * sucemfem/BoundaryConditions/container.py:39-42) as a separate step on already assembled values:
  * flagged rows of the block become unit rows, pattern kept, columns untouched. */
 SFEM_API int sfem_apply_ident(sfem_pattern_t pat, const uint8_t* d_row_flags, double* d_values, void* stream);
+
+/* ---- host-buffer entry points: the whole path with HOST arrays in and out --------------------------------------
+ * What a host consumer gets from the reference today: FunctionSpace(mesh, family, order) (EMProblem.py:100-105),
+ * assemble(M), assemble(S) [, assemble(S_0)] + apply_essential (SystemMatrices.py:54-55) and A.data()
+ * (Utilities/Converters.py:37).  All pointers of these calls are HOST pointers; page-locked memory
+ * (sfem_host_alloc, cudaHostRegister, torch pin_memory) lets the copies run at PCIe rate and asynchronously.
+ *
+ * sfem_host_job_create: copies the mesh (h_coords double [n_vertices][gdim], h_cells int32 [n_cells][gdim+1], UFC
+ *   order) and the per-cell coefficients (h_eps_r / h_mu_r double [n_cells] or NULL = 1.0) to the device, numbers the
+ *   entities, marks the PEC rows and counts the pattern; returns ndof and nnz so that the caller can size the outputs.
+ *   pec_mode 0: no essential condition; 1: all exterior facets (PECWallsBoundaryCondition, essential.py:86-99);
+ *   2: facets with h_facet_markers[f] == pec_region (uint32 [n_facets], first-appearance facet numbering).
+ * sfem_host_job_run: streams the rows in n_blocks blocks of equal non-zeros (<= 0: chosen by the library): pattern
+ *   fill + values + CSR expansion of block k on `stream` overlap the device->host copy of block k-1.  Outputs:
+ *   h_rowptr int64 [ndof+1], h_cols int32 [nnz], h_S / h_T / h_S0 double [nnz]; any of cols/S/T/S0 may be NULL
+ *   (skipped).  Returns when all outputs are complete.  Device memory in flight: two blocks. */
+SFEM_API int sfem_host_job_create(int gdim, int64_t n_vertices, const double* h_coords, int64_t n_cells,
+                         const int32_t* h_cells, int order, const double* h_eps_r, const double* h_mu_r, int pec_mode,
+                         const uint32_t* h_facet_markers, uint32_t pec_region, void* stream, int64_t* ndof,
+                         int64_t* nnz, sfem_host_job_t* out);
+SFEM_API int sfem_host_job_run(sfem_host_job_t job, int64_t* h_rowptr, int32_t* h_cols, double* h_S, double* h_T,
+                      double* h_S0, int n_blocks);
+SFEM_API int sfem_host_job_destroy(sfem_host_job_t job);
+/* The same streaming hand-off for a space that already lives on the device (what the sucemfem mirror calls when the
+ * MatrixClass is the host matrix, EMDrivenProblem.py:82-87): sfem_space_count_nnz sizes the outputs (one count pass
+ * over all rows, cached in the space), sfem_space_assemble_to_host streams the row blocks.  d_* are DEVICE arrays
+ * (d_eps_r / d_mu_r double [n_cells] or NULL = 1.0; d_pec_row_flags uint8 [ndof] or NULL), h_* HOST arrays as above. */
+SFEM_API int sfem_space_count_nnz(sfem_space_t space, void* stream, int64_t* nnz);
+SFEM_API int sfem_space_assemble_to_host(sfem_space_t space, const double* d_eps_r, const double* d_mu_r,
+                                const uint8_t* d_pec_row_flags, int64_t* h_rowptr, int32_t* h_cols, double* h_S,
+                                double* h_T, double* h_S0, int n_blocks, void* stream);
+/* page-locked host memory for the arrays above (cudaHostAlloc / cudaFreeHost) */
+SFEM_API int sfem_host_alloc(size_t bytes, void** out);
+SFEM_API int sfem_host_free(void* p);
 
 #ifdef __cplusplus
 }

@@ -17,6 +17,7 @@ def _lib():
         subprocess.check_call(['make', '-C', _HERE])
     lib = C.CDLL(_SO)
     lib.oc_pattern.restype = C.c_int64
+    lib.oc_pattern_mt.restype = C.c_int64
     return lib
 
 
@@ -27,7 +28,7 @@ def _p(a):
 class CPUAssembler(object):
     """Numbering + pattern once (untimed set-up), then assemble() = the timed DOLFIN-style cell loop."""
 
-    def __init__(self, coords, cells, order):
+    def __init__(self, coords, cells, order, threads=1):
         self.lib = _lib()
         self.coords = np.ascontiguousarray(coords, np.float64)
         self.cells = np.ascontiguousarray(cells, np.int32)
@@ -45,9 +46,11 @@ class CPUAssembler(object):
         self.lib.oc_cell_dofs(_p(self.cell_edges), _p(self.cell_faces), C.c_int64(Cn), C.c_int64(self.E), order,
                               _p(self.cd))
         self.rowptr = np.empty(self.ndof + 1, np.int64)
-        nnz = self.lib.oc_pattern(_p(self.cd), C.c_int64(Cn), self.nd, C.c_int64(self.ndof), _p(self.rowptr), None)
+        nnz = self.lib.oc_pattern_mt(_p(self.cd), C.c_int64(Cn), self.nd, C.c_int64(self.ndof), _p(self.rowptr), None,
+                                     threads)
         self.cols = np.empty(nnz, np.int32)
-        self.lib.oc_pattern(_p(self.cd), C.c_int64(Cn), self.nd, C.c_int64(self.ndof), _p(self.rowptr), _p(self.cols))
+        self.lib.oc_pattern_mt(_p(self.cd), C.c_int64(Cn), self.nd, C.c_int64(self.ndof), _p(self.rowptr), _p(self.cols),
+                               threads)
         self.Mhat = np.ascontiguousarray(R.mass_tensor(3, order))
         self.Chat = np.ascontiguousarray(R.curl_tensor(3, order))
 

@@ -91,8 +91,31 @@ void oc_cell_dofs(const int32_t* cell_edges, const int32_t* cell_faces, int64_t 
   }
 }
 
-/* pattern: two passes (count, fill) over a dof -> cells incidence built by counting sort */
-int64_t oc_pattern(const int32_t* cd, int64_t C, int nd, int64_t ndof, int64_t* rowptr, int32_t* cols /* may be NULL */) {
+/* in-place ascending sort of int32 (median-of-three quicksort, insertion sort below 16) */
+static void sort_i32(int32_t* a, int64_t n) {
+  while (n > 16) {
+    int32_t x = a[0], y = a[n / 2], z = a[n - 1], p;
+    if (x > y) { int32_t t = x; x = y; y = t; }
+    p = z < x ? x : (z > y ? y : z);
+    int64_t i = 0, j = n - 1;
+    while (i <= j) {
+      while (a[i] < p) ++i;
+      while (a[j] > p) --j;
+      if (i <= j) { int32_t t = a[i]; a[i] = a[j]; a[j] = t; ++i; --j; }
+    }
+    if (j + 1 < n - i) { sort_i32(a, j + 1); a += i; n -= i; } else { sort_i32(a + i, n - i); n = j + 1; }
+  }
+  for (int64_t i = 1; i < n; ++i) {
+    int32_t v = a[i]; int64_t j = i - 1;
+    while (j >= 0 && a[j] > v) { a[j + 1] = a[j]; --j; }
+    a[j + 1] = v;
+  }
+}
+
+/* pattern (DOLFIN SparsityPatternBuilder + tensor init): a dof -> cells incidence by counting sort, then per row the
+ * sorted union of the incident cells' dof lists.  cols == NULL: count only (rowptr filled); otherwise rowptr must hold
+ * the result of the count call and cols is filled.  Rows are independent: OpenMP over rows when threads > 1. */
+int64_t oc_pattern_mt(const int32_t* cd, int64_t C, int nd, int64_t ndof, int64_t* rowptr, int32_t* cols, int threads) {
   int64_t* ptr = (int64_t*)calloc(ndof + 1, sizeof(int64_t));
   int64_t i, c, r; int j;
   for (i = 0; i < C * nd; ++i) ptr[cd[i] + 1]++;
@@ -101,19 +124,40 @@ int64_t oc_pattern(const int32_t* cd, int64_t C, int nd, int64_t ndof, int64_t* 
   int64_t* fill = (int64_t*)malloc(sizeof(int64_t) * ndof);
   memcpy(fill, ptr, sizeof(int64_t) * ndof);
   for (c = 0; c < C; ++c) for (j = 0; j < nd; ++j) inc[fill[cd[c * nd + j]]++] = (int32_t)c;
-  int64_t cap = 4096; int64_t* tmp = (int64_t*)malloc(sizeof(int64_t) * cap);
-  int64_t nnz = 0;
-  rowptr[0] = 0;
-  for (r = 0; r < ndof; ++r) {
-    int64_t m = (ptr[r + 1] - ptr[r]) * nd, k = 0, u = 0;
-    if (m > cap) { cap = 2 * m; tmp = (int64_t*)realloc(tmp, sizeof(int64_t) * cap); }
-    for (i = ptr[r]; i < ptr[r + 1]; ++i) for (j = 0; j < nd; ++j) tmp[k++] = cd[(int64_t)inc[i] * nd + j];
-    qsort(tmp, m, sizeof(int64_t), cmp_i64);
-    for (i = 0; i < m; ++i) if (i == 0 || tmp[i] != tmp[i - 1]) { if (cols) cols[nnz + u] = (int32_t)tmp[i]; ++u; }
-    nnz += u; rowptr[r + 1] = nnz;
+  int64_t maxm = 0;
+  for (r = 0; r < ndof; ++r) if ((ptr[r + 1] - ptr[r]) * nd > maxm) maxm = (ptr[r + 1] - ptr[r]) * nd;
+#ifdef _OPENMP
+  if (threads < 1) threads = omp_get_max_threads();
+#pragma omp parallel num_threads(threads) if (threads > 1)
+#endif
+  {
+    int32_t* tmp = (int32_t*)malloc(sizeof(int32_t) * (maxm + 1));
+    int64_t rr;
+#ifdef _OPENMP
+#pragma omp for schedule(static, 1024)
+#endif
+    for (rr = 0; rr < ndof; ++rr) {
+      int64_t m = (ptr[rr + 1] - ptr[rr]) * nd, k = 0, u = 0, ii; int jj;
+      for (ii = ptr[rr]; ii < ptr[rr + 1]; ++ii) for (jj = 0; jj < nd; ++jj) tmp[k++] = cd[(int64_t)inc[ii] * nd + jj];
+      sort_i32(tmp, m);
+      if (cols) {
+        int32_t* out = cols + rowptr[rr];
+        for (ii = 0; ii < m; ++ii) if (ii == 0 || tmp[ii] != tmp[ii - 1]) out[u++] = tmp[ii];
+      } else {
+        for (ii = 0; ii < m; ++ii) if (ii == 0 || tmp[ii] != tmp[ii - 1]) ++u;
+        rowptr[rr + 1] = u;
+      }
+    }
+    free(tmp);
   }
-  free(tmp); free(fill); free(inc); free(ptr);
+  if (!cols) { rowptr[0] = 0; for (r = 0; r < ndof; ++r) rowptr[r + 1] += rowptr[r]; }
+  int64_t nnz = rowptr[ndof];
+  free(fill); free(inc); free(ptr);
   return nnz;
+}
+
+int64_t oc_pattern(const int32_t* cd, int64_t C, int nd, int64_t ndof, int64_t* rowptr, int32_t* cols /* may be NULL */) {
+  return oc_pattern_mt(cd, C, nd, ndof, rowptr, cols, 1);
 }
 
 static inline int64_t find_slot(const int64_t* rowptr, const int32_t* cols, int32_t r, int32_t c) {

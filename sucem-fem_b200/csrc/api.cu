@@ -11,6 +11,23 @@ namespace sfem {
 static thread_local std::string g_last_error;
 void set_error(const std::string& msg) { g_last_error = msg; }
 
+cudaError_t dev_malloc_bytes(void** p, size_t bytes, cudaStream_t st) {
+  static bool pool_ready[64] = {};
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  if (dev >= 0 && dev < 64 && !pool_ready[dev]) {  // idempotent: a race only repeats the same attribute write
+    cudaMemPool_t pool;
+    e = cudaDeviceGetDefaultMemPool(&pool, dev);
+    if (e != cudaSuccess) return e;
+    uint64_t keep = ~0ull;
+    e = cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    if (e != cudaSuccess) return e;
+    pool_ready[dev] = true;
+  }
+  return cudaMallocAsync(p, bytes ? bytes : 16, st);
+}
+
 namespace {
 inline unsigned grid_for(int64_t n, int bs = 256) { return (unsigned)((n + bs - 1) / bs); }
 
@@ -149,6 +166,22 @@ __global__ void k_find_bounds(const int64_t* __restrict__ inc_ptr, int64_t E, in
   out[p] = p == nparts ? n : lo;
 }
 
+// the same split inside one entity class [g0, g1) (edges, or faces / cell interiors): rank p then owns one range of
+// each class, so every rank runs the same mix of edge-row and face-row work
+__global__ void k_find_bounds_class(const int64_t* __restrict__ inc_ptr, int64_t g0, int64_t g1, int nparts,
+                                    int64_t* __restrict__ out) {
+  int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p > nparts) return;
+  const __int128 total = inc_ptr[g1] - inc_ptr[g0];
+  const int64_t target = inc_ptr[g0] + (int64_t)(total * p / nparts);
+  int64_t lo = g0, hi = g1;
+  while (lo < hi) {
+    int64_t mid = (lo + hi) >> 1;
+    if (inc_ptr[mid] < target) lo = mid + 1; else hi = mid;
+  }
+  out[p] = p == nparts ? g1 : (p == 0 ? g0 : lo);
+}
+
 // row-only ident on assembled values: one warp per row entity
 __global__ void k_ident(const int64_t* __restrict__ ent_rowptr, const int32_t* __restrict__ ent_cols, int q,
                         int64_t ent_lo, int64_t n_rows, const uint8_t* __restrict__ flags,
@@ -198,6 +231,16 @@ int sfem_mesh_create(int gdim, int64_t n_vertices, const double* d_coords, int64
   return 0;
 }
 
+int sfem_release_cached_memory(void) {
+  int dev = 0;
+  SFEM_CUDA(cudaGetDevice(&dev));
+  cudaMemPool_t pool;
+  SFEM_CUDA(cudaDeviceGetDefaultMemPool(&pool, dev));
+  SFEM_CUDA(cudaDeviceSynchronize());
+  SFEM_CUDA(cudaMemPoolTrimTo(pool, 0));
+  return 0;
+}
+
 int sfem_mesh_destroy(sfem_mesh_t mesh) {
   delete mesh;
   return 0;
@@ -230,6 +273,7 @@ int sfem_space_create(sfem_mesh_t mesh, int order, void* stream, sfem_space_t* o
   auto* sp = new sfem_space_s();
   sp->mesh = mesh;
   sp->device = mesh->device;
+  sp->stream = (cudaStream_t)stream;
   sp->order = order;
   int rc = build_numbering(sp, (cudaStream_t)stream);
   if (rc != 0) {
@@ -243,17 +287,23 @@ int sfem_space_create(sfem_mesh_t mesh, int order, void* stream, sfem_space_t* o
 int sfem_space_destroy(sfem_space_t sp) {
   if (!sp) return 0;
   DeviceGuard dg(sp->device);
-  cudaFree(sp->cell_edges);
-  cudaFree(sp->cell_faces);
-  cudaFree(sp->inc_ptr);
-  cudaFree(sp->inc_cell);
-  cudaFree(sp->inc_loc);
-  cudaFree(sp->facet_ncells);
-  cudaFree(sp->facet_first_cell);
-  cudaFree(sp->facet_first_loc);
-  cudaFree(sp->cell_extmask);
-  cudaFree(sp->coords4);
-  cudaFree(sp->ones);
+  cudaStream_t st = sp->stream;
+  dev_free(sp->cell_edges, st);
+  dev_free(sp->cell_faces, st);
+  dev_free(sp->inc_ptr, st);
+  dev_free(sp->inc_cell, st);
+  dev_free(sp->inc_loc, st);
+  dev_free(sp->facet_ncells, st);
+  dev_free(sp->facet_first_cell, st);
+  dev_free(sp->facet_first_loc, st);
+  dev_free(sp->cell_extmask, st);
+  dev_free(sp->coords4, st);
+  dev_free(sp->ones, st);
+  dev_free(sp->rowptr_all, st);
+  if (sp->drain) {
+    cudaStreamSynchronize(sp->drain);
+    cudaStreamDestroy(sp->drain);
+  }
   delete sp;
   return 0;
 }
@@ -323,9 +373,9 @@ int sfem_expand_material(int64_t n_cells, const uint32_t* d_regions, int n_regio
   uint32_t* d_ids = nullptr;
   double* d_vals = nullptr;
   unsigned long long* d_bad = nullptr;
-  SFEM_CUDA(cudaMalloc(&d_ids, n_regions * 4));
-  SFEM_CUDA(cudaMalloc(&d_vals, n_regions * 8));
-  SFEM_CUDA(cudaMalloc(&d_bad, 8));
+  SFEM_CUDA(dev_malloc(&d_ids, n_regions * 4, st));
+  SFEM_CUDA(dev_malloc(&d_vals, n_regions * 8, st));
+  SFEM_CUDA(dev_malloc(&d_bad, 8, st));
   SFEM_CUDA(cudaMemcpyAsync(d_ids, region_ids, n_regions * 4, cudaMemcpyHostToDevice, st));
   SFEM_CUDA(cudaMemcpyAsync(d_vals, values, n_regions * 8, cudaMemcpyHostToDevice, st));
   SFEM_CUDA(cudaMemsetAsync(d_bad, 0xff, 8, st));
@@ -333,9 +383,9 @@ int sfem_expand_material(int64_t n_cells, const uint32_t* d_regions, int n_regio
   unsigned long long h_bad = 0;
   SFEM_CUDA(cudaMemcpyAsync(&h_bad, d_bad, 8, cudaMemcpyDeviceToHost, st));
   SFEM_CUDA(cudaStreamSynchronize(st));
-  cudaFree(d_ids);
-  cudaFree(d_vals);
-  cudaFree(d_bad);
+  dev_free(d_ids, st);
+  dev_free(d_vals, st);
+  dev_free(d_bad, st);
   if (h_bad != ~0ull) {
     if (bad_region) *bad_region = (uint32_t)(h_bad & 0xffffffffu);
     set_error("Material number " + std::to_string((uint32_t)(h_bad & 0xffffffffu)) + " not found");
@@ -352,6 +402,7 @@ int sfem_pattern_create(sfem_space_t sp, int64_t ent_lo, int64_t ent_hi, void* s
   auto* pat = new sfem_pattern_s();
   pat->space = sp;
   pat->device = sp->device;
+  pat->stream = (cudaStream_t)stream;
   pat->ent_lo = ent_lo;
   pat->ent_hi = ent_hi;
   pat->n_rows_ent = ent_hi - ent_lo;
@@ -367,11 +418,12 @@ int sfem_pattern_create(sfem_space_t sp, int64_t ent_lo, int64_t ent_hi, void* s
 int sfem_pattern_destroy(sfem_pattern_t pat) {
   if (!pat) return 0;
   DeviceGuard dg(pat->device);
-  cudaFree(pat->ent_rowptr);
-  cudaFree(pat->ent_cols);
-  cudaFree(pat->pos);
-  cudaFree(pat->rec);
-  cudaFree(pat->abc_rows);
+  cudaStream_t st = pat->stream;
+  dev_free(pat->ent_rowptr, st);
+  dev_free(pat->ent_cols, st);
+  dev_free(pat->pos, st);
+  dev_free(pat->rec, st);
+  dev_free(pat->abc_rows, st);
   delete pat;
   return 0;
 }
@@ -397,12 +449,28 @@ int sfem_partition_rows(sfem_space_t sp, int nparts, int64_t* ent_bounds, void* 
   DeviceGuard dg(sp->mesh->device);
   cudaStream_t st = (cudaStream_t)stream;
   int64_t* d_out = nullptr;
-  SFEM_CUDA(cudaMalloc(&d_out, (nparts + 1) * 8));
+  SFEM_CUDA(dev_malloc(&d_out, (nparts + 1) * 8, st));
   k_find_bounds<<<grid_for(nparts + 1, 64), 64, 0, st>>>(sp->inc_ptr, std::min(sp->E, sp->n_ent), sp->n_ent, nparts, d_out);
   SFEM_CUDA(cudaMemcpyAsync(ent_bounds, d_out, (nparts + 1) * 8, cudaMemcpyDeviceToHost, st));
   SFEM_CUDA(cudaStreamSynchronize(st));
-  cudaFree(d_out);
+  dev_free(d_out, st);
   ent_bounds[0] = 0;
+  return 0;
+}
+
+int sfem_partition_rows_by_class(sfem_space_t sp, int nparts, int64_t* edge_bounds, int64_t* other_bounds, void* stream) {
+  SFEM_CHECK(sp && edge_bounds && other_bounds && nparts > 0, "bad arguments");
+  DeviceGuard dg(sp->mesh->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  int64_t* d_out = nullptr;
+  SFEM_CUDA(dev_malloc(&d_out, 2 * (nparts + 1) * 8, st));
+  const int64_t E = std::min(sp->E, sp->n_ent);
+  k_find_bounds_class<<<grid_for(nparts + 1, 64), 64, 0, st>>>(sp->inc_ptr, 0, E, nparts, d_out);
+  k_find_bounds_class<<<grid_for(nparts + 1, 64), 64, 0, st>>>(sp->inc_ptr, E, sp->n_ent, nparts, d_out + nparts + 1);
+  SFEM_CUDA(cudaMemcpyAsync(edge_bounds, d_out, (nparts + 1) * 8, cudaMemcpyDeviceToHost, st));
+  SFEM_CUDA(cudaMemcpyAsync(other_bounds, d_out + nparts + 1, (nparts + 1) * 8, cudaMemcpyDeviceToHost, st));
+  SFEM_CUDA(cudaStreamSynchronize(st));
+  dev_free(d_out, st);
   return 0;
 }
 

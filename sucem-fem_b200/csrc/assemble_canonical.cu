@@ -791,7 +791,7 @@ int assemble_canonical_ST(const sfem_pattern_s* pat, const double* eps, const do
   const sfem_mesh_s* m = sp->mesh;
   if (!eps || !mu) {  // default coefficients: the kernels always read a per-cell array
     if (!sp->ones) {
-      SFEM_CUDA(cudaMalloc(&sp->ones, m->C * sizeof(double)));
+      SFEM_CUDA(dev_malloc(&sp->ones, m->C * sizeof(double), st));
       k_fill_ones<<<(unsigned)((m->C + 255) / 256), 256, 0, st>>>(sp->ones, m->C);
     }
     if (!eps) eps = sp->ones;

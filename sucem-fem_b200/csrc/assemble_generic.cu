@@ -312,21 +312,21 @@ static int build_abc_rows(sfem_pattern_s* pat, cudaStream_t st) {
   const int64_t n = pat->n_rows_ent;
   uint8_t* flags = nullptr;
   int64_t* d_count = nullptr;
-  SFEM_CUDA(cudaMalloc(&flags, std::max<int64_t>(n, 1)));
-  SFEM_CUDA(cudaMalloc(&d_count, 8));
-  SFEM_CUDA(cudaMalloc(&pat->abc_rows, std::max<int64_t>(n, 1) * 8));
+  SFEM_CUDA(dev_malloc(&flags, std::max<int64_t>(n, 1), st));
+  SFEM_CUDA(dev_malloc(&d_count, 8, st));
+  SFEM_CUDA(dev_malloc(&pat->abc_rows, std::max<int64_t>(n, 1) * 8, st));
   k_abc_row_flags<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(sp->inc_ptr, sp->inc_cell, sp->cell_extmask,
                                                             pat->ent_lo, n, flags);
   cub::CountingInputIterator<int64_t> it(0);
   size_t tb = 0;
   SFEM_CUDA(cub::DeviceSelect::Flagged(nullptr, tb, it, flags, pat->abc_rows, d_count, (int)n, st));
   void* tmp = nullptr;
-  SFEM_CUDA(cudaMalloc(&tmp, tb + 16));
+  SFEM_CUDA(dev_malloc(&tmp, tb + 16, st));
   SFEM_CUDA(cub::DeviceSelect::Flagged(tmp, tb, it, flags, pat->abc_rows, d_count, (int)n, st));
   int64_t h = 0;
   SFEM_CUDA(cudaMemcpyAsync(&h, d_count, 8, cudaMemcpyDeviceToHost, st));
   SFEM_CUDA(cudaStreamSynchronize(st));
-  cudaFree(tmp); cudaFree(flags); cudaFree(d_count);
+  dev_free(tmp, st); dev_free(flags, st); dev_free(d_count, st);
   pat->n_abc_rows = h;
   return 0;
 }
@@ -354,7 +354,7 @@ int launch_generic(const sfem_pattern_s* pat, int form, const double* coef_a, co
   const int32_t* cell_facets = DIM == 3 ? sp->cell_faces : sp->cell_edges;
   double* geo = nullptr;
   if (form != SFEM_FORM_ABC) {
-    SFEM_CUDA(cudaMallocAsync((void**)&geo, m->C * 12 * sizeof(double), st));
+    SFEM_CUDA(dev_malloc(&geo, m->C * 12 * sizeof(double), st));
     // coef_a = eps_r (mass), coef_b = mu_r (stiffness)
     k_cell_geometry<DIM><<<(unsigned)((m->C + 255) / 256), 256, 0, st>>>(m->coords, m->cells, coef_a, coef_b, m->C, geo);
   }
@@ -380,7 +380,7 @@ int launch_generic(const sfem_pattern_s* pat, int form, const double* coef_a, co
                                                                    sp->cell_extmask, facet_mask, pec, out_a, out_b);
   }
   SFEM_CUDA(cudaGetLastError());
-  if (geo) SFEM_CUDA(cudaFreeAsync(geo, st));
+  if (geo) dev_free(geo, st);
   return 0;
 }
 

@@ -159,9 +159,9 @@ struct Tmp {
   void* p = nullptr;
   cudaStream_t st;
   explicit Tmp(cudaStream_t s) : st(s) {}
-  cudaError_t alloc(size_t bytes) { return cudaMallocAsync(&p, bytes ? bytes : 16, st); }
+  cudaError_t alloc(size_t bytes) { return dev_malloc(&p, bytes ? bytes : 16, st); }
   ~Tmp() {
-    if (p) cudaFreeAsync(p, st);
+    if (p) dev_free(p, st);
   }
   template <class T>
   T* as() { return (T*)p; }
@@ -222,7 +222,7 @@ int number_class(const sfem_mesh_s* m, int32_t* cell_x, int64_t* n_out, int64_t*
   k_assign<<<grid_for(n), 256, 0, st>>>(seq, headpos.as<int32_t>(), firstidx.as<int32_t>(), cell_x, ent_of_p,
                                         count.as<unsigned int>(), n);
   int64_t* ptr = nullptr;
-  SFEM_CUDA(cudaMalloc(&ptr, (ne + 1) * 8));
+  SFEM_CUDA(dev_malloc(&ptr, (ne + 1) * 8, st));
   Tmp cnt64(st);
   SFEM_CUDA(cnt64.alloc((ne + 1) * 8));
   k_count_to_i64<<<grid_for(ne + 1), 256, 0, st>>>(count.as<unsigned int>(), cnt64.as<int64_t>(), ne + 1);
@@ -245,13 +245,13 @@ int build_numbering(sfem_space_s* sp, cudaStream_t st) {
   const int64_t C = m->C;
   {
     int* bad = nullptr;
-    SFEM_CUDA(cudaMalloc(&bad, 4));
+    SFEM_CUDA(dev_malloc(&bad, 4, st));
     SFEM_CUDA(cudaMemsetAsync(bad, 0, 4, st));
     k_check_sorted<<<grid_for(C), 256, 0, st>>>(m->cells, m->nv, C, m->V, bad);
     int h = 0;
     SFEM_CUDA(cudaMemcpyAsync(&h, bad, 4, cudaMemcpyDeviceToHost, st));
     SFEM_CUDA(cudaStreamSynchronize(st));
-    cudaFree(bad);
+    dev_free(bad, st);
     SFEM_CHECK(h == 0, "cells must list in-range vertex ids in strictly ascending order (UFC ordering)");
   }
   const bool d3 = m->gdim == 3;
@@ -263,9 +263,9 @@ int build_numbering(sfem_space_s* sp, cudaStream_t st) {
   // unified incidence arrays of the dof entities
   const int64_t inc_edges = C * sp->ne_loc;
   const int64_t inc_total = C * sp->n_ent_cell;
-  SFEM_CUDA(cudaMalloc(&sp->inc_cell, std::max<int64_t>(inc_total, 1) * 4));
-  SFEM_CUDA(cudaMalloc(&sp->inc_loc, std::max<int64_t>(inc_total, 1)));
-  SFEM_CUDA(cudaMalloc(&sp->cell_edges, C * sp->ne_loc * 4));
+  SFEM_CUDA(dev_malloc(&sp->inc_cell, std::max<int64_t>(inc_total, 1) * 4, st));
+  SFEM_CUDA(dev_malloc(&sp->inc_loc, std::max<int64_t>(inc_total, 1), st));
+  SFEM_CUDA(dev_malloc(&sp->cell_edges, C * sp->ne_loc * 4, st));
   int64_t* ptr_e = nullptr;
   if (d3)
     SFEM_TRY((number_class<6, 2>(m, sp->cell_edges, &sp->E, &ptr_e, 0, sp->inc_cell, sp->inc_loc, 0, st)));
@@ -276,7 +276,7 @@ int build_numbering(sfem_space_s* sp, cudaStream_t st) {
   int32_t* f_inc_cell = nullptr;
   uint8_t* f_inc_loc = nullptr;
   if (d3) {
-    SFEM_CUDA(cudaMalloc(&sp->cell_faces, C * 4 * 4));
+    SFEM_CUDA(dev_malloc(&sp->cell_faces, C * 4 * 4, st));
     if (q == 2) {
       f_inc_cell = sp->inc_cell + inc_edges;
       f_inc_loc = sp->inc_loc + inc_edges;
@@ -285,17 +285,17 @@ int build_numbering(sfem_space_s* sp, cudaStream_t st) {
       f_inc_cell = sp->inc_cell;
       f_inc_loc = sp->inc_loc;
     } else {
-      SFEM_CUDA(cudaMalloc(&f_inc_cell, C * 4 * 4));
-      SFEM_CUDA(cudaMalloc(&f_inc_loc, C * 4));
+      SFEM_CUDA(dev_malloc(&f_inc_cell, C * 4 * 4, st));
+      SFEM_CUDA(dev_malloc(&f_inc_loc, C * 4, st));
       SFEM_TRY((number_class<4, 3>(m, sp->cell_faces, &sp->F, &ptr_f, 0, f_inc_cell, f_inc_loc, 6, st)));
     }
   }
   // facets
   sp->n_facets = d3 ? sp->F : sp->E;
-  SFEM_CUDA(cudaMalloc(&sp->facet_ncells, std::max<int64_t>(sp->n_facets, 1)));
-  SFEM_CUDA(cudaMalloc(&sp->facet_first_cell, std::max<int64_t>(sp->n_facets, 1) * 4));
-  SFEM_CUDA(cudaMalloc(&sp->facet_first_loc, std::max<int64_t>(sp->n_facets, 1)));
-  SFEM_CUDA(cudaMalloc(&sp->cell_extmask, C));
+  SFEM_CUDA(dev_malloc(&sp->facet_ncells, std::max<int64_t>(sp->n_facets, 1), st));
+  SFEM_CUDA(dev_malloc(&sp->facet_first_cell, std::max<int64_t>(sp->n_facets, 1) * 4, st));
+  SFEM_CUDA(dev_malloc(&sp->facet_first_loc, std::max<int64_t>(sp->n_facets, 1), st));
+  SFEM_CUDA(dev_malloc(&sp->cell_extmask, C, st));
   if (d3) {
     k_facet_info<<<grid_for(sp->F), 256, 0, st>>>(ptr_f, f_inc_cell, f_inc_loc, 6, sp->facet_ncells,
                                                   sp->facet_first_cell, sp->facet_first_loc, sp->F);
@@ -309,7 +309,7 @@ int build_numbering(sfem_space_s* sp, cudaStream_t st) {
   sp->n_ent = sp->E + (q == 2 ? (d3 ? sp->F : C) : 0);
   sp->ndof = q * sp->n_ent;
   sp->n_inc = inc_total;
-  SFEM_CUDA(cudaMalloc(&sp->inc_ptr, (sp->n_ent + 1) * 8));
+  SFEM_CUDA(dev_malloc(&sp->inc_ptr, (sp->n_ent + 1) * 8, st));
   SFEM_CUDA(cudaMemcpyAsync(sp->inc_ptr, ptr_e, (sp->E + 1) * 8, cudaMemcpyDeviceToDevice, st));
   if (q == 2 && d3) {
     SFEM_CUDA(cudaMemcpyAsync(sp->inc_ptr + sp->E, ptr_f, (sp->F + 1) * 8, cudaMemcpyDeviceToDevice, st));
@@ -318,16 +318,16 @@ int build_numbering(sfem_space_s* sp, cudaStream_t st) {
                                                           inc_edges, 3, C);
   }
   if (d3) {
-    SFEM_CUDA(cudaMalloc(&sp->coords4, m->V * 32));
+    SFEM_CUDA(dev_malloc(&sp->coords4, m->V * 32, st));
     k_pad_coords<<<grid_for(m->V * 4), 256, 0, st>>>(m->coords, sp->coords4, m->V);
   }
   SFEM_CUDA(cudaGetLastError());
   SFEM_CUDA(cudaStreamSynchronize(st));
-  cudaFree(ptr_e);
-  if (ptr_f) cudaFree(ptr_f);
+  dev_free(ptr_e, st);
+  if (ptr_f) dev_free(ptr_f, st);
   if (d3 && q == 1) {
-    cudaFree(f_inc_cell);
-    cudaFree(f_inc_loc);
+    dev_free(f_inc_cell, st);
+    dev_free(f_inc_loc, st);
   }
   return 0;
 }

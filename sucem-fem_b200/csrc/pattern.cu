@@ -216,19 +216,20 @@ __global__ void k_len_to_i64(const int32_t* __restrict__ len, int64_t* __restric
 
 // dof-level CSR from the entity-level one: dof row q*g+k; columns q*h+k'
 __global__ void k_export(const int64_t* __restrict__ ent_rowptr, const int32_t* __restrict__ ent_cols, int q,
-                         int64_t n_rows_ent, int64_t* __restrict__ rowptr, int32_t* __restrict__ cols) {
+                         int64_t n_rows_ent, int64_t nnz_base, int64_t* __restrict__ rowptr,
+                         int32_t* __restrict__ cols) {
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t r = blockIdx.x * (int64_t)(blockDim.x >> 5) + w;
   if (r > n_rows_ent) return;
   if (r == n_rows_ent) {
-    if (lane == 0) rowptr[q * r] = (int64_t)q * q * ent_rowptr[r];
+    if (lane == 0) rowptr[q * r] = nnz_base + (int64_t)q * q * ent_rowptr[r];
     return;
   }
   const int64_t a = ent_rowptr[r];
   const int len = (int)(ent_rowptr[r + 1] - a);
   for (int k = 0; k < q; ++k) {
     const int64_t rs = (int64_t)q * q * a + (int64_t)k * q * len;
-    if (lane == 0) rowptr[q * r + k] = rs;
+    if (lane == 0) rowptr[q * r + k] = nnz_base + rs;
     if (cols)
       for (int idx = lane; idx < q * len; idx += 32) {
         int s = idx / q, kp = idx - s * q;
@@ -239,73 +240,87 @@ __global__ void k_export(const int64_t* __restrict__ ent_rowptr, const int32_t* 
 
 inline unsigned grid_for(int64_t n, int bs = 256) { return (unsigned)((n + bs - 1) / bs); }
 
+__global__ void k_rebase(const int64_t* __restrict__ src, int64_t* __restrict__ dst, int64_t n) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i <= n) dst[i] = src[i] - src[0];
+}
+
 }  // namespace
 
-int build_pattern(sfem_pattern_s* pat, cudaStream_t st) {
-  const sfem_space_s* sp = pat->space;
-  const int64_t n = pat->n_rows_ent;
+// Count pass over the row entities [ent_lo, ent_hi): allocates *rowptr_out [n+1] (exclusive scan of the row lengths,
+// offsets relative to ent_lo) and returns the longest edge row / other row.  Synchronises `st`.
+int count_pattern_rows(const sfem_space_s* sp, int64_t ent_lo, int64_t ent_hi, cudaStream_t st, int64_t** rowptr_out,
+                       int64_t* nnz_ent, int* max_len_edges, int* max_len_other) {
+  const int64_t n = ent_hi - ent_lo;
   SpaceView sv = make_view(sp);
   const bool canon = pos_is_canonical(sp);
-  int64_t bounds[2];
-  SFEM_CUDA(cudaMemcpyAsync(&bounds[0], sp->inc_ptr + pat->ent_lo, 8, cudaMemcpyDeviceToHost, st));
-  SFEM_CUDA(cudaMemcpyAsync(&bounds[1], sp->inc_ptr + pat->ent_hi, 8, cudaMemcpyDeviceToHost, st));
-  SFEM_CUDA(cudaStreamSynchronize(st));
-  pat->inc_base = bounds[0];
-  pat->n_inc_block = bounds[1] - bounds[0];
-
   int32_t* row_len = nullptr;
   int64_t* len64 = nullptr;
   int* overflow = nullptr;
-  SFEM_CUDA(cudaMalloc(&row_len, std::max<int64_t>(n, 1) * 4));
-  SFEM_CUDA(cudaMalloc(&len64, (n + 1) * 8));
-  SFEM_CUDA(cudaMalloc(&overflow, 4));
+  int64_t* rowptr = nullptr;
+  SFEM_CUDA(dev_malloc(&row_len, std::max<int64_t>(n, 1) * 4, st));
+  SFEM_CUDA(dev_malloc(&len64, (n + 1) * 8, st));
+  SFEM_CUDA(dev_malloc(&overflow, 4, st));
   SFEM_CUDA(cudaMemsetAsync(overflow, 0, 4, st));
-  SFEM_CUDA(cudaMalloc(&pat->ent_rowptr, (n + 1) * 8));
+  SFEM_CUDA(dev_malloc(&rowptr, (n + 1) * 8, st));
   const unsigned grid = (unsigned)((n + kWarpsPerBlock - 1) / kWarpsPerBlock);
   if (n > 0)
-    k_pattern<false><<<grid, kWarpsPerBlock * 32, 0, st>>>(sv, sp->mesh->cells, sp->inc_ptr, sp->inc_cell, sp->inc_loc, canon, pat->ent_lo, n,
-                                                           pat->inc_base, row_len, nullptr, nullptr, nullptr,
-                                                           nullptr, overflow);
+    k_pattern<false><<<grid, kWarpsPerBlock * 32, 0, st>>>(sv, sp->mesh->cells, sp->inc_ptr, sp->inc_cell, sp->inc_loc, canon, ent_lo, n,
+                                                           0, row_len, nullptr, nullptr, nullptr, nullptr, overflow);
   k_len_to_i64<<<grid_for(n + 1), 256, 0, st>>>(row_len, len64, n);
   size_t tb = 0;
-  SFEM_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tb, len64, pat->ent_rowptr, (int)(n + 1), st));
+  SFEM_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tb, len64, rowptr, (int)(n + 1), st));
   size_t tb2 = 0;
   SFEM_CUDA(cub::DeviceReduce::Max(nullptr, tb2, row_len, (int32_t*)nullptr, (int)std::max<int64_t>(n, 1), st));
   void* tmp = nullptr;
-  SFEM_CUDA(cudaMalloc(&tmp, std::max(tb, tb2) + 16));
-  SFEM_CUDA(cub::DeviceScan::ExclusiveSum(tmp, tb, len64, pat->ent_rowptr, (int)(n + 1), st));
+  SFEM_CUDA(dev_malloc(&tmp, std::max(tb, tb2) + 16, st));
+  SFEM_CUDA(cub::DeviceScan::ExclusiveSum(tmp, tb, len64, rowptr, (int)(n + 1), st));
   int32_t* d_max = (int32_t*)len64;  // len64 is dead after the scan
-  const int64_t n_edge_rows = std::max<int64_t>(0, std::min(pat->ent_hi, sp->E) - pat->ent_lo);
+  const int64_t n_edge_rows = std::max<int64_t>(0, std::min(ent_hi, sp->E) - ent_lo);
   if (n_edge_rows > 0) SFEM_CUDA(cub::DeviceReduce::Max(tmp, tb2, row_len, d_max, (int)n_edge_rows, st));
   if (n > n_edge_rows)
     SFEM_CUDA(cub::DeviceReduce::Max(tmp, tb2, row_len + n_edge_rows, d_max + 1, (int)(n - n_edge_rows), st));
   int h_over = 0, h_max2[2] = {0, 0};
-  SFEM_CUDA(cudaMemcpyAsync(&pat->nnz_ent, pat->ent_rowptr + n, 8, cudaMemcpyDeviceToHost, st));
+  SFEM_CUDA(cudaMemcpyAsync(nnz_ent, rowptr + n, 8, cudaMemcpyDeviceToHost, st));
   SFEM_CUDA(cudaMemcpyAsync(&h_over, overflow, 4, cudaMemcpyDeviceToHost, st));
   if (n_edge_rows > 0) SFEM_CUDA(cudaMemcpyAsync(&h_max2[0], d_max, 4, cudaMemcpyDeviceToHost, st));
   if (n > n_edge_rows) SFEM_CUDA(cudaMemcpyAsync(&h_max2[1], d_max + 1, 4, cudaMemcpyDeviceToHost, st));
   SFEM_CUDA(cudaStreamSynchronize(st));
-  cudaFree(tmp);
-  cudaFree(len64);
-  cudaFree(row_len);
+  dev_free(tmp, st);
+  dev_free(len64, st);
+  dev_free(row_len, st);
+  dev_free(overflow, st);
   if (h_over) {
-    cudaFree(overflow);
+    dev_free(rowptr, st);
     set_error("an entity has more incident cells than the pattern builder supports (valence*entities > 1024)");
     return 3;
   }
-  pat->max_row_len_edges = h_max2[0];
-  pat->max_row_len_other = h_max2[1];
-  pat->max_row_len = std::max(h_max2[0], h_max2[1]);
-  SFEM_CUDA(cudaMalloc(&pat->ent_cols, std::max<int64_t>(pat->nnz_ent, 1) * 4));
-  SFEM_CUDA(cudaMalloc(&pat->pos, std::max<int64_t>(pat->n_inc_block * sp->n_ent_cell, 1) * 2));
-  if (canon && pat->max_row_len <= 255) SFEM_CUDA(cudaMalloc(&pat->rec, std::max<int64_t>(pat->n_inc_block, 1) * 32));
+  *rowptr_out = rowptr;
+  *max_len_edges = h_max2[0];
+  *max_len_other = h_max2[1];
+  return 0;
+}
+
+// Fill pass: expects ent_rowptr, nnz_ent, max_row_len*, inc_base and n_inc_block of `pat` to be set.
+int fill_pattern(sfem_pattern_s* pat, cudaStream_t st) {
+  const sfem_space_s* sp = pat->space;
+  const int64_t n = pat->n_rows_ent;
+  SpaceView sv = make_view(sp);
+  const bool canon = pos_is_canonical(sp);
+  const unsigned grid = (unsigned)((n + kWarpsPerBlock - 1) / kWarpsPerBlock);
+  const int64_t n_edge_rows = std::max<int64_t>(0, std::min(pat->ent_hi, sp->E) - pat->ent_lo);
+  int* overflow = nullptr;
+  SFEM_CUDA(dev_malloc(&overflow, 4, st));
+  SFEM_CUDA(cudaMemsetAsync(overflow, 0, 4, st));
+  SFEM_CUDA(dev_malloc(&pat->ent_cols, std::max<int64_t>(pat->nnz_ent, 1) * 4, st));
+  SFEM_CUDA(dev_malloc(&pat->pos, std::max<int64_t>(pat->n_inc_block * sp->n_ent_cell, 1) * 2, st));
+  if (canon && pat->max_row_len <= 255) SFEM_CUDA(dev_malloc(&pat->rec, std::max<int64_t>(pat->n_inc_block, 1) * 32, st));
   if (n > 0)
     k_pattern<true><<<grid, kWarpsPerBlock * 32, 0, st>>>(sv, sp->mesh->cells, sp->inc_ptr, sp->inc_cell, sp->inc_loc, canon, pat->ent_lo, n,
                                                           pat->inc_base, nullptr, pat->ent_rowptr, pat->ent_cols,
                                                           pat->pos, reinterpret_cast<uint8_t*>(pat->rec), overflow);
   pat->ring_ok = false;
   if (pat->rec && n_edge_rows > 0) {
-    SFEM_CUDA(cudaMemsetAsync(overflow, 0, 4, st));
     k_edge_ring<<<grid_for(n_edge_rows, 128), 128, 0, st>>>(sv, sp->mesh->cells, sp->inc_ptr, sp->inc_cell, sp->inc_loc,
                                                             pat->ent_lo, n_edge_rows, pat->inc_base, pat->ent_rowptr,
                                                             pat->ent_cols, reinterpret_cast<uint8_t*>(pat->rec), overflow);
@@ -317,15 +332,45 @@ int build_pattern(sfem_pattern_s* pat, cudaStream_t st) {
     pat->ring_ok = true;
   }
   SFEM_CUDA(cudaGetLastError());
-  SFEM_CUDA(cudaStreamSynchronize(st));
-  cudaFree(overflow);
+  dev_free(overflow, st);
   return 0;
 }
 
-int export_pattern(const sfem_pattern_s* pat, int64_t* d_rowptr, int32_t* d_cols, cudaStream_t st) {
+int build_pattern(sfem_pattern_s* pat, cudaStream_t st) {
+  const sfem_space_s* sp = pat->space;
+  int64_t bounds[2];
+  SFEM_CUDA(cudaMemcpyAsync(&bounds[0], sp->inc_ptr + pat->ent_lo, 8, cudaMemcpyDeviceToHost, st));
+  SFEM_CUDA(cudaMemcpyAsync(&bounds[1], sp->inc_ptr + pat->ent_hi, 8, cudaMemcpyDeviceToHost, st));
+  SFEM_TRY(count_pattern_rows(sp, pat->ent_lo, pat->ent_hi, st, &pat->ent_rowptr, &pat->nnz_ent, &pat->max_row_len_edges,
+                              &pat->max_row_len_other));  // synchronises st: bounds are valid
+  pat->inc_base = bounds[0];
+  pat->n_inc_block = bounds[1] - bounds[0];
+  pat->max_row_len = std::max(pat->max_row_len_edges, pat->max_row_len_other);
+  SFEM_TRY(fill_pattern(pat, st));
+  SFEM_CUDA(cudaStreamSynchronize(st));
+  return 0;
+}
+
+// A block [ent_lo, ent_hi) of a pattern whose count pass was done for a superset of rows: rowptr_all is the (device)
+// row pointer of the row entities starting at entity all_lo.  Host-side sizes come from the caller.
+int build_pattern_block(sfem_pattern_s* pat, const int64_t* rowptr_all, int64_t all_lo, int64_t nnz_ent,
+                        int64_t inc_base, int64_t n_inc_block, int max_len_edges, int max_len_other, cudaStream_t st) {
+  const int64_t n = pat->n_rows_ent;
+  SFEM_CUDA(dev_malloc(&pat->ent_rowptr, (n + 1) * 8, st));
+  k_rebase<<<grid_for(n + 1), 256, 0, st>>>(rowptr_all + (pat->ent_lo - all_lo), pat->ent_rowptr, n);
+  pat->nnz_ent = nnz_ent;
+  pat->inc_base = inc_base;
+  pat->n_inc_block = n_inc_block;
+  pat->max_row_len_edges = max_len_edges;
+  pat->max_row_len_other = max_len_other;
+  pat->max_row_len = std::max(max_len_edges, max_len_other);
+  return fill_pattern(pat, st);
+}
+
+int export_pattern(const sfem_pattern_s* pat, int64_t* d_rowptr, int32_t* d_cols, cudaStream_t st, int64_t nnz_base) {
   const int64_t n = pat->n_rows_ent;
   const unsigned grid = (unsigned)((n + 1 + 7) / 8);
-  k_export<<<grid, 256, 0, st>>>(pat->ent_rowptr, pat->ent_cols, pat->space->order, n, d_rowptr, d_cols);
+  k_export<<<grid, 256, 0, st>>>(pat->ent_rowptr, pat->ent_cols, pat->space->order, n, nnz_base, d_rowptr, d_cols);
   SFEM_CUDA(cudaGetLastError());
   return 0;
 }

@@ -35,6 +35,18 @@ void set_error(const std::string& msg);
     if (_rc != 0) return _rc;    \
   } while (0)
 
+// Device memory: stream-ordered allocations from the device's default memory pool.  The library raises the pool's
+// release threshold once per device, so freed blocks stay cached instead of being returned to the driver at every
+// stream synchronisation (set-up after set-up then reuses them); sfem_release_cached_memory() trims the pool.
+cudaError_t dev_malloc_bytes(void** p, size_t bytes, cudaStream_t st);
+template <class T>
+inline cudaError_t dev_malloc(T** p, size_t bytes, cudaStream_t st) {
+  return dev_malloc_bytes(reinterpret_cast<void**>(p), bytes, st);
+}
+inline void dev_free(void* p, cudaStream_t st) {
+  if (p) cudaFreeAsync(p, st);
+}
+
 // Local topology of the UFC reference cells.
 // tet edges e0=(2,3) e1=(1,3) e2=(1,2) e3=(0,3) e4=(0,2) e5=(0,1); faces f_i opposite v_i
 // triangle edges e_i opposite v_i
@@ -70,6 +82,7 @@ struct sfem_mesh_s {
 struct sfem_space_s {
   sfem_mesh_s* mesh = nullptr;
   int device = 0;
+  cudaStream_t stream = nullptr;  // stream of the creating call: the handle's buffers are freed in its order
   int order = 0;         // = dofs per entity q
   int ne_loc = 0;        // local edges per cell (6 | 3)
   int nf_loc = 0;        // local faces per cell (4 | 0)
@@ -93,11 +106,17 @@ struct sfem_space_s {
   uint8_t* cell_extmask = nullptr;    // [C] bit lf set <=> local facet lf is exterior
   double* coords4 = nullptr;          // [V][4] 32-byte padded copy of the coordinates (3-D; vector gathers)
   double* ones = nullptr;             // [C] 1.0, the default eps_r / mu_r (allocated on first use)
+  // count pass over ALL rows (lazily, sfem_space_count_nnz): entity-level row pointer, longest rows
+  int64_t* rowptr_all = nullptr;      // [n_ent+1]
+  int64_t nnz_ent_all = 0;
+  int max_len_edges_all = 0, max_len_other_all = 0;
+  cudaStream_t drain = nullptr;       // device->host drain stream of sfem_space_assemble_to_host (lazily created)
 };
 
 struct sfem_pattern_s {
   sfem_space_s* space = nullptr;
   int device = 0;
+  cudaStream_t stream = nullptr;  // stream of the creating call: the handle's buffers are freed in its order
   int64_t ent_lo = 0, ent_hi = 0;
   int64_t n_rows_ent = 0;
   int64_t nnz_ent = 0;            // entity-level non-zeros of the block
@@ -145,7 +164,12 @@ inline bool pos_is_canonical(const sfem_space_s* s) { return s->mesh->gdim == 3;
 
 int build_numbering(sfem_space_s* sp, cudaStream_t st);
 int build_pattern(sfem_pattern_s* pat, cudaStream_t st);
-int export_pattern(const sfem_pattern_s* pat, int64_t* d_rowptr, int32_t* d_cols, cudaStream_t st);
+int count_pattern_rows(const sfem_space_s* sp, int64_t ent_lo, int64_t ent_hi, cudaStream_t st, int64_t** rowptr_out,
+                       int64_t* nnz_ent, int* max_len_edges, int* max_len_other);
+int build_pattern_block(sfem_pattern_s* pat, const int64_t* rowptr_all, int64_t all_lo, int64_t nnz_ent,
+                        int64_t inc_base, int64_t n_inc_block, int max_len_edges, int max_len_other, cudaStream_t st);
+// rowptr entries are offset by nnz_base (0 for a stand-alone block)
+int export_pattern(const sfem_pattern_s* pat, int64_t* d_rowptr, int32_t* d_cols, cudaStream_t st, int64_t nnz_base = 0);
 int assemble_generic(const sfem_pattern_s* pat, int form, const double* coef_a, const double* coef_b,
                      const uint8_t* facet_mask, const uint8_t* pec, double* out_a, double* out_b,
                      cudaStream_t st);

@@ -31,7 +31,25 @@ class SystemMatrices(object):
         forms = dict(self.matrix_forms)
         mass = [(k, f) for k, f in forms.items() if isinstance(f, Forms.BilinearForm) and f.kind == 'mass']
         stiff = [(k, f) for k, f in forms.items() if isinstance(f, Forms.BilinearForm) and f.kind == 'stiffness']
-        if (len(mass) == 1 and len(stiff) == 1 and mass[0][1].function_space is stiff[0][1].function_space
+        abc = [(k, f) for k, f in forms.items() if isinstance(f, Forms.BilinearForm) and f.kind == 'abc']
+        same_space = (len(mass) == 1 and len(stiff) == 1 and mass[0][1].function_space is stiff[0][1].function_space
+                      and all(f.function_space is mass[0][1].function_space for _, f in abc))
+        if same_space and issubclass(self.MatrixClass, dolfin.HostCSRMatrix):
+            # host matrix class: stream row blocks to page-locked host arrays while they are assembled
+            (mname, mform), (sname, sform) = mass[0], stiff[0]
+            space = mform.function_space.device_space
+            flags = self.boundary_conditions.get_essential_row_flags(mform.function_space)
+            eps = None if mform.coefficient is None else mform.coefficient.device_values()
+            mu = None if sform.coefficient is None else sform.coefficient.device_values()
+            want = ('cols', 'S', 'T') + (('S0',) if len(abc) == 1 else ())
+            host = space.assemble_to_host(eps, mu, flags, want=want)
+            named = [(sname, 'S'), (mname, 'T')] + ([(abc[0][0], 'S0')] if len(abc) == 1 else [])
+            for name, key in named:
+                mat = self.MatrixClass()
+                mat.init_host(space.ndof, host['rowptr'], host['cols'], host[key])
+                system_matrices[name] = mat
+                del forms[name]
+        elif (len(mass) == 1 and len(stiff) == 1 and mass[0][1].function_space is stiff[0][1].function_space
                 and issubclass(self.MatrixClass, dolfin.DeviceCSRMatrix)):
             (mname, mform), (sname, sform) = mass[0], stiff[0]
             space = mform.function_space.device_space

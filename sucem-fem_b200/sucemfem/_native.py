@@ -26,6 +26,7 @@ def _load():
     sig = {
         'sfem_last_error': (C.c_char_p, []),
         'sfem_version': (C.c_char_p, []),
+        'sfem_release_cached_memory': (i32, []),
         'sfem_mesh_create': (i32, [i32, i64, vp, i64, vp, vp, P(vp)]),
         'sfem_mesh_destroy': (i32, [vp]),
         'sfem_fill_unit_mesh': (i32, [i32, i32, i32, P(dbl), P(dbl), vp, vp, vp]),
@@ -43,10 +44,18 @@ def _load():
         'sfem_pattern_info': (i32, [vp, P(i64), P(i64), P(i64)]),
         'sfem_pattern_export': (i32, [vp, vp, vp, vp]),
         'sfem_partition_rows': (i32, [vp, i32, P(i64), vp]),
+        'sfem_partition_rows_by_class': (i32, [vp, i32, P(i64), P(i64), vp]),
         'sfem_assemble': (i32, [vp, i32, vp, vp, vp, vp, i32, vp]),
         'sfem_assemble_ST': (i32, [vp, vp, vp, vp, vp, vp, i32, vp]),
         'sfem_apply_ident': (i32, [vp, vp, vp, vp]),
         'sfem_launches_per_assemble_ST': (i32, [vp, i32]),
+        'sfem_host_job_create': (i32, [i32, i64, vp, i64, vp, i32, vp, vp, i32, vp, C.c_uint32, vp, P(i64), P(i64), P(vp)]),
+        'sfem_host_job_run': (i32, [vp, vp, vp, vp, vp, vp, i32]),
+        'sfem_host_job_destroy': (i32, [vp]),
+        'sfem_space_count_nnz': (i32, [vp, vp, P(i64)]),
+        'sfem_space_assemble_to_host': (i32, [vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, vp]),
+        'sfem_host_alloc': (i32, [C.c_size_t, P(vp)]),
+        'sfem_host_free': (i32, [vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)      # AttributeError here = the library does not export what the header declares

@@ -27,6 +27,11 @@ def require_cuda():
         raise RuntimeError("sucemfem (B200 build) needs a CUDA device: there is no CPU fallback")
 
 
+def pinned_empty(n, dtype):
+    """Page-locked host tensor (cudaHostAlloc through torch)."""
+    return torch.empty(int(n), dtype=dtype, pin_memory=True)
+
+
 class DeviceMesh(object):
     def __init__(self, coords, cells, device=None):
         """coords [V, gdim] float64, cells [C, gdim+1] integer (host numpy arrays or device tensors)."""
@@ -127,6 +132,40 @@ class DeviceSpace(object):
             N.check(N.lib.sfem_partition_rows(self.handle, nparts, b, _stream_ptr()))
         return [int(x) for x in b]
 
+    def partition_by_class(self, nparts):
+        """(edge_bounds, other_bounds): rank p owns edges [eb[p], eb[p+1]) and faces/interiors [ob[p], ob[p+1])."""
+        eb, ob = (C.c_int64 * (nparts + 1))(), (C.c_int64 * (nparts + 1))()
+        with torch.cuda.device(self.mesh.device):
+            N.check(N.lib.sfem_partition_rows_by_class(self.handle, nparts, eb, ob, _stream_ptr()))
+        return [int(x) for x in eb], [int(x) for x in ob]
+
+    def count_nnz(self):
+        """nnz of the full dof-level pattern (one count pass over all rows, cached in the space handle)."""
+        nnz = C.c_int64()
+        with torch.cuda.device(self.mesh.device):
+            N.check(N.lib.sfem_space_count_nnz(self.handle, _stream_ptr(), C.byref(nnz)))
+        return nnz.value
+
+    def assemble_to_host(self, eps_r=None, mu_r=None, pec_flags=None, want=('S', 'T'), out=None, n_blocks=0):
+        """Stream the CSR of the requested matrices to page-locked HOST arrays, row block by row block (pattern fill,
+        values and CSR expansion of block k overlap the device->host copy of block k-1; two blocks live in HBM).
+        want: subset of ('cols', 'S', 'T', 'S0') ('rowptr' always).  out: dict of pinned CPU tensors to reuse
+        (page-locking tens of GB is slow, so callers that repeat the call keep them).  Returns the dict."""
+        nnz = self.count_nnz()
+        out = {} if out is None else out
+        spec = {'rowptr': (self.ndof + 1, torch.int64), 'cols': (nnz, torch.int32), 'S': (nnz, torch.float64),
+                'T': (nnz, torch.float64), 'S0': (nnz, torch.float64)}
+        for k in ('rowptr',) + tuple(want):
+            n, dt = spec[k]
+            if k not in out or out[k].numel() != n or out[k].dtype != dt:
+                out[k] = pinned_empty(n, dt)
+        hp = lambda k: C.c_void_p(out[k].data_ptr()) if k in want or k == 'rowptr' else C.c_void_p(0)
+        with torch.cuda.device(self.mesh.device):
+            N.check(N.lib.sfem_space_assemble_to_host(self.handle, _ptr(eps_r), _ptr(mu_r), _ptr(pec_flags), hp('rowptr'),
+                                                      hp('cols'), hp('S'), hp('T'), hp('S0'), int(n_blocks),
+                                                      _stream_ptr()))
+        return out
+
     def pattern(self, ent_lo=0, ent_hi=-1):
         key = (ent_lo, ent_hi)
         if key not in self._patterns:
@@ -209,3 +248,65 @@ def expand_material(regions, region_values, n_cells=None):
         raise ValueError('Material number %d not found' % bad.value)
     N.check(rc)
     return out
+
+
+class HostAssemblyJob(object):
+    """The whole path with HOST arrays in and out (sfem_host_job_*): numpy / CPU-tensor mesh, per-cell eps_r and mu_r
+    and facet markers in; scipy-ready (rowptr, cols, S, T[, S0]) in page-locked host arrays out.  What a reference
+    user gets from FunctionSpace + calc_system_matrices() + A.data()
+    (/root/reference/sucemfem/SystemMatrices.py:46-58, /root/reference/sucemfem/Utilities/Converters.py:37).
+
+    pec: None (no essential condition), 'exterior' (PEC walls: all exterior facets) or (markers uint32 [n_facets],
+    region)."""
+
+    def __init__(self, coords, cells, order, eps_r=None, mu_r=None, pec=None, pec_region=999):
+        require_cuda()
+        as_t = lambda a, dt: None if a is None else (a if isinstance(a, torch.Tensor) else torch.from_numpy(
+            np.ascontiguousarray(a))).to(dt).contiguous()
+        self._keep = [as_t(coords, torch.float64), as_t(cells, torch.int32), as_t(eps_r, torch.float64),
+                      as_t(mu_r, torch.float64)]
+        co, ce, ep, mu = self._keep
+        mode, markers = 0, None
+        if isinstance(pec, str):
+            assert pec == 'exterior'
+            mode = 1
+        elif pec is not None:
+            markers, pec_region = pec
+            markers = torch.from_numpy(np.ascontiguousarray(np.asarray(markers, dtype=np.uint32)).view(np.int32))
+            self._keep.append(markers)
+            mode = 2
+        hp = lambda t: C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+        h, nd, nnz = C.c_void_p(), C.c_int64(), C.c_int64()
+        self.handle = None
+        N.check(N.lib.sfem_host_job_create(int(co.shape[1]), co.shape[0], hp(co), ce.shape[0], hp(ce), int(order),
+                                           hp(ep), hp(mu), mode, hp(markers), int(pec_region), _stream_ptr(),
+                                           C.byref(nd), C.byref(nnz), C.byref(h)))
+        self.handle, self.ndof, self.nnz = h, nd.value, nnz.value
+
+    def run(self, want=('cols', 'S', 'T'), out=None, n_blocks=0):
+        out = {} if out is None else out
+        spec = {'rowptr': (self.ndof + 1, torch.int64), 'cols': (self.nnz, torch.int32), 'S': (self.nnz, torch.float64),
+                'T': (self.nnz, torch.float64), 'S0': (self.nnz, torch.float64)}
+        for k in ('rowptr',) + tuple(want):
+            n, dt = spec[k]
+            if k not in out or out[k].numel() != n or out[k].dtype != dt:
+                out[k] = pinned_empty(n, dt)
+        hp = lambda k: C.c_void_p(out[k].data_ptr()) if k in want or k == 'rowptr' else C.c_void_p(0)
+        N.check(N.lib.sfem_host_job_run(self.handle, hp('rowptr'), hp('cols'), hp('S'), hp('T'), hp('S0'), int(n_blocks)))
+        return out
+
+    def close(self):
+        if self.handle:
+            N.lib.sfem_host_job_destroy(self.handle)
+            self.handle = None
+
+    __del__ = close
+
+
+def assemble_host(coords, cells, order, eps_r=None, mu_r=None, pec=None, want=('cols', 'S', 'T'), out=None, n_blocks=0):
+    """One call: host mesh + coefficients in -> host CSR out (see HostAssemblyJob)."""
+    job = HostAssemblyJob(coords, cells, order, eps_r, mu_r, pec)
+    try:
+        return job.run(want, out, n_blocks)
+    finally:
+        job.close()

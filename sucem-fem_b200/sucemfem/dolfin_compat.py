@@ -221,8 +221,40 @@ class DeviceCSRMatrix(object):
         return self.to_scipy() + (other.to_scipy() if isinstance(other, DeviceCSRMatrix) else other)
 
 
+class HostCSRMatrix(DeviceCSRMatrix):
+    """A matrix whose CSR arrays live in (page-locked) HOST memory, like the reference's dolfin.uBLASSparseMatrix that
+    EMDrivenProblem selects for the scipy hand-off (/root/reference/sucemfem/ProblemConfigurations/
+    EMDrivenProblem.py:82-87).  SystemMatrices fills it by streaming row blocks out of the device while they are
+    being assembled (DeviceSpace.assemble_to_host); data() then costs nothing.  assemble(form, tensor=HostCSRMatrix())
+    of a single form takes the device path and copies."""
+
+    def __init__(self):
+        DeviceCSRMatrix.__init__(self)
+        self._host = None
+        self._ndof = None
+
+    def init_host(self, ndof, rowptr, cols, values):
+        self._ndof, self._host = ndof, (rowptr, cols, values)
+
+    def size(self, dim):
+        return self._ndof if self._host is not None else DeviceCSRMatrix.size(self, dim)
+
+    def data(self):
+        if self._host is None:
+            return DeviceCSRMatrix.data(self)
+        return tuple(t.numpy() for t in self._host)
+
+    def ident(self, row_flags):
+        if self._host is None:
+            return DeviceCSRMatrix.ident(self, row_flags)
+        rp, cl, v = self.data()
+        for r in np.nonzero(row_flags.cpu().numpy())[0]:
+            a, b = rp[r], rp[r + 1]
+            v[a:b] = (cl[a:b] == r).astype(np.float64)
+
+
 PETScMatrix = DeviceCSRMatrix
-uBLASSparseMatrix = DeviceCSRMatrix
+uBLASSparseMatrix = HostCSRMatrix
 
 
 def assemble(form, tensor=None, pec_row_flags=None, kernel=N.KERNEL_AUTO):

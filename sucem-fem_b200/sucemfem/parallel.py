@@ -23,6 +23,16 @@ def split_by_weight(weights_prefix, nparts):
     return [int(x) for x in b]
 
 
+def split_by_class(weights_prefix, n_edges, nparts):
+    """One range of edge entities and one range of face / interior entities per rank, each class balanced on its own
+    (mirrors sfem_partition_rows_by_class): every rank then runs the same mix of edge-row and face-row work.
+    Returns (edge_bounds, other_bounds), nparts+1 boundaries each, in the combined entity numbering."""
+    wp = torch.as_tensor(weights_prefix, dtype=torch.int64)
+    eb = split_by_weight(wp[:n_edges + 1], nparts)
+    ob = [n_edges + x for x in split_by_weight(wp[n_edges:], nparts)]
+    return eb, ob
+
+
 def my_block(bounds, rank=None):
     rank = dist.get_rank() if rank is None else rank
     return bounds[rank], bounds[rank + 1]
@@ -60,3 +70,11 @@ def gather_csr_blocks(rowptr_block, cols_block, values_block, group=None):
         vals.append(vls[p][:nz])
         off += nz
     return torch.cat(rowptr), torch.cat(cols), torch.cat(vals)
+
+
+def gather_csr_two_class(edge_block, other_block, group=None):
+    """Full CSR from the two-class partition: edge_block / other_block = (rowptr, cols, values) of this rank's edge
+    rows and face rows.  Global row order is all edge rows (rank order) followed by all face rows (rank order)."""
+    rp_e, cl_e, vl_e = gather_csr_blocks(*edge_block, group=group)
+    rp_o, cl_o, vl_o = gather_csr_blocks(*other_block, group=group)
+    return torch.cat([rp_e, rp_o[1:] + rp_e[-1]]), torch.cat([cl_e, cl_o]), torch.cat([vl_e, vl_o])

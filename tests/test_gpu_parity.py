@@ -133,6 +133,73 @@ def test_row_blocks_concatenate_to_full(dev):
         assert np.array_equal(np.concatenate(cs), cl.cpu().numpy())
 
 
+def test_two_class_row_blocks_concatenate_to_full(dev):
+    """The bench / multi-GPU partition: rank p owns one edge range and one face range (sfem_partition_rows_by_class).
+    Edge blocks then face blocks, in rank order, are the full matrix bit for bit (canonical kernels)."""
+    import torch
+    from sucemfem import _native as N
+    co, ce = meshes.unit_cube(4)
+    m = dev.DeviceMesh(co, ce)
+    sp = dev.DeviceSpace(m, 2)
+    full = sp.pattern()
+    S, T = full.assemble_ST(kernel=N.KERNEL_CANONICAL)
+    rp, cl = full.csr()
+    for P in (2, 5, 8):
+        eb, ob = sp.partition_by_class(P)
+        assert eb[0] == 0 and eb[-1] == sp.n_edges == ob[0] and ob[-1] == sp.n_entities
+        assert all(x <= y for x, y in zip(eb, eb[1:])) and all(x <= y for x, y in zip(ob, ob[1:]))
+        Ss, Ts, cs = [], [], []
+        for b in (eb, ob):
+            for p in range(P):
+                blk = dev.DevicePattern(sp, b[p], b[p + 1])
+                s, t = blk.assemble_ST(kernel=N.KERNEL_CANONICAL)
+                Ss.append(s); Ts.append(t); cs.append(blk.csr()[1])
+        assert torch.equal(torch.cat(Ss), S) and torch.equal(torch.cat(Ts), T) and torch.equal(torch.cat(cs), cl)
+    # order 1 has no second class: the face ranges are empty
+    sp1 = dev.DeviceSpace(m, 1)
+    eb, ob = sp1.partition_by_class(3)
+    assert eb[-1] == sp1.n_entities and ob == [sp1.n_entities] * 4
+
+
+@pytest.mark.parametrize('name,order', [('cube3_jitter', 2), ('cube3x2x4', 1), ('square4x2', 2)])
+def test_streamed_host_output_equals_device_matrices(dev, name, order):
+    """sfem_host_job_* / sfem_space_assemble_to_host: host arrays in, host CSR out, streamed in row blocks; every block
+    count gives the device path's S, T, S_0, rowptr and cols bit for bit (PEC from markers and 'exterior')."""
+    import torch
+    from sucemfem import _native as N
+    co, ce = MESHES[name]
+    rng = np.random.default_rng(11)
+    eps, mu = rng.uniform(1, 16, len(ce)), rng.uniform(1, 2, len(ce))
+    m = dev.DeviceMesh(co, ce)
+    sp = dev.DeviceSpace(m, order)
+    pat = sp.pattern()
+    markers = torch.zeros(sp.n_facets, dtype=torch.int32, device='cuda')
+    sp.mark_exterior_facets(markers, 999)
+    flags = sp.pec_row_flags(markers, 999)
+    d_eps, d_mu = torch.from_numpy(eps).cuda(), torch.from_numpy(mu).cuda()
+    S, T = pat.assemble_ST(d_eps, d_mu, flags)
+    S0 = pat.assemble(N.FORM_ABC, pec_flags=flags)
+    rp, cl = pat.csr()
+    want = {'rowptr': rp, 'cols': cl, 'S': S, 'T': T, 'S0': S0}
+    assert sp.count_nnz() == pat.nnz
+    for nb in (0, 1, 2, 7):
+        out = sp.assemble_to_host(d_eps, d_mu, flags, want=('cols', 'S', 'T', 'S0'), n_blocks=nb)
+        for k, v in want.items():
+            assert out[k].is_pinned() and torch.equal(out[k], v.cpu()), (nb, k)
+    # host arrays in: PEC walls by mode ('exterior') and by an explicit marker array
+    for pec in ('exterior', (markers.cpu().numpy().astype(np.uint32), 999)):
+        job = dev.HostAssemblyJob(co, ce, order, eps, mu, pec=pec)
+        assert (job.ndof, job.nnz) == (sp.ndof, pat.nnz)
+        out = job.run(want=('cols', 'S', 'T'), n_blocks=3)
+        for k in ('rowptr', 'cols', 'S', 'T'):
+            assert torch.equal(out[k], want[k].cpu()), k
+        job.close()
+    # no essential condition, default coefficients, only one matrix requested
+    T1 = pat.assemble(N.FORM_MASS)       # a single matrix goes through the single-form kernel
+    out = dev.assemble_host(co, ce, order, want=('T',), n_blocks=2)
+    assert torch.equal(out['T'], T1.cpu()) and torch.equal(out['rowptr'], rp.cpu())
+
+
 def test_material_expansion(dev):
     import torch
     reg = torch.tensor([0, 1000, 1001, 1000, 0], dtype=torch.int32, device='cuda')

@@ -42,7 +42,18 @@ def _worker(rank, world, port, ret):
     full_rp, full_cols, full_vals = parallel.gather_csr_blocks(rp, cols, vals)
     ok = (np.array_equal(full_rp.numpy(), ref['rowptr']) and np.array_equal(full_cols.numpy(), ref['cols'])
           and np.array_equal(full_vals.numpy(), ref['S']) and bounds[0] == 0 and bounds[-1] == n_ent)
-    ret[rank] = bool(ok) and (hi - lo) > 0
+    # the two-class partition the bench uses: one edge range + one face range per rank
+    eb, ob = parallel.split_by_class(prefix, num['E'], world)
+
+    def block(b):
+        a0, a1 = 2 * b[rank], 2 * b[rank + 1]
+        s0, s1 = ref['rowptr'][a0], ref['rowptr'][a1]
+        return (torch.from_numpy(ref['rowptr'][a0:a1 + 1] - s0), torch.from_numpy(ref['cols'][s0:s1].copy()),
+                torch.from_numpy(ref['M'][s0:s1].copy()))
+    rp2, cl2, vl2 = parallel.gather_csr_two_class(block(eb), block(ob))
+    ok2 = (np.array_equal(rp2.numpy(), ref['rowptr']) and np.array_equal(cl2.numpy(), ref['cols'])
+           and np.array_equal(vl2.numpy(), ref['M']) and eb[-1] == num['E'] == ob[0] and ob[-1] == n_ent)
+    ret[rank] = bool(ok) and bool(ok2) and (hi - lo) > 0
     dist.barrier()
     dist.destroy_process_group()
 
