@@ -149,6 +149,24 @@ SFEM_API int sfem_launches_per_assemble_ST(sfem_pattern_t pat, int kernel);
  * flagged rows of the block become unit rows, pattern kept, columns untouched. */
 SFEM_API int sfem_apply_ident(sfem_pattern_t pat, const uint8_t* d_row_flags, double* d_values, void* stream);
 
+/* ---- consumers that stay on the device (solvers of the reference, sucemfem/Utilities/LinalgSolvers.py) ----------
+ * y = sum_m c_m (A_m x) for n_mats <= 4 matrices that share the pattern `pat` (d_values: HOST array of n_mats DEVICE
+ * pointers, each double [nnz]); coef_re_im: HOST array [2*n_mats] (re, im) or NULL = all 1.  complex_vectors != 0:
+ * d_x complex128 [ndof], d_y complex128 [n_rows of the block] (interleaved re, im); else real arrays and real c_m.
+ * This is `M*x` (EMVectorWaveEigenproblem.py:86,98) and A = S - k0^2 M + j k0 S_0 (EMDrivenProblem.py:67-72) applied
+ * without forming A. */
+SFEM_API int sfem_matvec(sfem_pattern_t pat, int n_mats, const double* const* d_values, const double* coef_re_im,
+                int complex_vectors, const double* d_x, double* d_y, void* stream);
+/* BiCGStab on sum_m c_m A_m (scipy.sparse.linalg.bicgstab as called by BiCGStabSolver, LinalgSolvers.py:239-249;
+ * solve_sparse_system, :303-322).  d_b complex128 [ndof]; d_x complex128 [ndof]: initial guess in, solution out.
+ * preconditioner 0: none, 1: diagonal (1/diag(A), LinalgSolvers.py:115).  Stops when ||b - A x|| <= rtol ||b||.
+ * Returns 0 on convergence, 6 when maxiter was reached (x = last iterate), 5 on breakdown.  Needs the pattern of
+ * all rows.  Synchronises the stream every iteration (the scalars of the recurrence are reduced on the device and
+ * read back). */
+SFEM_API int sfem_bicgstab(sfem_pattern_t pat, int n_mats, const double* const* d_values, const double* coef_re_im,
+                  const double* d_b, double* d_x, int preconditioner, double rtol, int maxiter, int* iterations,
+                  double* relres, void* stream);
+
 /* ---- host-buffer entry points: the whole path with HOST arrays in and out --------------------------------------
  * What a host consumer gets from the reference today: FunctionSpace(mesh, family, order) (EMProblem.py:100-105),
  * assemble(M), assemble(S) [, assemble(S_0)] + apply_essential (SystemMatrices.py:54-55) and A.data()

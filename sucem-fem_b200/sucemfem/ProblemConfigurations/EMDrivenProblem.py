@@ -20,6 +20,12 @@ class CombineForms(Forms.CombineGalerkinForms):
 
 class DrivenProblemABC(EMProblem):
     FormCombiner = CombineForms
+    # The reference hands its matrices to scipy (uBLASSparseMatrix = host CSR, EMDrivenProblem.py:82-87).  Setting
+    # this to dolfin.PETScMatrix (device CSR) keeps S, M, S_0 in HBM for get_LHS_operator() and the device solver.
+    matrix_class = dolfin.uBLASSparseMatrix
+
+    def set_matrix_class(self, matrix_class):
+        self.matrix_class = matrix_class
 
     def set_sources(self, sources):
         self.sources = sources
@@ -35,6 +41,15 @@ class DrivenProblemABC(EMProblem):
         S_0 = dolfin_ublassparse_to_scipy_csr(self.system_matrices['S_0'])
         return S - k0 ** 2 * M + 1j * k0 * S_0
 
+    def get_LHS_operator(self):
+        """The same matrix as a device operator (never formed): needs device-resident matrices
+        (set_matrix_class(dolfin.PETScMatrix) before init_problem)."""
+        k0 = 2 * N.pi * self.frequency / c0
+        sm = self.system_matrices
+        if sm['S_0'] is None:
+            return dolfin.DeviceLinearOperator([sm['S'], sm['M']], [1.0, -k0 ** 2])
+        return dolfin.DeviceLinearOperator([sm['S'], sm['M'], sm['S_0']], [1.0, -k0 ** 2, 1j * k0])
+
     def get_RHS(self):
         RHS = N.zeros(self.get_global_dimension(), N.complex128)
         dofnos, contribs = self._get_RHS_contributions()
@@ -44,7 +59,7 @@ class DrivenProblemABC(EMProblem):
         return RHS
 
     def _init_system_matrices(self):
-        EMProblem._init_system_matrices(self, matrix_class=dolfin.uBLASSparseMatrix)
+        EMProblem._init_system_matrices(self, matrix_class=self.matrix_class)
 
     def _get_RHS_contributions(self):
         self.sources.set_function_space(self.function_space)

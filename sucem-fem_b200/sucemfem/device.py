@@ -221,6 +221,50 @@ class DevicePattern(object):
                                            kernel, _stream_ptr()))
         return S, T
 
+    def matvec(self, values, x, coefs=None, out=None):
+        """y = sum_m coefs[m] * (A_m x) for value arrays that share this pattern (sfem_matvec).  x: device tensor
+        [ndof], float64 or complex128; coefs: python complex / float per matrix (default 1)."""
+        values = list(values)
+        cplx = x.dtype == torch.complex128
+        assert x.dtype in (torch.float64, torch.complex128) and x.is_contiguous()
+        if out is None:
+            out = torch.empty(self.n_rows, dtype=x.dtype, device=x.device)
+        vp = (C.c_void_p * len(values))(*[v.data_ptr() for v in values])
+        co = None
+        if coefs is not None:
+            flat = []
+            for c in coefs:
+                flat += [complex(c).real, complex(c).imag]
+            co = (C.c_double * len(flat))(*flat)
+        with torch.cuda.device(self.space.mesh.device):
+            N.check(N.lib.sfem_matvec(self.handle, len(values), vp, co, int(cplx), _ptr(x), _ptr(out), _stream_ptr()))
+        return out
+
+    def bicgstab(self, values, coefs, b, x0=None, preconditioner='diagonal', rtol=1e-5, maxiter=None):
+        """Solve (sum_m coefs[m] A_m) x = b with BiCGStab on the device (sfem_bicgstab).  Returns (x, info, iterations,
+        relres) with scipy's info convention (0 converged, > 0 = maxiter reached, < 0 breakdown)."""
+        values = list(values)
+        dev = self.space.mesh.device
+        b = torch.as_tensor(b, device=dev).to(torch.complex128).contiguous()
+        x = torch.zeros_like(b) if x0 is None else torch.as_tensor(x0, device=dev).to(torch.complex128).clone().contiguous()
+        vp = (C.c_void_p * len(values))(*[v.data_ptr() for v in values])
+        flat = []
+        for c in coefs:
+            flat += [complex(c).real, complex(c).imag]
+        co = (C.c_double * len(flat))(*flat)
+        pre = {None: 0, 'none': 0, 'diagonal': 1}[preconditioner.lower() if isinstance(preconditioner, str) else None]
+        maxiter = 10 * self.space.ndof if maxiter is None else int(maxiter)      # scipy's default
+        it, rr = C.c_int(0), C.c_double(0.0)
+        with torch.cuda.device(dev):
+            rc = N.lib.sfem_bicgstab(self.handle, len(values), vp, co, _ptr(b), _ptr(x), pre, float(rtol), maxiter,
+                                     C.byref(it), C.byref(rr), _stream_ptr())
+        if rc == 6:
+            return x, it.value, it.value, rr.value
+        if rc == 5:
+            return x, -10, it.value, rr.value
+        N.check(rc)
+        return x, 0, it.value, rr.value
+
     def apply_ident(self, flags, values):
         with torch.cuda.device(self.space.mesh.device):
             N.check(N.lib.sfem_apply_ident(self.handle, _ptr(flags), _ptr(values), _stream_ptr()))

@@ -221,6 +221,50 @@ class DeviceCSRMatrix(object):
         return self.to_scipy() + (other.to_scipy() if isinstance(other, DeviceCSRMatrix) else other)
 
 
+class DeviceLinearOperator(object):
+    """sum_m c_m A_m of device matrices that share one pattern, applied without being formed (sfem_matvec) -- e.g. the
+    driven system matrix S - k0^2 M + j k0 S_0 (/root/reference/sucemfem/ProblemConfigurations/EMDrivenProblem.py:67-72).
+    Quacks enough like a scipy sparse matrix for solver code: shape, dtype, matvec, `A * x`, diagonal()."""
+
+    def __init__(self, matrices, coefficients):
+        mats = [m for m in matrices]
+        assert len(mats) == len(coefficients) and len(mats) >= 1
+        assert all(m.pattern is mats[0].pattern for m in mats), 'the matrices must share one pattern'
+        self.pattern = mats[0].pattern
+        self.values = [m.values for m in mats]
+        self.coefficients = [complex(c) for c in coefficients]
+        n = self.pattern.space.ndof
+        self.shape = (n, n)
+        self.dtype = np.dtype(np.complex128)
+
+    def matvec(self, x):
+        host = not isinstance(x, torch.Tensor)
+        xd = torch.as_tensor(np.ascontiguousarray(x), device=self.pattern.space.mesh.device) if host else x
+        y = self.pattern.matvec(self.values, xd.to(torch.complex128).contiguous(), self.coefficients)
+        return y.cpu().numpy() if host else y
+
+    __mul__ = matvec
+    dot = matvec
+
+    def diagonal(self):
+        n = self.shape[0]
+        rp, cl = self.pattern.csr()
+        rows = torch.repeat_interleave(torch.arange(n, device=rp.device), rp[1:] - rp[:-1])
+        sel = cl.long() == rows
+        d = torch.zeros(n, dtype=torch.complex128, device=rp.device)
+        for v, c in zip(self.values, self.coefficients):
+            d[rows[sel]] += c * v[sel]
+        return d.cpu().numpy()
+
+    def to_scipy(self):
+        out = None
+        for v, c in zip(self.values, self.coefficients):
+            m = DeviceCSRMatrix()
+            m.init(self.pattern, v)
+            out = c * m.to_scipy() if out is None else out + c * m.to_scipy()
+        return out
+
+
 class HostCSRMatrix(DeviceCSRMatrix):
     """A matrix whose CSR arrays live in (page-locked) HOST memory, like the reference's dolfin.uBLASSparseMatrix that
     EMDrivenProblem selects for the scipy hand-off (/root/reference/sucemfem/ProblemConfigurations/

@@ -1,0 +1,136 @@
+"""Device consumers of the assembled matrices: the fused multi-matrix SpMV over the shared
+entity-block pattern and the native BiCGStab, against scipy on the same matrices; and the reference's solver API
+(sucemfem/Utilities/LinalgSolvers.py) driving them."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN
+from oracle import meshes
+
+pytestmark = pytest.mark.gpu
+
+c0 = 299792458
+
+
+@pytest.mark.parametrize('mesh,order', [('cube', 2), ('cube', 1), ('square', 2), ('square', 1)])
+def test_matvec_matches_scipy(mesh, order):
+    import torch
+    from sucemfem import device as dev, _native as N
+    from sucemfem import dolfin_compat as dolfin
+    co, ce = meshes.unit_cube(3, 2, 4) if mesh == 'cube' else meshes.unit_square(5, 4)
+    rng = np.random.default_rng(3)
+    co = co + 0.03 * rng.standard_normal(co.shape)
+    sp = dev.DeviceSpace(dev.DeviceMesh(co, ce), order)
+    pat = sp.pattern()
+    mats = [pat.assemble(f) for f in (N.FORM_STIFFNESS, N.FORM_MASS, N.FORM_ABC)]
+    coefs = [1.0, -2.5, 0.7j]
+    sc = []
+    for v in mats:
+        m = dolfin.DeviceCSRMatrix()
+        m.init(pat, v)
+        sc.append(m.to_scipy())
+    A = sum(c * m for c, m in zip(coefs, sc))
+    x = rng.standard_normal(sp.ndof) + 1j * rng.standard_normal(sp.ndof)
+    y = pat.matvec(mats, torch.from_numpy(x).cuda(), coefs).cpu().numpy()
+    ref = A @ x
+    assert np.abs(y - ref).max() <= 1e-13 * np.abs(ref).max()
+    # real vectors, real coefficients, a single matrix (M*x of the eigen solver)
+    xr = rng.standard_normal(sp.ndof)
+    yr = pat.matvec(mats[1:2], torch.from_numpy(xr).cuda()).cpu().numpy()
+    assert np.abs(yr - sc[1] @ xr).max() <= 1e-13 * np.abs(sc[1] @ xr).max()
+    # row blocks give slices of the product (multi-GPU contract)
+    b = sp.partition(3)
+    blk = dev.DevicePattern(sp, b[1], b[2])
+    vb = [blk.assemble(f) for f in (N.FORM_STIFFNESS, N.FORM_MASS, N.FORM_ABC)]
+    yb = blk.matvec(vb, torch.from_numpy(x).cuda(), coefs).cpu().numpy()
+    assert np.abs(yb - ref[blk.row_begin:blk.row_begin + blk.n_rows]).max() <= 1e-13 * np.abs(ref).max()
+
+
+def _problem(device_resident):
+    from sucemfem import dolfin_compat as dolfin
+    from sucemfem.BoundaryConditions import ABCBoundaryCondition, BoundaryConditions
+    from sucemfem.ProblemConfigurations.EMDrivenProblem import DrivenProblemABC
+    from sucemfem.Utilities.MeshGenerators import get_centred_cube
+    from sucemfem.Sources import current_source
+    from sucemfem.Sources.fillament_current_source import FillamentCurrentSource
+    g = np.load(os.path.join(GOLDEN, 'driven_order2_unitcube3.npz'))
+    freq = float(g['freq'])
+    lam = c0 / freq
+    mesh = get_centred_cube(np.array([lam] * 3) * 0.25, lam / 6)
+    srcs = current_source.CurrentSources()
+    fil = FillamentCurrentSource()
+    fil.set_source_endpoints(g['source_endpoints'])
+    fil.set_value(float(g['I']))
+    srcs.add_source(fil)
+    material_mesh_func = dolfin.MeshFunction('uint', mesh, 3)
+    material_mesh_func.set_all(0)
+    abc = ABCBoundaryCondition()
+    abc.set_region_number(1)
+    bcs = BoundaryConditions()
+    bcs.add_boundary_condition(abc)
+    dp = DrivenProblemABC()
+    if device_resident:
+        dp.set_matrix_class(dolfin.PETScMatrix)
+    dp.set_mesh(mesh)
+    dp.set_basis_order(2)
+    dp.set_material_regions({0: dict(eps_r=1, mu_r=1)})
+    dp.set_region_meshfunction(material_mesh_func)
+    dp.set_boundary_conditions(bcs)
+    dp.set_sources(srcs)
+    dp.init_problem()
+    dp.set_frequency(freq)
+    return dp, g
+
+
+def test_device_bicgstab_reproduces_reference_solution():
+    """The reference's shipped order-2 driven solution (fixture 5, generated with UMFPACK) from the DEVICE solver:
+    S, M, S_0 stay in HBM, A is applied as a fused three-matrix SpMV, BiCGStab with the reference's 'diagonal'
+    preconditioner (examples/infinitesimal_dipole/driver.py:83)."""
+    from sucemfem.Utilities import LinalgSolvers
+    dp, g = _problem(device_resident=True)
+    A = dp.get_LHS_operator()
+    b = dp.get_RHS()
+    # the operator is the reference's LHS matrix
+    As = A.to_scipy()
+    x0 = np.random.default_rng(0).standard_normal(len(b)) + 0j
+    assert np.abs(A * x0 - As @ x0).max() <= 1e-13 * np.abs(As @ x0).max()
+    assert np.allclose(A.diagonal(), As.diagonal(), rtol=1e-13, atol=0)
+    solver = LinalgSolvers.BiCGStabSolver(A, 'diagonal')
+    solver.rtol = 1e-12
+    x = solver.solve(b)
+    assert solver.info == 0 and solver.iterations > 1
+    assert np.linalg.norm(As @ x - b) <= 1e-11 * np.linalg.norm(b)
+    assert np.linalg.norm(x - g['x']) / np.linalg.norm(g['x']) < 1e-8
+    # un-preconditioned, default tolerance, through the reference's convenience function
+    x2 = LinalgSolvers.solve_sparse_system(A, b, preconditioner_type=None)
+    assert np.linalg.norm(As @ x2 - b) <= 1.01e-5 * np.linalg.norm(b)
+
+
+def test_host_solver_path_matches_reference_usage():
+    """solve_sparse_system on the scipy LHS (what the reference's drivers do) gives the same solution."""
+    from sucemfem.Utilities import LinalgSolvers
+    dp, g = _problem(device_resident=False)
+    A, b = dp.get_LHS_matrix(), dp.get_RHS()
+    s = LinalgSolvers.BiCGStabSolver(A, 'diagonal')
+    s.rtol = 1e-12
+    x = s.solve(b)
+    assert np.linalg.norm(x - g['x']) / np.linalg.norm(g['x']) < 1e-8
+    x3 = LinalgSolvers.UMFPACKSolver(A).solve(b)
+    assert np.linalg.norm(x3 - g['x']) / np.linalg.norm(g['x']) < 1e-11
+
+
+def test_bicgstab_reports_non_convergence_and_zero_rhs():
+    import torch
+    from sucemfem import device as dev, _native as N
+    co, ce = meshes.unit_cube(2)
+    sp = dev.DeviceSpace(dev.DeviceMesh(co, ce), 2)
+    pat = sp.pattern()
+    S, M = pat.assemble_ST()
+    b = torch.zeros(sp.ndof, dtype=torch.complex128, device='cuda')
+    x, info, its, rr = pat.bicgstab([S, M], [1.0, 1.0], b)
+    assert info == 0 and float(x.abs().max()) == 0.0
+    b[3] = 1.0
+    x, info, its, rr = pat.bicgstab([S, M], [1.0, 1.0], b, rtol=1e-14, maxiter=2)
+    assert info > 0 and its == 2 and rr > 1e-14
