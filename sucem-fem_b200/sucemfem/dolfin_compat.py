@@ -109,6 +109,8 @@ class MeshFunction(object):
                 n = mesh.num_cells()
             elif self._dim == tdim - 1:
                 n = mesh.num_facets()
+            elif self._dim == 1:
+                n = mesh._numbering().n_edges
             elif self._dim == 0:
                 n = mesh.num_vertices()
             else:
@@ -127,6 +129,14 @@ class MeshFunction(object):
 
 def CellFunction(value_type, mesh):
     return MeshFunction(value_type, mesh, mesh.topology().dim())
+
+
+def FaceFunction(value_type, mesh):
+    return MeshFunction(value_type, mesh, 2)
+
+
+def EdgeFunction(value_type, mesh):
+    return MeshFunction(value_type, mesh, 1)
 
 
 class DomainBoundary(object):

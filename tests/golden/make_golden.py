@@ -30,6 +30,19 @@ def load(p):
         return pickle.load(f, encoding='latin1')
 
 
+def read_dolfin_xml_mesh(path):
+    import xml.etree.ElementTree as ET
+    mesh = ET.parse(path).getroot().find('mesh')
+    vs, cs = mesh.find('vertices'), mesh.find('cells')
+    co = np.zeros((int(vs.get('size')), 3))
+    for v in vs:
+        co[int(v.get('index'))] = [float(v.get(a)) for a in 'xyz']
+    ce = np.zeros((int(cs.get('size')), 4), np.int32)
+    for c in cs:
+        ce[int(c.get('index'))] = [int(c.get('v%d' % i)) for i in range(4)]
+    return co, ce
+
+
 def main():
     lhs = np.load(REF + 'ProblemConfigurations/tests/LHS_matrix.npy')
     rhs = load('ProblemConfigurations/tests/RHS_vector.pickle')
@@ -39,9 +52,14 @@ def main():
     np.savez_compressed(os.path.join(HERE, 'fillament_source_order2.npz'), **{k: np.asarray(v) for k, v in d.items()})
     d = load('PostProcessing/tests/data/power_flux_reference_dofs_f-1000000000.000000_o-2_s-0.074948_'
              'l-0.100000_h-0.166667.pickle')
+    # the mesh the reference's flux tests read back (coordinates rounded by the XML writer: the known answers below
+    # belong to THIS mesh, not to the exact get_centred_cube one the solution was computed on)
+    mco, mce = read_dolfin_xml_mesh(REF + 'PostProcessing/tests/data/' + d['meshfile'])
     np.savez_compressed(os.path.join(HERE, 'driven_order2_unitcube3.npz'), x=d['x'], freq=d['freq'],
                         order=d['order'], source_endpoints=d['source_endpoints'], I=d['I'],
-                        known_answer_variational_flux=np.complex128(26.9015957282 - 7.85747240242e-08j))
+                        mesh_coordinates=mco, mesh_cells=mce,
+                        known_answer_variational_flux=np.complex128(26.9015957282 - 7.85747240242e-08j),
+                        known_answer_surface_flux=26.3586862457)
     d = load('PostProcessing/tests/data/reference_dofs-2-0.149896229-0.0499654096667.pickle')
     np.savez_compressed(os.path.join(HERE, 'driven_order2_unitcube5.npz'), **{k: np.asarray(v) for k, v in d.items()})
 

@@ -1,0 +1,98 @@
+"""Post-processing functionals through the mirrored API, against the reference's known answers
+(/root/reference/sucemfem/PostProcessing/tests/test_power_flux.py:55-77, test_Postprocessing.py:33-52)."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN
+
+pytestmark = pytest.mark.gpu
+
+c0 = 299792458
+
+
+def _fixture_space():
+    from sucemfem import dolfin_compat as dolfin
+    g = np.load(os.path.join(GOLDEN, 'driven_order2_unitcube3.npz'))
+    # the fixture's ..._mesh.xml as the reference's test reads it back: coordinates rounded by the XML writer (the
+    # known answers belong to this mesh; on the exact get_centred_cube mesh the flux is 26.90157383)
+    mesh = dolfin.Mesh(coordinates=g['mesh_coordinates'], cells=g['mesh_cells'])
+    V = dolfin.FunctionSpace(mesh, "Nedelec 1st kind H(curl)", int(g['order']))
+    return V, g, 2 * np.pi * float(g['freq']) / c0
+
+
+def test_variational_surface_flux_known_answer():
+    """test_power_flux.py:59-77: VariationalSurfaceFlux of the shipped solution = 26.9015957282-7.85747240242e-08j
+    (assertAlmostEqual: 7 decimal places)."""
+    from sucemfem.PostProcessing import power_flux
+    V, g, k0 = _fixture_space()
+    DUT = power_flux.VariationalSurfaceFlux(V)
+    DUT.set_k0(k0)
+    DUT.set_dofs(g['x'])
+    got = DUT.calc_flux()
+    assert abs(got - complex(g['known_answer_variational_flux'])) < 5e-8
+
+
+def test_surface_flux_known_answer():
+    """test_power_flux.py:35-55: SurfaceFlux (Poynting vector over the exterior facets) = 26.3586862457."""
+    from sucemfem.PostProcessing import power_flux
+    V, g, k0 = _fixture_space()
+    DUT = power_flux.SurfaceFlux(V)
+    DUT.set_k0(k0)
+    DUT.set_dofs(g['x'])
+    assert abs(DUT.calc_flux() - float(g['known_answer_surface_flux'])) < 5e-8
+
+
+def test_functional_symmetry():
+    """test_Postprocessing.py:33-52: swapping E and g leaves the functional unchanged."""
+    from sucemfem import dolfin_compat as dolfin
+    from sucemfem.PostProcessing import CalcEMFunctional
+    mesh = dolfin.UnitCube(2, 2, 2)
+    V = dolfin.FunctionSpace(mesh, "Nedelec 1st kind H(curl)", 1)
+    n = V.dofmap().global_dimension()
+    rng = np.random.default_rng(2)
+    E = rng.random(n) + 1j * rng.random(n)
+    gd = rng.random(n) + 1j * rng.random(n)
+    DUT = CalcEMFunctional(V)
+    DUT.set_k0(rng.random() * 10)
+    DUT.set_g_dofs(gd)
+    DUT.set_E_dofs(E)
+    v1 = DUT.calc_functional()
+    DUT.set_g_dofs(E)
+    DUT.set_E_dofs(gd)
+    v2 = DUT.calc_functional()
+    assert abs(v1 - v2) <= 1e-13 * abs(v1)
+
+
+def test_boundary_edge_cells_and_reconstruct():
+    from sucemfem import dolfin_compat as dolfin, Geometry
+    from sucemfem.PostProcessing import Reconstruct
+    mesh = dolfin.UnitCube(4, 4, 4)
+    cf = dolfin.CellFunction('uint', mesh)
+    cf.set_all(0)
+    Geometry.BoundaryEdgeCells(mesh).mark(cf, 1)
+    # a cell is unmarked iff none of its vertices... has an edge on the boundary: with n = 4 only cells whose
+    # 6 edges are all interior remain
+    co, ce = mesh.coordinates(), mesh.cells()
+    onb = np.any((co == 0) | (co == 1), axis=1)
+    # an edge lies on the boundary iff both end points share a boundary plane
+    planes = np.stack([co[:, d] == v for d in range(3) for v in (0.0, 1.0)], axis=1)      # [V, 6]
+    expect = np.zeros(len(ce), bool)
+    for a in range(4):
+        for b in range(a + 1, 4):
+            expect |= np.any(planes[ce[:, a]] & planes[ce[:, b]], axis=1)
+    assert np.array_equal(cf.array().astype(bool), expect) and 0 < expect.sum() < len(ce) and onb.any()
+    # reconstruct a constant field: the order-1 interpolant of E = (1, 2, 3) has dofs t_e . E and is exact
+    V = dolfin.FunctionSpace(mesh, "Nedelec 1st kind H(curl)", 1)
+    sp = V.device_space
+    cell_edges = sp.cell_entities()[0].cpu().numpy()
+    Ev = np.array([1.0, 2.0, 3.0])
+    dofs = np.zeros(sp.ndof)
+    loc = [(2, 3), (1, 3), (1, 2), (0, 3), (0, 2), (0, 1)]
+    for k, (a, b) in enumerate(loc):
+        dofs[cell_edges[:, k]] = (co[ce[:, b]] - co[ce[:, a]]) @ Ev
+    rec = Reconstruct(V)
+    rec.set_dof_values(dofs)
+    pts = np.random.default_rng(4).random((7, 3))
+    assert np.allclose(rec.reconstruct_points(pts), Ev[None, :], rtol=0, atol=1e-12)
