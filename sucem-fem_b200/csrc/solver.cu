@@ -42,8 +42,12 @@ __device__ __forceinline__ double2 cfma(double2 acc, double2 a, double2 b) {  //
 }
 
 // y[q*r + k] = sum_m c_m sum_cols A_m[q*r + k, col] x[col]      (CPLX: x, y complex; else real and c_m real)
-template <int Q, bool CPLX>
-__global__ void __launch_bounds__(256) k_matvec(MatvecArgs p, const double* __restrict__ x, double* __restrict__ y) {
+// Half a warp per row entity; two column entities per lane and iteration are in flight (rows of order-2 tets hold
+// 13-45 column entities: one or two iterations).  NM is a template parameter so that the value pointers and
+// coefficients live in registers / immediate constant-bank operands.
+template <int Q, int NM, bool CPLX>
+__global__ void __launch_bounds__(256, NM >= 3 ? 3 : 4) k_matvec(MatvecArgs p, const double* __restrict__ x,
+                                                                  double* __restrict__ y) {
   const int sub = threadIdx.x & 15;
   const int64_t r = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 4;
   const bool valid = r < p.n_rows_ent;
@@ -54,31 +58,57 @@ __global__ void __launch_bounds__(256) k_matvec(MatvecArgs p, const double* __re
     const int64_t a = p.ent_rowptr[r];
     const int len = (int)(p.ent_rowptr[r + 1] - a);
     const int64_t base = (int64_t)Q * Q * a;
-    for (int s = sub; s < len; s += 16) {
-      const int64_t c = p.ent_cols[a + s];
-      double2 xv[Q];
+    for (int s0 = sub; s0 < len; s0 += 32) {
+      constexpr int U = 2;
+      int sl[U];
+      int64_t c[U];
 #pragma unroll
-      for (int j = 0; j < Q; ++j) {
-        if (CPLX) xv[j] = reinterpret_cast<const double2*>(x)[Q * c + j];
-        else xv[j] = make_double2(x[Q * c + j], 0.0);
+      for (int u = 0; u < U; ++u) {
+        sl[u] = s0 + 16 * u;
+        c[u] = sl[u] < len ? (int64_t)p.ent_cols[a + sl[u]] : (int64_t)-1;
       }
+      // matrix entries first (independent of the column ids), combined over the matrices
+      double2 w[U][Q][Q];
 #pragma unroll
-      for (int k = 0; k < Q; ++k) {
-        double2 w[Q];  // combined (complex) matrix entries of row k, column entity s
+      for (int u = 0; u < U; ++u)
 #pragma unroll
-        for (int j = 0; j < Q; ++j) w[j] = make_double2(0.0, 0.0);
-        for (int m = 0; m < p.n_mats; ++m) {
-          const double* v = p.vals[m] + base + (int64_t)k * Q * len + (int64_t)Q * s;
-          if (Q == 2) {
-            const double2 vv = *reinterpret_cast<const double2*>(v);
-            w[0].x = fma(p.cre[m], vv.x, w[0].x); w[0].y = fma(p.cim[m], vv.x, w[0].y);
-            w[1].x = fma(p.cre[m], vv.y, w[1].x); w[1].y = fma(p.cim[m], vv.y, w[1].y);
-          } else {
-            w[0].x = fma(p.cre[m], v[0], w[0].x); w[0].y = fma(p.cim[m], v[0], w[0].y);
+        for (int k = 0; k < Q; ++k) {
+#pragma unroll
+          for (int j = 0; j < Q; ++j) w[u][k][j] = make_double2(0.0, 0.0);
+          if (sl[u] < len) {
+#pragma unroll
+            for (int m = 0; m < NM; ++m) {
+              const double* v = p.vals[m] + base + (int64_t)k * Q * len + (int64_t)Q * sl[u];
+              if (Q == 2) {
+                const double2 vv = __ldcs(reinterpret_cast<const double2*>(v));
+                w[u][k][0].x = fma(p.cre[m], vv.x, w[u][k][0].x);
+                w[u][k][1].x = fma(p.cre[m], vv.y, w[u][k][1].x);
+                if (CPLX) {
+                  w[u][k][0].y = fma(p.cim[m], vv.x, w[u][k][0].y);
+                  w[u][k][1].y = fma(p.cim[m], vv.y, w[u][k][1].y);
+                }
+              } else {
+                const double vv = __ldcs(v);
+                w[u][k][0].x = fma(p.cre[m], vv, w[u][k][0].x);
+                if (CPLX) w[u][k][0].y = fma(p.cim[m], vv, w[u][k][0].y);
+              }
+            }
           }
         }
 #pragma unroll
-        for (int j = 0; j < Q; ++j) acc[k] = cfma(acc[k], w[j], xv[j]);
+      for (int u = 0; u < U; ++u) {
+        if (c[u] < 0) continue;
+#pragma unroll
+        for (int j = 0; j < Q; ++j) {
+          double2 xv;
+          if (CPLX) xv = reinterpret_cast<const double2*>(x)[Q * c[u] + j];
+          else xv = make_double2(x[Q * c[u] + j], 0.0);
+#pragma unroll
+          for (int k = 0; k < Q; ++k) {
+            if (CPLX) acc[k] = cfma(acc[k], w[u][k][j], xv);
+            else acc[k].x = fma(w[u][k][j].x, xv.x, acc[k].x);
+          }
+        }
       }
     }
   }
@@ -246,14 +276,24 @@ int fill_args(const sfem_pattern_s* pat, int n_mats, const double* const* d_valu
   return 0;
 }
 
+template <int Q, bool CPLX>
+void launch_matvec_nm(const MatvecArgs& a, unsigned grid, const double* x, double* y, cudaStream_t st) {
+  switch (a.n_mats) {
+    case 1: k_matvec<Q, 1, CPLX><<<grid, 256, 0, st>>>(a, x, y); break;
+    case 2: k_matvec<Q, 2, CPLX><<<grid, 256, 0, st>>>(a, x, y); break;
+    case 3: k_matvec<Q, 3, CPLX><<<grid, 256, 0, st>>>(a, x, y); break;
+    default: k_matvec<Q, 4, CPLX><<<grid, 256, 0, st>>>(a, x, y); break;
+  }
+}
+
 int launch_matvec(const sfem_pattern_s* pat, const MatvecArgs& a, bool cplx, const double* x, double* y, cudaStream_t st) {
   if (pat->n_rows_ent == 0) return 0;
   const unsigned grid = grid_for(pat->n_rows_ent * 16);
   const int q = pat->space->order;
-  if (q == 2 && cplx) k_matvec<2, true><<<grid, 256, 0, st>>>(a, x, y);
-  else if (q == 2) k_matvec<2, false><<<grid, 256, 0, st>>>(a, x, y);
-  else if (cplx) k_matvec<1, true><<<grid, 256, 0, st>>>(a, x, y);
-  else k_matvec<1, false><<<grid, 256, 0, st>>>(a, x, y);
+  if (q == 2 && cplx) launch_matvec_nm<2, true>(a, grid, x, y, st);
+  else if (q == 2) launch_matvec_nm<2, false>(a, grid, x, y, st);
+  else if (cplx) launch_matvec_nm<1, true>(a, grid, x, y, st);
+  else launch_matvec_nm<1, false>(a, grid, x, y, st);
   SFEM_CUDA(cudaGetLastError());
   return 0;
 }
