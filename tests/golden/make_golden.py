@@ -62,6 +62,20 @@ def main():
                         known_answer_surface_flux=26.3586862457)
     d = load('PostProcessing/tests/data/reference_dofs-2-0.149896229-0.0499654096667.pickle')
     np.savez_compressed(os.path.join(HERE, 'driven_order2_unitcube5.npz'), **{k: np.asarray(v) for k, v in d.items()})
+    # far-field fixtures of test_ntff.py:80-110 (the near-field input is the dof vector above, on the NOT recentred
+    # get_centred_cube(domain_size, max_edge_len) mesh) and the testing-expression samples of test_ntff.py:33-61
+    out = {}
+    for kind in ('surface', 'variational'):
+        t = load('PostProcessing/tests/data/reference_%s_ntff-2-0.149896229-0.0499654096667.pickle' % kind)
+        ff, nf = t['ff_result_data'], t['nf_input_data']
+        assert np.array_equal(nf['x'], d['x'])
+        out.update({kind + '_E_ff': np.asarray(ff['E_ff']), kind + '_theta_deg': np.asarray(ff['theta_deg'], float),
+                    kind + '_phi_deg': np.asarray(ff['phi_deg'], float)})
+        out.update(dict(domain_size=np.asarray(nf['domain_size']), max_edge_len=float(nf['max_edge_len']),
+                        freq=float(nf['freq']), order=int(nf['order'])))
+    t = load('PostProcessing/tests/data/interpolant_test_data.pickle')
+    out.update({'interp_' + k: np.asarray(v) for k, v in t.items()})
+    np.savez_compressed(os.path.join(HERE, 'ntff_order2_unitcube5.npz'), **out)
 
 
 def prism():

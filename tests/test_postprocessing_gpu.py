@@ -96,3 +96,79 @@ def test_boundary_edge_cells_and_reconstruct():
     rec.set_dof_values(dofs)
     pts = np.random.default_rng(4).random((7, 3))
     assert np.allclose(rec.reconstruct_points(pts), Ev[None, :], rtol=0, atol=1e-12)
+
+
+def _ntff_environment():
+    """test_ntff.py:63-78 (NTFFEnvironment): the shipped near-field dofs on get_centred_cube(domain_size, max_edge_len)."""
+    from sucemfem import dolfin_compat as dolfin
+    from sucemfem.Utilities.MeshGenerators import get_centred_cube
+    g = np.load(os.path.join(GOLDEN, 'ntff_order2_unitcube5.npz'))
+    x = np.load(os.path.join(GOLDEN, 'driven_order2_unitcube5.npz'))['x']
+    mesh = get_centred_cube(g['domain_size'], float(g['max_edge_len']))
+    V = dolfin.FunctionSpace(mesh, "Nedelec 1st kind H(curl)", int(g['order']))
+    return V, g, x
+
+
+@pytest.mark.parametrize('kind', ['surface', 'variational'])
+def test_ntff_reference_far_fields(kind):
+    """test_ntff.py:80-110: far field of the shipped near-field solution at six directions against the shipped
+    reference values, with the reference's tolerance rtol=1e-12, atol=1e-7."""
+    from sucemfem.PostProcessing import surface_ntff, variational_ntff
+    V, g, x = _ntff_environment()
+    DUT = (surface_ntff if kind == 'surface' else variational_ntff).NTFF(V)
+    DUT.set_frequency(float(g['freq']))
+    DUT.set_dofs(x)
+    actual = [DUT.calc_pt(th, ph) for th, ph in zip(g[kind + '_theta_deg'], g[kind + '_phi_deg'])]
+    assert np.allclose(actual, g[kind + '_E_ff'], rtol=1e-12, atol=1e-7)
+    if kind == 'variational':       # polynomial forms + interpolation only: reproduced to round-off
+        assert np.abs(np.array(actual) - g[kind + '_E_ff']).max() < 1e-12
+
+
+def test_transform_testing_expression_reference_samples():
+    """test_ntff.py:42-61: real and imaginary parts of the testing expression at the shipped sample points."""
+    from sucemfem.PostProcessing import variational_ntff
+    g = np.load(os.path.join(GOLDEN, 'ntff_order2_unitcube5.npz'))
+    DUT = variational_ntff.TransformTestingExpression()
+    k0, rhat, coords = float(g['interp_k0']), g['interp_rhat'], g['interp_coords']
+    for i, ahat in enumerate(g['interp_ahats']):
+        DUT.set_parms(rhat, ahat, k0)
+        er, ei = DUT.get_expression()
+        assert np.allclose(er(coords), g['interp_vals'][i].real, rtol=1e-10, atol=1e-7)
+        assert np.allclose(ei(coords), g['interp_vals'][i].imag, rtol=1e-10, atol=1e-7)
+        v = np.zeros(3)
+        er.eval(v, coords[0])
+        assert np.allclose(v, g['interp_vals'][i][0].real, rtol=1e-10, atol=1e-7)
+
+
+def test_surface_interpolant_reproduces_member_functions():
+    """Interpolating a function of the space on the boundary returns its boundary dofs (order 1 and 2)."""
+    from sucemfem import dolfin_compat as dolfin
+    from sucemfem.Interpolation import SurfaceInterpolant
+    import torch
+    mesh = dolfin.UnitCube(3, 3, 3)
+    for order in (1, 2):
+        V = dolfin.FunctionSpace(mesh, "Nedelec 1st kind H(curl)", order)
+        SI = SurfaceInterpolant(V)
+        A = np.array([[0.3, -1.0, 0.2], [0.5, 0.1, -0.7], [-0.4, 0.9, 0.6]])
+        lin = (lambda p: np.asarray(p) @ A.T + np.array([1.0, 2.0, 3.0])) if order == 2 else \
+              (lambda p: np.cross(np.array([0.2, -0.5, 0.9]), np.asarray(p)) + np.array([1.0, 2.0, 3.0]))
+        SI.set_interpolant(lambda p: lin(p) * (1 + 2j))
+        x = SI.calculate_interpolation()
+        # the interpolant is a member of the space: its reconstruction on a boundary face equals the function
+        sp = V.device_space
+        markers = torch.zeros(sp.n_facets, dtype=torch.int32, device='cuda')
+        sp.mark_exterior_facets(markers, 1)
+        onb = sp.pec_row_flags(markers, 1).cpu().numpy().astype(bool)
+        assert np.all(x[~onb] == 0) and np.abs(x[onb]).max() > 0
+        SI.set_interpolant_expression(lambda pts: lin(pts), lambda pts: 2 * lin(pts))
+        assert np.allclose(SI.calculate_interpolation(), x, rtol=1e-14, atol=1e-14)
+        from sucemfem.PostProcessing._facets import ExteriorFacets, tri_rule
+        fac = ExteriorFacets(V)
+        pts, _ = tri_rule(2)
+        for sel, X, nrm, pos in fac.groups(pts):
+            E, _ = fac.fields(sel, X, x)
+            n = nrm / np.linalg.norm(nrm, axis=1)[:, None]
+            want = lin(pos.reshape(-1, 3)).reshape(pos.shape) * (1 + 2j)
+            # only the tangential trace is fixed by the boundary dofs
+            tang = lambda F: F - np.einsum('npd,nd->np', F, n)[..., None] * n[:, None, :]
+            assert np.allclose(tang(E), tang(want), rtol=0, atol=1e-12)
