@@ -1,0 +1,91 @@
+"""Host-side mirrors around the path that need no GPU: mesh file formats, matrix IO, the solver classes on scipy
+matrices.  Bodies follow the reference's tests (file:line in the docstrings)."""
+import os
+
+import numpy as np
+import scipy.sparse
+
+
+def test_sparse_identity_and_residual_shapes():
+    """/root/reference/sucemfem/Utilities/tests/test_LinalgSolvers.py:35-100"""
+    from sucemfem.Utilities.LinalgSolvers import solve_sparse_system, calculate_residual, BiCGStabSolver, UMFPACKSolver
+    n = 1000
+    A = scipy.sparse.eye(n, n, format='csr')
+    b = np.random.default_rng(0).random(n)
+    x = solve_sparse_system(A, b)
+    np.testing.assert_array_equal(b, x)
+    x = solve_sparse_system(A, b, preconditioner_type='diagonal')
+    np.testing.assert_array_equal(b, x)
+    for bb, xx in ((b, b.copy()), (b.reshape(1, n), b.copy()), (b.reshape(n, 1), b.copy()),
+                   (b, b.copy().reshape(n, 1)), (b.reshape(1, n), b.copy().reshape(n, 1)),
+                   (b.reshape(n, 1), b.copy().reshape(n, 1))):
+        assert calculate_residual(A, xx, bb) == 0
+    # a non-trivial complex system, logging as in the reference
+    rng = np.random.default_rng(1)
+    B = scipy.sparse.random(200, 200, density=0.05, random_state=2, format='csr') + 10 * scipy.sparse.eye(200)
+    B = (B + 0.3j * scipy.sparse.eye(200)).tocsr()
+    rhs = rng.standard_normal(200) + 1j * rng.standard_normal(200)
+    s = BiCGStabSolver(B, 'diagonal')
+    s.rtol = 1e-12
+    seen = []
+    s.add_user_callback(lambda solver, res: seen.append(res))
+    x = s.solve(rhs)
+    assert np.linalg.norm(B @ x - rhs) <= 1e-10 * np.linalg.norm(rhs)
+    log = s.get_logging_data()
+    assert log['id'][0] == 'init' and 'solve::begin' in log['id'] and log['id'][-1] == 'solve::end' and len(seen) > 4
+    assert np.allclose(UMFPACKSolver(B).solve(rhs), x, rtol=1e-9, atol=1e-12)
+
+
+def test_matrix_io_round_trip(tmp_path):
+    """/root/reference/sucemfem/Utilities/tests/test_MatrixIO.py:40-75"""
+    from sucemfem.Utilities.MatrixIO import load_scipy_matrix_from_mat, save_scipy_matrix_as_mat
+    path = str(tmp_path / 'MatrixIO')
+    A = scipy.sparse.rand(300, 300, density=0.02, format='csr', random_state=3)
+    assert save_scipy_matrix_as_mat(path, 'A', A)
+    L = load_scipy_matrix_from_mat(path, 'A')
+    np.testing.assert_equal(L.shape, A.shape)
+    np.testing.assert_equal(L.data, A.data)
+    np.testing.assert_equal(L.indices, A.indices)
+    np.testing.assert_equal(L.indptr, A.indptr)
+    D = np.random.default_rng(4).random((7, 5))
+    save_scipy_matrix_as_mat(path, 'D', D)
+    np.testing.assert_equal(load_scipy_matrix_from_mat(path, 'D'), D)
+    assert load_scipy_matrix_from_mat(path, 'missing') is None
+
+
+def test_femmesh_reader_and_converters(tmp_path):
+    """/root/reference/sucemfem/Utilities/MeshIO.py:38-117, MeshConverters.py:24-68: BLOCK nodes / tets with 1-based
+    numbering -> mesh with UFC-ordered cells."""
+    from sucemfem.Testing.Meshes import InscribedTet
+    from sucemfem.Utilities import MeshIO, MeshConverters
+    it = InscribedTet()
+    f = tmp_path / 'inscribed.femmesh'
+    rng = np.random.default_rng(5)
+    with open(f, 'w') as fo:
+        fo.write('BLOCK nodes\n%d\n' % len(it.coordinates))
+        for i in rng.permutation(len(it.coordinates)):
+            fo.write('%d %r %r %r\n' % ((i + 1,) + tuple(float(c) for c in it.coordinates[i])))
+        fo.write('ENDBLOCK\nBLOCK tets\n%d\n' % len(it.element_nodes))
+        for i, nodes in enumerate(it.element_nodes):
+            fo.write('%d %d %s\n' % (i + 1, 7, ' '.join(str(int(v) + 1) for v in nodes[::-1])))
+        fo.write('ENDBLOCK\nBLOCK tris\n0\nENDBLOCK\n')
+    rd = MeshIO.FemmeshReader(str(f))
+    try:
+        rd.get_nodes()
+        raise AssertionError('expected the not-read error')
+    except Exception as e:
+        assert 'read_meshfile' in str(e)
+    mesh = MeshIO.femmesh_2_dolfin_mesh(str(f))
+    np.testing.assert_array_equal(mesh.coordinates(), it.coordinates)
+    np.testing.assert_array_equal(mesh.cells(), np.sort(it.element_nodes, axis=1))
+    rd.read_meshfile()
+    assert rd.get_mesh_filename() == 'inscribed.femmesh' and set(rd.get_tet_property_nos()) == {7}
+    lm = MeshConverters.dolfin_mesh_2_listmesh(mesh)
+    m2 = MeshConverters.listmesh_2_dolfin_mesh(lm)
+    np.testing.assert_array_equal(m2.cells(), mesh.cells())
+    np.testing.assert_array_equal(m2.coordinates(), mesh.coordinates())
+
+
+def test_circuit_s11():
+    from sucemfem.PostProcessing.circuit import S11
+    assert S11(50.0, 50.0) == 0 and np.allclose(S11([0.0, 1e30], 50.0), [-1.0, 1.0])
