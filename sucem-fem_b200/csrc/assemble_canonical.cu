@@ -197,11 +197,29 @@ __device__ __forceinline__ void tile_store_wait(int lane) {
   __syncwarp();
 }
 
+// Loads that are issued well ahead of their use must not be consumed early: the compiler likes to hoist the cheap
+// arithmetic that depends on them (address formation, subtraction of a base, byte extraction) right behind the load,
+// where it then waits for the full memory latency.  An empty asm with the register as in/out operand pins the first
+// use to the place where it is written.
+__device__ __forceinline__ void keep_opaque(unsigned& v) { asm volatile("" : "+r"(v)); }
+__device__ __forceinline__ void keep_opaque(int64_t& v) { asm volatile("" : "+l"(v)); }
+__device__ __forceinline__ void keep_opaque(uint4& v) {
+  asm volatile("" : "+r"(v.x), "+r"(v.y), "+r"(v.z), "+r"(v.w));
+}
+
 // pecbits: bit k set <=> dof row (entity, k) is Dirichlet-constrained (loaded at the start of the batch)
 __device__ __forceinline__ unsigned load_pecbits(const CanonArgs& p, int64_t g, bool valid) {
   if (!p.pec || !valid) return 0u;
   const uchar2 f = *reinterpret_cast<const uchar2*>(p.pec + 2 * g);
   return (f.x ? 1u : 0u) | (f.y ? 2u : 0u);
+}
+// the same in two halves: the raw two flag bytes (loaded at the start of the batch) and their decoding (at the use)
+__device__ __forceinline__ unsigned load_pecraw(const CanonArgs& p, int64_t g, bool valid) {
+  if (!p.pec || !valid) return 0u;
+  return *reinterpret_cast<const unsigned short*>(p.pec + 2 * g);
+}
+__device__ __forceinline__ unsigned decode_pecraw(unsigned raw) {
+  return ((raw & 0xffu) ? 1u : 0u) | ((raw >> 8) ? 2u : 0u);
 }
 __device__ __forceinline__ void pec_overwrite(unsigned pecbits, double2* __restrict__ row0, int len, int self) {
 #pragma unroll
@@ -272,11 +290,34 @@ __device__ __forceinline__ EdgeMeta load_edge_meta(const CanonArgs& p, int64_t b
   }
   return m;
 }
+// the same in two halves: the raw loads (i0, i1 still count from the start of the space's incidence array) ...
+__device__ __forceinline__ EdgeMeta load_edge_meta_raw(const CanonArgs& p, int64_t batch, int lane) {
+  EdgeMeta m;
+  const int64_t r = p.r_begin + batch * 16 + (lane >> 1);
+  if (r < p.r_end) {
+    const int64_t g = p.ent_lo + r;
+    m.a = p.ent_rowptr[r];
+    m.a1 = p.ent_rowptr[r + 1];
+    m.i0 = p.inc_ptr[g];
+    m.i1 = p.inc_ptr[g + 1];
+  } else {
+    m.a = m.a1 = 0;
+    m.i0 = p.inc_base + 1; m.i1 = p.inc_base;
+  }
+  return m;
+}
+// ... and the first use, placed by the caller where the loads have had time to arrive
+__device__ __forceinline__ void finish_edge_meta(const CanonArgs& p, EdgeMeta& m) {
+  keep_opaque(m.i0);
+  keep_opaque(m.i1);
+  m.i0 -= p.inc_base;
+  m.i1 -= p.inc_base;
+}
 
 template <bool MASS>
 __device__ __forceinline__ void edge_pass(const CanonArgs& p, const unsigned long long* __restrict__ s_desc,
                                           const unsigned* __restrict__ s_fsel, double2* __restrict__ tile, int lane,
-                                          const EdgeMeta& m, unsigned pecbits, int off, int span, int nsteps,
+                                          const EdgeMeta& m, unsigned pecraw, int off, int span, int nsteps,
                                           Item& cur, uint4& rc1a, uint4& rc1b,
                                           int64_t nf, int64_t nf_end, double* __restrict__ out_first) {
   // cur: this lane's first item (loaded or in flight); rc1: record of its second item; [nf, nf_end): this lane's
@@ -325,6 +366,8 @@ __device__ __forceinline__ void edge_pass(const CanonArgs& p, const unsigned lon
       // last step: the first item of the next pass, and the record of its second item
       if (nf < nf_end) {
         if (nf + 2 < nf_end) { rc2a = rec[2 * (nf + 2)]; rc2b = rec[2 * (nf + 2) + 1]; }
+        keep_opaque(rfa);  // loaded at the start of the pass; first use here
+        keep_opaque(rfb);
         gather_item(p, rfa, rfb, cur);
       }
     }
@@ -393,7 +436,9 @@ __device__ __forceinline__ void edge_pass(const CanonArgs& p, const unsigned lon
   if (valid && h == 0) {
     row0[self_slot] = self[0];
     row0[len + self_slot] = self[1];
-    if (pecbits) pec_overwrite(pecbits, row0, len, self_slot);
+    unsigned pr = pecraw;
+    keep_opaque(pr);  // loaded at the start of the batch; first use here
+    if (pr) pec_overwrite(decode_pecraw(pr), row0, len, self_slot);
   }
   tile_store_issue(tile, out_first, (unsigned)span * 16u, lane);
 }
@@ -423,7 +468,7 @@ __global__ void __launch_bounds__(kThreadsEdges, SFEM_EDGE_CTAS) k_canon_edges(C
   }
 #pragma unroll 1
   for (; b < nb; b += W) {
-    const EdgeMeta mn = load_edge_meta(p, b + W, lane);  // beyond the end: empty
+    EdgeMeta mn = load_edge_meta_raw(p, b + W, lane);  // beyond the end: empty; finished after the S pass
     const bool valid = m.i0 <= m.i1 && m.a1 > m.a;
     // the warp's span: chunks [2 a_first, 2 a_last_end) of the value arrays (lane pairs are consecutive entities)
     const unsigned vmask = __ballot_sync(0xffffffffu, valid);
@@ -435,10 +480,11 @@ __global__ void __launch_bounds__(kThreadsEdges, SFEM_EDGE_CTAS) k_canon_edges(C
     int nsteps = valid ? (int)((m.i1 - m.i0 + 1) >> 1) : 0;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) nsteps = max(nsteps, __shfl_xor_sync(0xffffffffu, nsteps, o));
-    const unsigned pecbits = load_pecbits(p, p.ent_lo + p.r_begin + b * 16 + (lane >> 1), valid);
-    edge_pass<false>(p, s_desc, s_fsel, tile, lane, m, pecbits, off, span, nsteps, cur, rc1a, rc1b, m.i0 + h, m.i1,
+    const unsigned pecraw = load_pecraw(p, p.ent_lo + p.r_begin + b * 16 + (lane >> 1), valid);
+    edge_pass<false>(p, s_desc, s_fsel, tile, lane, m, pecraw, off, span, nsteps, cur, rc1a, rc1b, m.i0 + h, m.i1,
                      p.S + 4 * a_first);
-    edge_pass<true>(p, s_desc, s_fsel, tile, lane, m, pecbits, off, span, nsteps, cur, rc1a, rc1b, mn.i0 + h, mn.i1,
+    finish_edge_meta(p, mn);
+    edge_pass<true>(p, s_desc, s_fsel, tile, lane, m, pecraw, off, span, nsteps, cur, rc1a, rc1b, mn.i0 + h, mn.i1,
                     p.T + 4 * a_first);
     m = mn;
   }
