@@ -186,8 +186,18 @@ __device__ __forceinline__ void tile_store_issue(const double2* tile, double* gd
   __syncwarp();
   if (lane == 0 && bytes > 0) {
     const unsigned src = (unsigned)__cvta_generic_to_shared(tile);
+#ifndef SFEM_NO_STORE_HINT
+    // the value arrays are written once and never read by these kernels: evict-first keeps the 126 MB L2 for the
+    // gathered inputs (records are read again by the T pass, vertex data by every neighbouring entity)
+    unsigned long long policy;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;" ::"l"(gdst), "r"(src),
+                 "r"(bytes), "l"(policy)
+                 : "memory");
+#else
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(src), "r"(bytes)
                  : "memory");
+#endif
     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
   }
 }
