@@ -189,6 +189,13 @@ SFEM_API int sfem_host_job_create(int gdim, int64_t n_vertices, const double* h_
 SFEM_API int sfem_host_job_run(sfem_host_job_t job, int64_t* h_rowptr, int32_t* h_cols, double* h_S, double* h_T,
                       double* h_S0, int n_blocks);
 SFEM_API int sfem_host_job_destroy(sfem_host_job_t job);
+/* Multi-GPU use of a job: every rank creates the job from the same mesh, asks the job's space for its row ranges
+ * (sfem_partition_rows_by_class), sizes its outputs with sfem_space_rows_nnz and streams only the rows of the entities
+ * [ent_lo, ent_hi): h_rowptr int64 [order*(ent_hi-ent_lo)+1] (offsets relative to the range), h_cols / values sized by
+ * the range's nnz.  No communication between the ranks. */
+SFEM_API int sfem_host_job_space(sfem_host_job_t job, sfem_space_t* space);
+SFEM_API int sfem_host_job_run_rows(sfem_host_job_t job, int64_t ent_lo, int64_t ent_hi, int64_t* h_rowptr, int32_t* h_cols,
+                           double* h_S, double* h_T, double* h_S0, int n_blocks);
 /* The same streaming hand-off for a space that already lives on the device (what the sucemfem mirror calls when the
  * MatrixClass is the host matrix, EMDrivenProblem.py:82-87): sfem_space_count_nnz sizes the outputs (one count pass
  * over all rows, cached in the space), sfem_space_assemble_to_host streams the row blocks.  d_* are DEVICE arrays
@@ -197,6 +204,12 @@ SFEM_API int sfem_space_count_nnz(sfem_space_t space, void* stream, int64_t* nnz
 SFEM_API int sfem_space_assemble_to_host(sfem_space_t space, const double* d_eps_r, const double* d_mu_r,
                                 const uint8_t* d_pec_row_flags, int64_t* h_rowptr, int32_t* h_cols, double* h_S,
                                 double* h_T, double* h_S0, int n_blocks, void* stream);
+/* the same for the rows of the entities [ent_lo, ent_hi) only (ent_hi = -1: to the end); outputs relative to the range */
+SFEM_API int sfem_space_rows_nnz(sfem_space_t space, int64_t ent_lo, int64_t ent_hi, void* stream, int64_t* nnz);
+SFEM_API int sfem_space_assemble_rows_to_host(sfem_space_t space, int64_t ent_lo, int64_t ent_hi, const double* d_eps_r,
+                                     const double* d_mu_r, const uint8_t* d_pec_row_flags, int64_t* h_rowptr,
+                                     int32_t* h_cols, double* h_S, double* h_T, double* h_S0, int n_blocks,
+                                     void* stream);
 /* page-locked host memory for the arrays above (cudaHostAlloc / cudaFreeHost) */
 SFEM_API int sfem_host_alloc(size_t bytes, void** out);
 SFEM_API int sfem_host_free(void* p);

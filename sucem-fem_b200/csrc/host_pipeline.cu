@@ -32,19 +32,20 @@ namespace {
 
 inline unsigned grid_for(int64_t n, int bs = 256) { return (unsigned)((n + bs - 1) / bs); }
 
-// block boundaries of (nearly) equal non-zeros + the row-pointer / incidence-pointer values there
-__global__ void k_block_bounds(const int64_t* __restrict__ rowptr_all, const int64_t* __restrict__ inc_ptr, int64_t n,
-                               int nblocks, int64_t* __restrict__ out) {
+// block boundaries of (nearly) equal non-zeros inside the row entities [r_lo, r_hi) + the row-pointer /
+// incidence-pointer values there
+__global__ void k_block_bounds(const int64_t* __restrict__ rowptr_all, const int64_t* __restrict__ inc_ptr, int64_t r_lo,
+                               int64_t r_hi, int nblocks, int64_t* __restrict__ out) {
   int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p > nblocks) return;
-  const __int128 total = rowptr_all[n];
-  const int64_t target = (int64_t)(total * p / nblocks);
-  int64_t lo = 0, hi = n;
+  const __int128 total = rowptr_all[r_hi] - rowptr_all[r_lo];
+  const int64_t target = rowptr_all[r_lo] + (int64_t)(total * p / nblocks);
+  int64_t lo = r_lo, hi = r_hi;
   while (lo < hi) {
     int64_t mid = (lo + hi) >> 1;
     if (rowptr_all[mid] < target) lo = mid + 1; else hi = mid;
   }
-  const int64_t b = p == nblocks ? n : (p == 0 ? 0 : lo);
+  const int64_t b = p == nblocks ? r_hi : (p == 0 ? r_lo : lo);
   out[3 * p] = b;
   out[3 * p + 1] = rowptr_all[b];
   out[3 * p + 2] = inc_ptr[b];
@@ -177,10 +178,50 @@ int sfem_host_job_run(sfem_host_job_t job, int64_t* h_rowptr, int32_t* h_cols, d
                                      n_blocks, job->st);
 }
 
+int sfem_host_job_run_rows(sfem_host_job_t job, int64_t ent_lo, int64_t ent_hi, int64_t* h_rowptr, int32_t* h_cols,
+                           double* h_S, double* h_T, double* h_S0, int n_blocks) {
+  SFEM_CHECK(job, "NULL job");
+  DeviceGuard dg(job->device);
+  return sfem_space_assemble_rows_to_host(job->space, ent_lo, ent_hi, job->d_eps, job->d_mu, job->d_flags, h_rowptr, h_cols,
+                                          h_S, h_T, h_S0, n_blocks, job->st);
+}
+
+int sfem_host_job_space(sfem_host_job_t job, sfem_space_t* out) {
+  SFEM_CHECK(job && out, "NULL argument");
+  *out = job->space;
+  return 0;
+}
+
+int sfem_space_rows_nnz(sfem_space_t sp, int64_t ent_lo, int64_t ent_hi, void* stream, int64_t* nnz) {
+  SFEM_CHECK(sp && nnz, "NULL argument");
+  if (ent_hi < 0) ent_hi = sp->n_ent;
+  SFEM_CHECK(0 <= ent_lo && ent_lo <= ent_hi && ent_hi <= sp->n_ent, "entity range out of bounds");
+  DeviceGuard dg(sp->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  SFEM_TRY(sfem_space_count_nnz(sp, stream, nullptr));
+  int64_t h[2] = {0, 0};
+  SFEM_CUDA(cudaMemcpyAsync(&h[0], sp->rowptr_all + ent_lo, 8, cudaMemcpyDeviceToHost, st));
+  SFEM_CUDA(cudaMemcpyAsync(&h[1], sp->rowptr_all + ent_hi, 8, cudaMemcpyDeviceToHost, st));
+  SFEM_CUDA(cudaStreamSynchronize(st));
+  *nnz = (int64_t)sp->order * sp->order * (h[1] - h[0]);
+  return 0;
+}
+
 int sfem_space_assemble_to_host(sfem_space_t sp, const double* d_eps_r, const double* d_mu_r,
                                 const uint8_t* d_pec_row_flags, int64_t* h_rowptr, int32_t* h_cols, double* h_S,
                                 double* h_T, double* h_S0, int n_blocks, void* stream) {
+  SFEM_CHECK(sp, "NULL space");
+  return sfem_space_assemble_rows_to_host(sp, 0, sp->n_ent, d_eps_r, d_mu_r, d_pec_row_flags, h_rowptr, h_cols, h_S, h_T,
+                                          h_S0, n_blocks, stream);
+}
+
+int sfem_space_assemble_rows_to_host(sfem_space_t sp, int64_t ent_lo, int64_t ent_hi, const double* d_eps_r,
+                                     const double* d_mu_r, const uint8_t* d_pec_row_flags, int64_t* h_rowptr,
+                                     int32_t* h_cols, double* h_S, double* h_T, double* h_S0, int n_blocks,
+                                     void* stream) {
   SFEM_CHECK(sp && h_rowptr, "NULL argument");
+  if (ent_hi < 0) ent_hi = sp->n_ent;
+  SFEM_CHECK(0 <= ent_lo && ent_lo <= ent_hi && ent_hi <= sp->n_ent, "entity range out of bounds");
   SFEM_CHECK(h_S || h_T || h_S0 || h_cols, "nothing to do: pass at least one output array");
   DeviceGuard dg(sp->device);
   cudaStream_t st = (cudaStream_t)stream;
@@ -188,8 +229,9 @@ int sfem_space_assemble_to_host(sfem_space_t sp, const double* d_eps_r, const do
   if (!sp->drain) SFEM_CUDA(cudaStreamCreateWithFlags(&sp->drain, cudaStreamNonBlocking));
   cudaStream_t cp = sp->drain;
   const int q = sp->order;
-  const int64_t n_ent = sp->n_ent;
-  const int64_t nnz = (int64_t)q * q * sp->nnz_ent_all;
+  const int64_t n_ent = ent_hi - ent_lo;
+  int64_t nnz = 0;
+  SFEM_TRY(sfem_space_rows_nnz(sp, ent_lo, ent_hi, stream, &nnz));
   SFEM_CHECK(!h_cols || sp->ndof < (int64_t)2147483647, "column ids exceed int32");
   if (n_blocks <= 0) n_blocks = (int)std::min<int64_t>(256, std::max<int64_t>(1, (nnz + (128ll << 20) - 1) / (128ll << 20)));
   n_blocks = (int)std::min<int64_t>(n_blocks, std::max<int64_t>(n_ent, 1));
@@ -198,7 +240,7 @@ int sfem_space_assemble_to_host(sfem_space_t sp, const double* d_eps_r, const do
   std::vector<int64_t> hb(3 * (n_blocks + 1));
   int64_t* d_b = nullptr;
   SFEM_CUDA(dev_malloc(&d_b, hb.size() * 8, st));
-  k_block_bounds<<<grid_for(n_blocks + 1, 64), 64, 0, st>>>(sp->rowptr_all, sp->inc_ptr, n_ent, n_blocks, d_b);
+  k_block_bounds<<<grid_for(n_blocks + 1, 64), 64, 0, st>>>(sp->rowptr_all, sp->inc_ptr, ent_lo, ent_hi, n_blocks, d_b);
   SFEM_CUDA(cudaMemcpyAsync(hb.data(), d_b, hb.size() * 8, cudaMemcpyDeviceToHost, st));
   SFEM_CUDA(cudaStreamSynchronize(st));
   dev_free(d_b, st);
@@ -208,6 +250,7 @@ int sfem_space_assemble_to_host(sfem_space_t sp, const double* d_eps_r, const do
     max_nnz_ent = std::max(max_nnz_ent, hb[3 * (k + 1) + 1] - hb[3 * k + 1]);
   }
   const int64_t cap = std::max<int64_t>((int64_t)q * q * max_nnz_ent, 1);
+  const int64_t base_ent = hb[1];  // entity-level non-zeros before the range: outputs are relative to the range
 
   struct Stage {
     double *S = nullptr, *T = nullptr, *S0 = nullptr;
@@ -250,7 +293,7 @@ int sfem_space_assemble_to_host(sfem_space_t sp, const double* d_eps_r, const do
     const int64_t lo = hb[3 * k], hi = hb[3 * (k + 1)];
     const int64_t off_ent = hb[3 * k + 1], nnz_ent = hb[3 * (k + 1) + 1] - off_ent;
     const int64_t inc_lo = hb[3 * k + 2], n_inc = hb[3 * (k + 1) + 2] - inc_lo;
-    const int64_t off = (int64_t)q * q * off_ent, nz = (int64_t)q * q * nnz_ent;
+    const int64_t off = (int64_t)q * q * (off_ent - base_ent), nz = (int64_t)q * q * nnz_ent;
     if (hi == lo) continue;
     if (k >= n_stage) RUN_CUDA(cudaStreamWaitEvent(st, s.drained, 0));
     sfem_pattern_s pat;
@@ -284,7 +327,7 @@ int sfem_space_assemble_to_host(sfem_space_t sp, const double* d_eps_r, const do
     if (h_T) RUN_CUDA(cudaMemcpyAsync(h_T + off, s.T, nz * 8, cudaMemcpyDeviceToHost, cp));
     if (h_S0) RUN_CUDA(cudaMemcpyAsync(h_S0 + off, s.S0, nz * 8, cudaMemcpyDeviceToHost, cp));
     if (h_cols) RUN_CUDA(cudaMemcpyAsync(h_cols + off, s.cols, nz * 4, cudaMemcpyDeviceToHost, cp));
-    RUN_CUDA(cudaMemcpyAsync(h_rowptr + q * lo, s.rowptr, (q * (hi - lo) + 1) * 8, cudaMemcpyDeviceToHost, cp));
+    RUN_CUDA(cudaMemcpyAsync(h_rowptr + q * (lo - ent_lo), s.rowptr, (q * (hi - lo) + 1) * 8, cudaMemcpyDeviceToHost, cp));
     RUN_CUDA(cudaEventRecord(s.drained, cp));
   }
 #undef RUN_CUDA

@@ -54,6 +54,10 @@ def _load():
         'sfem_host_job_create': (i32, [i32, i64, vp, i64, vp, i32, vp, vp, i32, vp, C.c_uint32, vp, P(i64), P(i64), P(vp)]),
         'sfem_host_job_run': (i32, [vp, vp, vp, vp, vp, vp, i32]),
         'sfem_host_job_destroy': (i32, [vp]),
+        'sfem_host_job_space': (i32, [vp, P(vp)]),
+        'sfem_host_job_run_rows': (i32, [vp, i64, i64, vp, vp, vp, vp, vp, i32]),
+        'sfem_space_rows_nnz': (i32, [vp, i64, i64, vp, P(i64)]),
+        'sfem_space_assemble_rows_to_host': (i32, [vp, i64, i64, vp, vp, vp, vp, vp, vp, vp, vp, i32, vp]),
         'sfem_space_count_nnz': (i32, [vp, vp, P(i64)]),
         'sfem_space_assemble_to_host': (i32, [vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, vp]),
         'sfem_host_alloc': (i32, [C.c_size_t, P(vp)]),

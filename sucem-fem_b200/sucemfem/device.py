@@ -339,6 +339,46 @@ class HostAssemblyJob(object):
         N.check(N.lib.sfem_host_job_run(self.handle, hp('rowptr'), hp('cols'), hp('S'), hp('T'), hp('S0'), int(n_blocks)))
         return out
 
+    # ---- multi-GPU: every rank creates the job from the same mesh and streams only the rows it owns ----------------
+    def partition_by_class(self, nparts):
+        """(edge_bounds, other_bounds) of the job's space: see DeviceSpace.partition_by_class."""
+        sp = C.c_void_p()
+        N.check(N.lib.sfem_host_job_space(self.handle, C.byref(sp)))
+        eb, ob = (C.c_int64 * (nparts + 1))(), (C.c_int64 * (nparts + 1))()
+        N.check(N.lib.sfem_partition_rows_by_class(sp, nparts, eb, ob, _stream_ptr()))
+        return [int(x) for x in eb], [int(x) for x in ob]
+
+    def rows_nnz(self, ent_lo, ent_hi):
+        sp, nnz = C.c_void_p(), C.c_int64()
+        N.check(N.lib.sfem_host_job_space(self.handle, C.byref(sp)))
+        N.check(N.lib.sfem_space_rows_nnz(sp, int(ent_lo), int(ent_hi), _stream_ptr(), C.byref(nnz)))
+        return nnz.value
+
+    def run_rows(self, ent_lo, ent_hi, want=('cols', 'S', 'T'), out=None, n_blocks=0, order=None):
+        """The rows of the entities [ent_lo, ent_hi) only; rowptr is relative to the range."""
+        out = {} if out is None else out
+        q = self.ndof // self._n_entities() if order is None else order
+        nnz = self.rows_nnz(ent_lo, ent_hi)
+        spec = {'rowptr': (q * (ent_hi - ent_lo) + 1, torch.int64), 'cols': (nnz, torch.int32),
+                'S': (nnz, torch.float64), 'T': (nnz, torch.float64), 'S0': (nnz, torch.float64)}
+        for k in ('rowptr',) + tuple(want):
+            n, dt = spec[k]
+            if k not in out or out[k].numel() != n or out[k].dtype != dt:
+                out[k] = pinned_empty(n, dt)
+        hp = lambda k: C.c_void_p(out[k].data_ptr()) if k in want or k == 'rowptr' else C.c_void_p(0)
+        N.check(N.lib.sfem_host_job_run_rows(self.handle, int(ent_lo), int(ent_hi), hp('rowptr'), hp('cols'), hp('S'),
+                                             hp('T'), hp('S0'), int(n_blocks)))
+        return out
+
+    def _n_entities(self):
+        sp = C.c_void_p()
+        N.check(N.lib.sfem_host_job_space(self.handle, C.byref(sp)))
+        nd, ne, nf, ndc = C.c_int64(), C.c_int64(), C.c_int64(), C.c_int()
+        N.check(N.lib.sfem_space_info(sp, C.byref(nd), C.byref(ne), C.byref(nf), C.byref(ndc)))
+        eb, ob = (C.c_int64 * 2)(), (C.c_int64 * 2)()
+        N.check(N.lib.sfem_partition_rows_by_class(sp, 1, eb, ob, _stream_ptr()))
+        return int(ob[1])
+
     def close(self):
         if self.handle:
             N.lib.sfem_host_job_destroy(self.handle)

@@ -194,6 +194,25 @@ def test_streamed_host_output_equals_device_matrices(dev, name, order):
         for k in ('rowptr', 'cols', 'S', 'T'):
             assert torch.equal(out[k], want[k].cpu()), k
         job.close()
+    # multi-GPU use: a rank streams only its edge range and its face range; outputs are relative to the range
+    job = dev.HostAssemblyJob(co, ce, order, eps, mu, pec='exterior')
+    eb, ob = job.partition_by_class(3)
+    assert (eb, ob) == sp.partition_by_class(3)
+    Ss, cs, rps = [], [], []
+    for b in (eb, ob):
+        for r in range(3):
+            if b[r + 1] == b[r]:
+                continue
+            o = job.run_rows(b[r], b[r + 1], want=('cols', 'S'), n_blocks=2)
+            assert o['S'].numel() == job.rows_nnz(b[r], b[r + 1]) and int(o['rowptr'][0]) == 0
+            Ss.append(o['S'].clone()); cs.append(o['cols'].clone()); rps.append(o['rowptr'].clone())
+    assert torch.equal(torch.cat(Ss), S.cpu()) and torch.equal(torch.cat(cs), cl.cpu())
+    full_rp, offs = [torch.zeros(1, dtype=torch.int64)], 0
+    for t in rps:
+        full_rp.append(t[1:] + offs)
+        offs += int(t[-1])
+    assert torch.equal(torch.cat(full_rp), rp.cpu())
+    job.close()
     # no essential condition, default coefficients, only one matrix requested
     T1 = pat.assemble(N.FORM_MASS)       # a single matrix goes through the single-form kernel
     out = dev.assemble_host(co, ce, order, want=('T',), n_blocks=2)
