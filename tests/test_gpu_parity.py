@@ -203,7 +203,7 @@ def test_streamed_host_output_equals_device_matrices(dev, name, order):
         for r in range(3):
             if b[r + 1] == b[r]:
                 continue
-            o = job.run_rows(b[r], b[r + 1], want=('cols', 'S'), n_blocks=2)
+            o = job.run_rows(b[r], b[r + 1], want=('cols', 'S', 'T'), n_blocks=2)
             assert o['S'].numel() == job.rows_nnz(b[r], b[r + 1]) and int(o['rowptr'][0]) == 0
             Ss.append(o['S'].clone()); cs.append(o['cols'].clone()); rps.append(o['rowptr'].clone())
     assert torch.equal(torch.cat(Ss), S.cpu()) and torch.equal(torch.cat(cs), cl.cpu())
