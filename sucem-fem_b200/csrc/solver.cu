@@ -13,6 +13,7 @@
 //   order 2; the 16 lanes read consecutive 16-byte chunks); complex FMAs; 4 xor-shuffle steps reduce the q sums.
 // BiCGStab is driven from the host side of the library (scalars come back per iteration for the convergence test);
 // vectors are complex (interleaved re, im) and live in caller-owned device arrays plus a pooled work space.
+#include <algorithm>
 #include <cmath>
 #include <complex>
 #include <vector>
@@ -46,17 +47,23 @@ __device__ __forceinline__ double2 cfma(double2 acc, double2 a, double2 b) {  //
 // 13-45 column entities: one or two iterations).  NM is a template parameter so that the value pointers and
 // coefficients live in registers / immediate constant-bank operands.
 template <int Q, int NM, bool CPLX>
-__global__ void __launch_bounds__(256, NM >= 3 ? 3 : 4) k_matvec(MatvecArgs p, const double* __restrict__ x,
+__global__ void __launch_bounds__(256, 3) k_matvec(MatvecArgs p, const double* __restrict__ x,
                                                                   double* __restrict__ y) {
-  const int sub = threadIdx.x & 15;
-  const int64_t r = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 4;
-  const bool valid = r < p.n_rows_ent;
-  double2 acc[Q];
+  const int lane = threadIdx.x & 31, sub = lane & 15;
+  const unsigned half_mask = 0xffffu << (lane & 16);
+  const int64_t n_hw = (int64_t)gridDim.x * (blockDim.x >> 4);  // persistent half-warps, rows r, r + n_hw, ...
+  int64_t r = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 4;
+  int64_t a = 0, a1 = 0;
+  if (r < p.n_rows_ent) { a = p.ent_rowptr[r]; a1 = p.ent_rowptr[r + 1]; }
+  while (r < p.n_rows_ent) {
+    // row pointer of this half-warp's next row, one row ahead
+    const int64_t rn = r + n_hw;
+    int64_t an = 0, a1n = 0;
+    if (rn < p.n_rows_ent) { an = p.ent_rowptr[rn]; a1n = p.ent_rowptr[rn + 1]; }
+    double2 acc[Q];
 #pragma unroll
-  for (int k = 0; k < Q; ++k) acc[k] = make_double2(0.0, 0.0);
-  if (valid) {
-    const int64_t a = p.ent_rowptr[r];
-    const int len = (int)(p.ent_rowptr[r + 1] - a);
+    for (int k = 0; k < Q; ++k) acc[k] = make_double2(0.0, 0.0);
+    const int len = (int)(a1 - a);
     const int64_t base = (int64_t)Q * Q * a;
     for (int s0 = sub; s0 < len; s0 += 32) {
       constexpr int U = 2;
@@ -111,20 +118,21 @@ __global__ void __launch_bounds__(256, NM >= 3 ? 3 : 4) k_matvec(MatvecArgs p, c
         }
       }
     }
-  }
 #pragma unroll
-  for (int k = 0; k < Q; ++k)
+    for (int k = 0; k < Q; ++k)
 #pragma unroll
-    for (int o = 8; o > 0; o >>= 1) {
-      acc[k].x += __shfl_xor_sync(0xffffffffu, acc[k].x, o);
-      if (CPLX) acc[k].y += __shfl_xor_sync(0xffffffffu, acc[k].y, o);
+      for (int o = 8; o > 0; o >>= 1) {
+        acc[k].x += __shfl_xor_sync(half_mask, acc[k].x, o);
+        if (CPLX) acc[k].y += __shfl_xor_sync(half_mask, acc[k].y, o);
+      }
+    if (sub == 0) {
+#pragma unroll
+      for (int k = 0; k < Q; ++k) {
+        if (CPLX) reinterpret_cast<double2*>(y)[Q * r + k] = acc[k];
+        else y[Q * r + k] = acc[k].x;
+      }
     }
-  if (valid && sub == 0) {
-#pragma unroll
-    for (int k = 0; k < Q; ++k) {
-      if (CPLX) reinterpret_cast<double2*>(y)[Q * r + k] = acc[k];
-      else y[Q * r + k] = acc[k].x;
-    }
+    r = rn; a = an; a1 = a1n;
   }
 }
 
@@ -288,7 +296,10 @@ void launch_matvec_nm(const MatvecArgs& a, unsigned grid, const double* x, doubl
 
 int launch_matvec(const sfem_pattern_s* pat, const MatvecArgs& a, bool cplx, const double* x, double* y, cudaStream_t st) {
   if (pat->n_rows_ent == 0) return 0;
-  const unsigned grid = grid_for(pat->n_rows_ent * 16);
+  int num_sms = 148;
+  SFEM_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, pat->device));
+  // persistent: as many CTAs as are resident (3 per SM by the kernel's launch bounds), at most one row per half-warp
+  const unsigned grid = (unsigned)std::min<int64_t>((int64_t)num_sms * 3, grid_for(pat->n_rows_ent * 16));
   const int q = pat->space->order;
   if (q == 2 && cplx) launch_matvec_nm<2, true>(a, grid, x, y, st);
   else if (q == 2) launch_matvec_nm<2, false>(a, grid, x, y, st);
