@@ -266,7 +266,7 @@ def main():
         torch.cuda.empty_cache()
         N.check(N.lib.sfem_release_cached_memory())
         try:
-            e2e = e2e_run(n, min(K, 3), rank, world)
+            e2e = e2e_run(n, min(K, 5), rank, world)
         except Exception as e:  # noqa: BLE001   (e.g. not enough page-lockable host memory for this rank's share)
             e2e = {"error": repr(e)[:300]}
         if world > 1:            # whole-job rate: all tets / the slowest rank's step
