@@ -71,6 +71,40 @@ def test_resonant_cavity_driver(order, expected):
     assert eigs_v.shape == (10, ep.get_global_dimension())
 
 
+@pytest.mark.parametrize('order,pec,expected', [
+    (1, True, [0.99027, 0.99882, 1.42117, 1.95559, 1.95692]),
+    (2, True, [0.99997, 1.00003, 1.41447, 2.00012, 2.00012]),
+    (1, False, [1.42167, 2.214, 2.25022, 2.86333]),
+    (2, False, [1.41448, 2.23712, 2.23838, 2.83564])])
+def test_2d_waveguide_driver(order, pec, expected):
+    """/root/reference/examples/2D_waveguide/eigenmode/driver.py:38-72 (TE: PEC walls) and TM_driver.py (no essential
+    condition) = BASELINE config 2 at the orders this build provides: UnitSquare(5,5) triangles, cutoff wavenumbers
+    k/pi against the regression anchors of SURVEY.md 8.3 and, loosely, against the analytic values."""
+    from sucemfem import dolfin_compat as dol
+    from sucemfem.ProblemConfigurations.EMVectorWaveEigenproblem import EigenProblem, DefaultEigenSolver
+    from sucemfem.BoundaryConditions import PECWallsBoundaryCondition
+    mesh = dol.UnitSquare(5, 5)
+    ep = EigenProblem()
+    ep.set_mesh(mesh)
+    ep.set_basis_order(order)
+    if pec:
+        pec_walls = PECWallsBoundaryCondition()
+        pec_walls.init_with_mesh(mesh)
+        ep.set_boundary_conditions(pec_walls)
+    ep.init_problem()
+    assert ep.get_global_dimension() == {1: 85, 2: 270}[order]
+    es = DefaultEigenSolver()
+    es.set_eigenproblem(ep)
+    es.set_sigma(1.5)
+    eigs_w, eigs_v = es.solve_problem(10)
+    res = np.sqrt(np.array(sorted(w for w in eigs_w.real if w > 0.5))) / np.pi
+    if pec:     # the identity rows of the PEC dofs put spurious modes at lambda = 1 (k/pi = 0.3183): drop them
+        res = res[np.abs(res - 1 / np.pi) > 1e-6]
+    assert np.allclose(res[:len(expected)], expected, atol=2e-5)
+    analytic = [1, 1, np.sqrt(2), 2, 2] if pec else [np.sqrt(2), np.sqrt(5), np.sqrt(5), np.sqrt(8)]
+    assert np.allclose(res[:len(analytic)], analytic, rtol=0.03)
+
+
 def test_cavity_eigenvalues_match_oracle_matrices_to_1e10():
     """north_star: resonant-cavity eigenvalues computed from both matrix sets must agree to 1e-10 (relative)."""
     import scipy.linalg as sla
