@@ -146,12 +146,18 @@ int sfem_host_job_create(int gdim, int64_t n_vertices, const double* h_coords, i
     } else {
       // PECWallsBoundaryCondition: a marker function that is `region` on every exterior facet and differs elsewhere
       JOB_CUDA(cudaMemsetAsync(d_markers, pec_region == 0 ? 0xff : 0, std::max<int64_t>(sp->n_facets, 1) * 4, st));
-      if ((rc = sfem_mark_exterior_facets(sp, d_markers, pec_region, stream)) != 0) return fail(rc);
+      rc = sfem_mark_exterior_facets(sp, d_markers, pec_region, stream);
     }
-    JOB_CUDA(dev_malloc(&job->d_flags, std::max<int64_t>(sp->ndof, 1), st));
-    JOB_CUDA(cudaMemsetAsync(job->d_flags, 0, std::max<int64_t>(sp->ndof, 1), st));
-    if ((rc = sfem_pec_row_flags(sp, d_markers, pec_region, job->d_flags, stream)) != 0) return fail(rc);
+    if (rc == 0 && dev_malloc(&job->d_flags, std::max<int64_t>(sp->ndof, 1), st) != cudaSuccess) {
+      set_error("out of device memory for the PEC row flags");
+      rc = 1;
+    }
+    if (rc == 0) {
+      cudaMemsetAsync(job->d_flags, 0, std::max<int64_t>(sp->ndof, 1), st);
+      rc = sfem_pec_row_flags(sp, d_markers, pec_region, job->d_flags, stream);
+    }
     dev_free(d_markers, st);
+    if (rc != 0) return fail(rc);
   }
   if ((rc = sfem_space_count_nnz(sp, stream, nnz)) != 0) return fail(rc);
 #undef JOB_CUDA

@@ -219,6 +219,23 @@ def test_streamed_host_output_equals_device_matrices(dev, name, order):
     assert torch.equal(out['T'], T1.cpu()) and torch.equal(out['rowptr'], rp.cpu())
 
 
+def test_host_job_rejects_bad_input(dev):
+    """Error behaviour of the host-buffer entry points: message through sfem_last_error, no partial handle."""
+    from sucemfem import _native as N
+    co, ce = meshes.unit_cube(2)
+    bad = ce.copy()
+    bad[3, [0, 1]] = bad[3, [1, 0]]                      # not in UFC (ascending) order
+    with pytest.raises(N.NativeError, match='ascending'):
+        dev.HostAssemblyJob(co, bad, 2)
+    with pytest.raises(N.NativeError, match='order 1 and 2'):
+        dev.HostAssemblyJob(co, ce, 3)
+    job = dev.HostAssemblyJob(co, ce, 1)
+    with pytest.raises(N.NativeError, match='out of bounds'):
+        job.run_rows(5, 10 ** 9, order=1)
+    job.close()
+    job.close()                                          # idempotent
+
+
 def test_material_expansion(dev):
     import torch
     reg = torch.tensor([0, 1000, 1001, 1000, 0], dtype=torch.int32, device='cuda')
