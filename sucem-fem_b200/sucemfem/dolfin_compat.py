@@ -25,7 +25,11 @@ class Mesh(object):
     """dolfin.Mesh: coordinates()/cells() are host arrays; device copies are made when a FunctionSpace is built."""
 
     def __init__(self, filename=None, coordinates=None, cells=None):
-        if filename is not None:
+        if filename is not None and str(filename).lower().endswith(('.msh', '.gmsh')):
+            from .Utilities import GmshIO   # gmsh file: converted on the fly (dolfin-convert's conventions)
+            gm = GmshIO.read_gmsh(filename)
+            coordinates, cells = gm.coordinates, gm.cells
+        elif filename is not None:
             coordinates, cells = _read_dolfin_xml(filename)
         if coordinates is None:
             coordinates, cells = np.zeros((0, 3)), np.zeros((0, 4), np.int32)

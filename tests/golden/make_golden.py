@@ -15,6 +15,8 @@ scalars, loaded with encoding='latin1':
   6    functional_tests/data/meshes/rectangular_prism.xml + rectangular_prism_facet_region.xml (gmsh mesh of the
        1 x 0.5 x 0.25 cavity and its PEC facet markers, indexed by DOLFIN's face numbering;
        test: functional_tests/test_EigenProblems.py:69-134)
+  f3   gmsh .msh files shipped together with their dolfin-convert XML output (sandbox/interior_integration/sample_mesh,
+       sandbox/eig/{lee_mittra92_fig6b,lee_mittra92_fig6c,rect-white}, sandbox/patch/patch) -> gmsh_pairs.npz
 """
 import os
 import pickle
@@ -97,6 +99,43 @@ def prism():
                         facet_markers=mk, facet_dim=int(mf.get('dim')))
 
 
+
+def gmsh_pairs():
+    """.msh files the reference ships TOGETHER WITH their dolfin-convert output (same mesh revision): the .msh text
+    is the reader's input, the XML contents are the expected output."""
+    import xml.etree.ElementTree as ET
+    R = '/root/reference/'
+    out = {}
+    for name, base in (('sample_mesh', 'sandbox/interior_integration/sample_mesh'),
+                       ('lee_mittra92_fig6c', 'sandbox/eig/lee_mittra92_fig6c'),
+                       ('lee_mittra92_fig6b', 'sandbox/eig/lee_mittra92_fig6b'),
+                       ('rect_white', 'sandbox/eig/rect-white'),
+                       ('patch', 'sandbox/patch/patch')):
+        with open(R + base + '.msh', 'rb') as f:
+            out[name + '__msh'] = np.frombuffer(f.read(), np.uint8)
+        mesh = ET.parse(R + base + '.xml').getroot().find('mesh')
+        dim = int(mesh.get('dim'))
+        vs, cs = mesh.find('vertices'), mesh.find('cells')
+        co = np.zeros((int(vs.get('size')), dim))
+        for v in vs:
+            co[int(v.get('index'))] = [float(v.get(a)) for a in 'xyz'[:dim]]
+        ce = np.zeros((int(cs.get('size')), dim + 1), np.int32)
+        for c in cs:
+            ce[int(c.get('index'))] = [int(c.get('v%d' % i)) for i in range(dim + 1)]
+        out[name + '__coordinates'], out[name + '__cells'] = co, ce
+        for kind in ('physical_region', 'facet_region'):
+            p = R + base + '_' + kind + '.xml'
+            if os.path.exists(p):
+                mf = ET.parse(p).getroot().find('meshfunction')
+                a = np.zeros(int(mf.get('size')), np.uint32)
+                for e in mf:
+                    a[int(e.get('index'))] = int(e.get('value'))
+                assert int(mf.get('dim')) == (dim if kind == 'physical_region' else dim - 1)
+                out[name + '__' + kind] = a
+    np.savez_compressed(os.path.join(HERE, 'gmsh_pairs.npz'), **out)
+
+
 if __name__ == '__main__':
     prism()
+    gmsh_pairs()
     main()
