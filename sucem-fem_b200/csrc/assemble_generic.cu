@@ -274,16 +274,31 @@ k_values_generic(PatView pv, const double* __restrict__ geo, const double* __res
   }
 }
 
-// rows that can carry ABC contributions: row entities with an incident cell that has an exterior facet
+// rows that can carry ABC contributions: row entities that LIE ON an exterior facet (the tangential trace of a basis
+// function vanishes on every facet that does not contain its entity, so all other rows of S_0 are zero).
+// inc_loc = local entity of the row entity in the incident cell (tets: edges 0-5, faces 6-9; triangles: edges 0-2,
+// interior 3); cell_extmask bit lf = local facet lf (opposite vertex lf) is exterior.
+template <int DIM>
 __global__ void k_abc_row_flags(const int64_t* __restrict__ inc_ptr, const int32_t* __restrict__ inc_cell,
-                                const uint8_t* __restrict__ cell_extmask, int64_t ent_lo, int64_t n_rows,
-                                uint8_t* __restrict__ flags) {
+                                const uint8_t* __restrict__ inc_loc, const uint8_t* __restrict__ cell_extmask,
+                                int64_t ent_lo, int64_t n_rows, uint8_t* __restrict__ flags) {
   const int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (r >= n_rows) return;
   const int64_t g = ent_lo + r;
   uint8_t f = 0;
-  for (int64_t i = inc_ptr[g]; i < inc_ptr[g + 1]; ++i)
-    if (cell_extmask[inc_cell[i]]) f = 1;
+  for (int64_t i = inc_ptr[g]; i < inc_ptr[g + 1]; ++i) {
+    const unsigned m = cell_extmask[inc_cell[i]];
+    if (!m) continue;
+    const int loc = inc_loc[i];
+    unsigned on;  // local facets that contain the local entity
+    if (DIM == 3) {
+      // tet edge (a,b) lies on the faces opposite the other two vertices: e0=(2,3) e1=(1,3) e2=(1,2) e3=(0,3) e4=(0,2) e5=(0,1)
+      on = loc < 6 ? ((0xCA6953u >> (4 * loc)) & 15u) : (1u << (loc - 6));
+    } else {
+      on = loc < 3 ? (1u << loc) : 0u;
+    }
+    if (m & on) f = 1;
+  }
   flags[r] = f;
 }
 
@@ -315,8 +330,12 @@ static int build_abc_rows(sfem_pattern_s* pat, cudaStream_t st) {
   SFEM_CUDA(dev_malloc(&flags, std::max<int64_t>(n, 1), st));
   SFEM_CUDA(dev_malloc(&d_count, 8, st));
   SFEM_CUDA(dev_malloc(&pat->abc_rows, std::max<int64_t>(n, 1) * 8, st));
-  k_abc_row_flags<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(sp->inc_ptr, sp->inc_cell, sp->cell_extmask,
-                                                            pat->ent_lo, n, flags);
+  if (sp->mesh->gdim == 3)
+    k_abc_row_flags<3><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(sp->inc_ptr, sp->inc_cell, sp->inc_loc,
+                                                                 sp->cell_extmask, pat->ent_lo, n, flags);
+  else
+    k_abc_row_flags<2><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(sp->inc_ptr, sp->inc_cell, sp->inc_loc,
+                                                                 sp->cell_extmask, pat->ent_lo, n, flags);
   cub::CountingInputIterator<int64_t> it(0);
   size_t tb = 0;
   SFEM_CUDA(cub::DeviceSelect::Flagged(nullptr, tb, it, flags, pat->abc_rows, d_count, (int)n, st));
