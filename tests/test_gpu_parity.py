@@ -34,6 +34,16 @@ def _meshes():
     out['square5_jitter'] = (co + 0.02 * rng.standard_normal(co.shape), ce)
     co, ce = meshes.centred_cube(0.0749, 0.05)
     out['centred'] = (co, ce)
+    # degenerate inputs: one cell; two cells that share nothing, with vertex ids no cell uses in between; an open
+    # fan of tets around one edge and the closed ring (an interior edge whose row holds every entity of the mesh)
+    out['single_tet'] = (rng.standard_normal((4, 3)), np.array([[0, 1, 2, 3]], np.int32))
+    out['single_tri'] = (rng.standard_normal((3, 2)), np.array([[0, 1, 2]], np.int32))
+    out['two_tets_apart'] = (rng.standard_normal((12, 3)), np.array([[0, 2, 5, 6], [8, 9, 10, 11]], np.int32))
+    ring = np.array([[np.cos(t), np.sin(t), 0.1 * np.sin(3 * t)] for t in 2 * np.pi * np.arange(5) / 5])
+    co = np.vstack([[0, 0, -1.0], [0, 0, 1.0], ring]) + 0.03 * rng.standard_normal((7, 3))
+    fan = np.array([[0, 1, 2 + k, 3 + k] for k in range(4)], np.int32)
+    out['tet_fan_open'] = (co, fan)
+    out['tet_ring_closed'] = (co, np.vstack([fan, [[0, 1, 2, 6]]]).astype(np.int32))
     return out
 
 
