@@ -38,38 +38,45 @@ def my_block(bounds, rank=None):
     return bounds[rank], bounds[rank + 1]
 
 
+def _all_gather_var(t, counts, group=None):
+    """All-gather of blocks of different lengths straight into ONE output array (rank order).  NCCL: torch issues one
+    grouped broadcast per rank into the output views (no padding, no staging copies); gloo (CPU tests) only knows
+    equal sizes, so blocks are padded to the longest one and compacted afterwards."""
+    world = dist.get_world_size(group)
+    out = torch.empty(int(sum(counts)), dtype=t.dtype, device=t.device)
+    views = list(out.split([int(c) for c in counts]))
+    if dist.get_backend(group) == 'nccl' or len(set(int(c) for c in counts)) == 1:
+        dist.all_gather(views, t.contiguous(), group=group)
+        return out
+    n = int(max(counts))
+    pad = torch.zeros(n, dtype=t.dtype, device=t.device)
+    pad[:t.numel()] = t
+    bufs = [torch.empty(n, dtype=t.dtype, device=t.device) for _ in range(world)]
+    dist.all_gather(bufs, pad, group=group)
+    for p in range(world):
+        views[p].copy_(bufs[p][:int(counts[p])])
+    return out
+
+
 def gather_csr_blocks(rowptr_block, cols_block, values_block, group=None):
     """All-gather row blocks (block-relative rowptr [nrows_p+1], cols [nnz_p], values [nnz_p]) into the full CSR on
-    every rank.  Blocks are padded to the largest block for the fixed-size all_gather."""
-    world = dist.get_world_size(group)
-    dev = values_block.device
-    sizes = torch.tensor([rowptr_block.numel() - 1, values_block.numel()], dtype=torch.int64, device=dev)
-    all_sizes = [torch.zeros_like(sizes) for _ in range(world)]
+    every rank (rank order = row order).  values_block may also be a list / tuple of value arrays sharing the pattern
+    (S, T, S_0): the pattern is then gathered once and a list of value arrays is returned."""
+    many = isinstance(values_block, (list, tuple))
+    vals_in = list(values_block) if many else [values_block]
+    dev = vals_in[0].device
+    sizes = torch.tensor([rowptr_block.numel() - 1, cols_block.numel()], dtype=torch.int64, device=dev)
+    all_sizes = [torch.zeros_like(sizes) for _ in range(dist.get_world_size(group))]
     dist.all_gather(all_sizes, sizes, group=group)
     all_sizes = torch.stack(all_sizes).cpu()
-    max_rows, max_nnz = int(all_sizes[:, 0].max()), int(all_sizes[:, 1].max())
-
-    def padded(t, n):
-        out = torch.zeros(n, dtype=t.dtype, device=dev)
-        out[:t.numel()] = t
-        return out
-
-    def gather(t, n):
-        bufs = [torch.zeros(n, dtype=t.dtype, device=dev) for _ in range(world)]
-        dist.all_gather(bufs, padded(t, n), group=group)
-        return bufs
-
-    rps = gather(rowptr_block[1:] - rowptr_block[0], max_rows)   # row end offsets, block-relative
-    cls = gather(cols_block, max_nnz)
-    vls = gather(values_block, max_nnz)
-    rowptr, cols, vals, off = [torch.zeros(1, dtype=rowptr_block.dtype, device=dev)], [], [], 0
-    for p in range(world):
-        nr, nz = int(all_sizes[p, 0]), int(all_sizes[p, 1])
-        rowptr.append(rps[p][:nr] + off)
-        cols.append(cls[p][:nz])
-        vals.append(vls[p][:nz])
-        off += nz
-    return torch.cat(rowptr), torch.cat(cols), torch.cat(vals)
+    n_rows, n_nnz = [int(x) for x in all_sizes[:, 0]], [int(x) for x in all_sizes[:, 1]]
+    ends = _all_gather_var(rowptr_block[1:] - rowptr_block[0], n_rows, group)    # row end offsets, block-relative
+    nnz_before = torch.tensor([0] + n_nnz[:-1], dtype=torch.int64).cumsum(0).to(device=dev, dtype=ends.dtype)
+    ends += torch.repeat_interleave(nnz_before, torch.tensor(n_rows, device=dev))
+    rowptr = torch.cat([torch.zeros(1, dtype=ends.dtype, device=dev), ends])
+    cols = _all_gather_var(cols_block, n_nnz, group)
+    vals = [_all_gather_var(v, n_nnz, group) for v in vals_in]
+    return rowptr, cols, (vals if many else vals[0])
 
 
 def gather_csr_two_class(edge_block, other_block, group=None):
@@ -77,4 +84,7 @@ def gather_csr_two_class(edge_block, other_block, group=None):
     rows and face rows.  Global row order is all edge rows (rank order) followed by all face rows (rank order)."""
     rp_e, cl_e, vl_e = gather_csr_blocks(*edge_block, group=group)
     rp_o, cl_o, vl_o = gather_csr_blocks(*other_block, group=group)
-    return torch.cat([rp_e, rp_o[1:] + rp_e[-1]]), torch.cat([cl_e, cl_o]), torch.cat([vl_e, vl_o])
+    rowptr, cols = torch.cat([rp_e, rp_o[1:] + rp_e[-1]]), torch.cat([cl_e, cl_o])
+    if isinstance(vl_e, list):
+        return rowptr, cols, [torch.cat([a, b]) for a, b in zip(vl_e, vl_o)]
+    return rowptr, cols, torch.cat([vl_e, vl_o])

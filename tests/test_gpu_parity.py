@@ -36,9 +36,13 @@ def _meshes():
     out['centred'] = (co, ce)
     # degenerate inputs: one cell; two cells that share nothing, with vertex ids no cell uses in between; an open
     # fan of tets around one edge and the closed ring (an interior edge whose row holds every entity of the mesh)
-    out['single_tet'] = (rng.standard_normal((4, 3)), np.array([[0, 1, 2, 3]], np.int32))
-    out['single_tri'] = (rng.standard_normal((3, 2)), np.array([[0, 1, 2]], np.int32))
-    out['two_tets_apart'] = (rng.standard_normal((12, 3)), np.array([[0, 2, 5, 6], [8, 9, 10, 11]], np.int32))
+    out['single_tet'] = (np.array([[0, 0, 0], [1, .1, 0], [.2, 1, 0], [.1, .3, 1.0]]), np.array([[0, 1, 2, 3]], np.int32))
+    out['single_tri'] = (np.array([[0, 0], [1, .2], [.3, 1.0]]), np.array([[0, 1, 2]], np.int32))
+    unit = np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0], [0, 0, 1.0]])
+    co = rng.standard_normal((12, 3))                       # vertices 1, 3, 4, 7 belong to no cell
+    co[[0, 2, 5, 6]] = 0.7 * unit + 0.05 * rng.standard_normal((4, 3))
+    co[[8, 9, 10, 11]] = 3.0 + 1.3 * unit[[1, 0, 2, 3]] + 0.05 * rng.standard_normal((4, 3))   # detJ < 0
+    out['two_tets_apart'] = (co, np.array([[0, 2, 5, 6], [8, 9, 10, 11]], np.int32))
     ring = np.array([[np.cos(t), np.sin(t), 0.1 * np.sin(3 * t)] for t in 2 * np.pi * np.arange(5) / 5])
     co = np.vstack([[0, 0, -1.0], [0, 0, 1.0], ring]) + 0.03 * rng.standard_normal((7, 3))
     fan = np.array([[0, 1, 2 + k, 3 + k] for k in range(4)], np.int32)
