@@ -38,12 +38,12 @@ def my_block(bounds, rank=None):
     return bounds[rank], bounds[rank + 1]
 
 
-def _all_gather_var(t, counts, group=None):
-    """All-gather of blocks of different lengths straight into ONE output array (rank order).  NCCL: torch issues one
-    grouped broadcast per rank into the output views (no padding, no staging copies); gloo (CPU tests) only knows
-    equal sizes, so blocks are padded to the longest one and compacted afterwards."""
+def _all_gather_var(t, counts, out, group=None):
+    """All-gather of blocks of different lengths straight into `out` (rank order, sum(counts) elements, usually a
+    slice of the final array).  NCCL: torch issues one grouped broadcast per rank into the output views (no padding,
+    no staging copies); gloo (CPU tests) only knows equal sizes, so blocks are padded to the longest one and
+    compacted afterwards."""
     world = dist.get_world_size(group)
-    out = torch.empty(int(sum(counts)), dtype=t.dtype, device=t.device)
     views = list(out.split([int(c) for c in counts]))
     if dist.get_backend(group) == 'nccl' or len(set(int(c) for c in counts)) == 1:
         dist.all_gather(views, t.contiguous(), group=group)
@@ -58,33 +58,48 @@ def _all_gather_var(t, counts, group=None):
     return out
 
 
-def gather_csr_blocks(rowptr_block, cols_block, values_block, group=None):
-    """All-gather row blocks (block-relative rowptr [nrows_p+1], cols [nnz_p], values [nnz_p]) into the full CSR on
-    every rank (rank order = row order).  values_block may also be a list / tuple of value arrays sharing the pattern
-    (S, T, S_0): the pattern is then gathered once and a list of value arrays is returned."""
-    many = isinstance(values_block, (list, tuple))
-    vals_in = list(values_block) if many else [values_block]
-    dev = vals_in[0].device
-    sizes = torch.tensor([rowptr_block.numel() - 1, cols_block.numel()], dtype=torch.int64, device=dev)
-    all_sizes = [torch.zeros_like(sizes) for _ in range(dist.get_world_size(group))]
+def gather_csr_classes(blocks, group=None):
+    """Full CSR on every rank from row blocks of several row CLASSES.  blocks = [(rowptr, cols, values), ...], one
+    entry per class, each this rank's block of that class: block-relative rowptr [nrows+1], cols [nnz], values [nnz]
+    or a list of value arrays sharing the pattern (S, T, S_0).  Global row order = class 0 (rank order), class 1
+    (rank order), ...  One small all_gather of the block sizes, then every array is gathered once, directly into its
+    slice of the final array."""
+    world = dist.get_world_size(group)
+    many = isinstance(blocks[0][2], (list, tuple))
+    vals_in = [list(b[2]) if many else [b[2]] for b in blocks]
+    dev = vals_in[0][0].device
+    sizes = torch.tensor([x for b in blocks for x in (b[0].numel() - 1, b[1].numel())], dtype=torch.int64, device=dev)
+    all_sizes = [torch.zeros_like(sizes) for _ in range(world)]
     dist.all_gather(all_sizes, sizes, group=group)
-    all_sizes = torch.stack(all_sizes).cpu()
-    n_rows, n_nnz = [int(x) for x in all_sizes[:, 0]], [int(x) for x in all_sizes[:, 1]]
-    ends = _all_gather_var(rowptr_block[1:] - rowptr_block[0], n_rows, group)    # row end offsets, block-relative
-    nnz_before = torch.tensor([0] + n_nnz[:-1], dtype=torch.int64).cumsum(0).to(device=dev, dtype=ends.dtype)
-    ends += torch.repeat_interleave(nnz_before, torch.tensor(n_rows, device=dev))
-    rowptr = torch.cat([torch.zeros(1, dtype=ends.dtype, device=dev), ends])
-    cols = _all_gather_var(cols_block, n_nnz, group)
-    vals = [_all_gather_var(v, n_nnz, group) for v in vals_in]
+    all_sizes = torch.stack(all_sizes).cpu().reshape(world, len(blocks), 2)
+    n_rows = [[int(x) for x in all_sizes[:, k, 0]] for k in range(len(blocks))]
+    n_nnz = [[int(x) for x in all_sizes[:, k, 1]] for k in range(len(blocks))]
+    tot_rows, tot_nnz = sum(map(sum, n_rows)), sum(map(sum, n_nnz))
+    rdt = blocks[0][0].dtype
+    rowptr = torch.empty(tot_rows + 1, dtype=rdt, device=dev)
+    rowptr[0] = 0
+    cols = torch.empty(tot_nnz, dtype=blocks[0][1].dtype, device=dev)
+    vals = [torch.empty(tot_nnz, dtype=v.dtype, device=dev) for v in vals_in[0]]
+    r0 = z0 = 0
+    for k, (rp, cl, _) in enumerate(blocks):
+        nr, nz = sum(n_rows[k]), sum(n_nnz[k])
+        ends = _all_gather_var(rp[1:] - rp[0], n_rows[k], rowptr[1 + r0:1 + r0 + nr], group)   # block-relative ends
+        before = torch.tensor([z0] + n_nnz[k][:-1], dtype=torch.int64).cumsum(0).to(device=dev, dtype=rdt)
+        ends += torch.repeat_interleave(before, torch.tensor(n_rows[k], device=dev))
+        _all_gather_var(cl, n_nnz[k], cols[z0:z0 + nz], group)
+        for v_out, v_in in zip(vals, vals_in[k]):
+            _all_gather_var(v_in, n_nnz[k], v_out[z0:z0 + nz], group)
+        r0, z0 = r0 + nr, z0 + nz
     return rowptr, cols, (vals if many else vals[0])
+
+
+def gather_csr_blocks(rowptr_block, cols_block, values_block, group=None):
+    """All-gather row blocks (block-relative rowptr [nrows_p+1], cols [nnz_p], values [nnz_p] or a list of value
+    arrays) of ONE contiguous range per rank into the full CSR on every rank (rank order = row order)."""
+    return gather_csr_classes([(rowptr_block, cols_block, values_block)], group=group)
 
 
 def gather_csr_two_class(edge_block, other_block, group=None):
     """Full CSR from the two-class partition: edge_block / other_block = (rowptr, cols, values) of this rank's edge
     rows and face rows.  Global row order is all edge rows (rank order) followed by all face rows (rank order)."""
-    rp_e, cl_e, vl_e = gather_csr_blocks(*edge_block, group=group)
-    rp_o, cl_o, vl_o = gather_csr_blocks(*other_block, group=group)
-    rowptr, cols = torch.cat([rp_e, rp_o[1:] + rp_e[-1]]), torch.cat([cl_e, cl_o])
-    if isinstance(vl_e, list):
-        return rowptr, cols, [torch.cat([a, b]) for a, b in zip(vl_e, vl_o)]
-    return rowptr, cols, torch.cat([vl_e, vl_o])
+    return gather_csr_classes([edge_block, other_block], group=group)
