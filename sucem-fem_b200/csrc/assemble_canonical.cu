@@ -382,6 +382,8 @@ __device__ __forceinline__ void edge_pass(const CanonArgs& p, const unsigned lon
       }
     }
     __syncwarp();
+    // 0 / 1 weights of the two possible carries (exact: x * 1 + y = x + y, x * 0 + y = y for finite x)
+    const double mg = (has_prev && h) ? 1.0 : 0.0, ms = (has_prev && !h) ? 1.0 : 0.0;
 #define SFEM_RING_ROW(K, FN)                                                                       \
     {                                                                                              \
       double2 n3 = make_double2(0.0, 0.0), n1 = n3, n8 = n3;                                       \
@@ -393,22 +395,20 @@ __device__ __forceinline__ void edge_pass(const CanonArgs& p, const unsigned lon
       }                                                                                            \
       /* hand the next-side blocks to the partner, which owns the next cell of the ring */         \
       const double2 g3 = shfl_xor1(n3), g1 = shfl_xor1(n1), g8 = shfl_xor1(n8);                    \
-      const double2 c4 = make_double2(sel_flag(h, g3.x, saved[K][0].x), sel_flag(h, g3.y, saved[K][0].y)); \
-      const double2 c2 = make_double2(sel_flag(h, g1.x, saved[K][1].x), sel_flag(h, g1.y, saved[K][1].y)); \
-      const double2 c9 = make_double2(sel_flag(h, g8.x, saved[K][2].x), sel_flag(h, g8.y, saved[K][2].y)); \
-      saved[K][0] = g3; saved[K][1] = g1; saved[K][2] = g8;                                        \
       if (active) {                                                                                \
         double2* row = row0 + K * len;                                                             \
         double2 r;                                                                                 \
         r = fix_columns<5>(fx, o[10], o[11]); self[K].x += r.x; self[K].y += r.y;                  \
+        /* carry from the previous cell of the ring: the partner's hand-over of THIS step (odd lane, weight mg) */ \
+        /* or of the previous step (even lane, weight ms); weights are 0 / 1, at most one of them is 1 */ \
         r = fix_columns<4, true>(fx, o[8], o[9]);                                                        \
-        r.x += sel_flag(has_prev, c4.x, 0.0); r.y += sel_flag(has_prev, c4.y, 0.0);                \
+        r.x = fma(g3.x, mg, fma(saved[K][0].x, ms, r.x)); r.y = fma(g3.y, mg, fma(saved[K][0].y, ms, r.y)); \
         row[slot_of<4>(sl)] = r;                                                                  \
         r = fix_columns<2, true>(fx, o[4], o[5]);                                                        \
-        r.x += sel_flag(has_prev, c2.x, 0.0); r.y += sel_flag(has_prev, c2.y, 0.0);                \
+        r.x = fma(g1.x, mg, fma(saved[K][1].x, ms, r.x)); r.y = fma(g1.y, mg, fma(saved[K][1].y, ms, r.y)); \
         row[slot_of<2>(sl)] = r;                                                                  \
         r = fix_columns<9>(fx, o[18], o[19]);                                                      \
-        r.x += sel_flag(has_prev, c9.x, 0.0); r.y += sel_flag(has_prev, c9.y, 0.0);                \
+        r.x = fma(g8.x, mg, fma(saved[K][2].x, ms, r.x)); r.y = fma(g8.y, mg, fma(saved[K][2].y, ms, r.y)); \
         row[slot_of<9>(sl)] = r;                                                                  \
         row[slot_of<0>(sl)] = fix_columns<0, true>(fx, o[0], o[1]);                                     \
         row[slot_of<7>(sl)] = fix_columns<7>(fx, o[14], o[15]);                                   \
@@ -424,6 +424,7 @@ __device__ __forceinline__ void edge_pass(const CanonArgs& p, const unsigned lon
           *q3 = n3; *q1 = n1; *q8 = n8;                                                            \
         }                                                                                          \
       }                                                                                            \
+      saved[K][0] = g3; saved[K][1] = g1; saved[K][2] = g8;                                        \
     }
     if (MASS) {
       SFEM_RING_ROW(0, canon_edge_mass_k0)

@@ -1,4 +1,4 @@
-timeout 600 python -m pytest tests/test_gpu_parity.py -x -q 2>&1 | tail -2
-ncu --metrics gpu__time_duration.sum,lts__t_sector_hit_rate.pct,dram__bytes_read.sum,dram__bytes_write.sum,smsp__issue_active.avg.pct_of_peak_sustained_active --clock-control none -k regex:k_canon -s 6 -c 2 python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu 2>&1 | grep -E "k_canon|gpu__time|lts__|dram__|issue" | head -14
-timeout 300 python bench.py --n 70 --steps 5 --no-e2e --no-cpu 2>&1 | tail -1 | python -c "import json,sys; d=json.loads(sys.stdin.read()); print('n70', d['value'], d['ms_per_step'], d['roofline']['frac'], d['setup_ms'])"
-timeout 300 python bench.py --steps 5 --no-e2e --no-cpu 2>&1 | tail -1 | python -c "import json,sys; d=json.loads(sys.stdin.read()); print('n119', d['value'], d['ms_per_step'], d['roofline']['frac'], d['setup_ms'])"
+# parity of the value kernels + the two bench sizes without the e2e / CPU legs (gpurun -- bash tools/quick_gpu.sh)
+timeout 300 python -m pytest tests/test_gpu_parity.py tests/test_gpu_fullsize.py -x -q 2>&1 | tail -2
+timeout 200 python bench.py --n 70 --steps 10 --no-e2e --no-cpu 2>&1 | tail -1 | python -c "import json,sys; d=json.loads(sys.stdin.read()); print('n70', d['value'], d['ms_per_step'], d['roofline']['frac'], d['setup_ms'])"
+timeout 200 python bench.py --steps 10 --no-e2e --no-cpu 2>&1 | tail -1 | python -c "import json,sys; d=json.loads(sys.stdin.read()); print('n119', d['value'], d['ms_per_step'], d['roofline']['frac'], d['setup_ms'])"
