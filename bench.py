@@ -266,7 +266,7 @@ def main():
         torch.cuda.empty_cache()
         N.check(N.lib.sfem_release_cached_memory())
         try:
-            e2e = e2e_run(n, min(K, 5), rank, world)
+            e2e = e2e_run(n, min(K, 9), rank, world)
         except Exception as e:  # noqa: BLE001   (e.g. not enough page-lockable host memory for this rank's share)
             e2e = {"error": repr(e)[:300]}
         if world > 1:            # whole-job rate: all tets / the slowest rank's step
@@ -374,8 +374,10 @@ def e2e_run(n, steps, rank=0, world=1):
     dt = sorted(times)[len(times) // 2]      # median step
     h2d = sum(x.numel() * x.element_size() for x in (h_co, h_ce, h_eps, h_mu))
     d2h = sum(x.numel() * x.element_size() for x in list(out.values()) + list(out2.values()))
+    # the copy shares the host's PCIe / memory system with the box's other tenants: single steps vary by 2x, so the
+    # reported step is the median of up to 9 (all of them are listed, the fastest one separately)
     return {"value": len(ce) / dt, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-            "ms_per_step": dt * 1e3, "steps_ms": [round(t * 1e3, 1) for t in times],
+            "ms_per_step": dt * 1e3, "steps_ms": [round(t * 1e3, 1) for t in times], "best_ms": round(min(times) * 1e3, 1),
             "create_ms": [round(t * 1e3, 1) for t in t_create],
             "includes": "H2D mesh+materials, numbering, PEC flags, pattern, S+T values, CSR expansion, D2H of rowptr/cols/S/T "
                         "(streamed in row blocks: D2H of block k overlaps assembly of block k+1)"

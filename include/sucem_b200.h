@@ -65,6 +65,8 @@ SFEM_API const char* sfem_version(void);
  * cached when handles are destroyed (repeated set-ups reuse them).  This returns the cached memory to the driver
  * (synchronises the device).  Buffers of a handle are freed in the order of the stream the handle was created on. */
 SFEM_API int sfem_release_cached_memory(void);
+/* Bytes the pool currently holds from the driver / bytes handed out to live buffers (diagnostics). */
+SFEM_API int sfem_cached_memory_info(int64_t* reserved_bytes, int64_t* used_bytes);
 
 /* ---- mesh: replaces dolfin.Mesh / UnitCube / UnitSquare as inputs of the path -------------------
  * (examples/resonant_cavity/driver.py:34, sucemfem/Utilities/MeshGenerators.py:32-36).

@@ -241,6 +241,19 @@ int sfem_release_cached_memory(void) {
   return 0;
 }
 
+int sfem_cached_memory_info(int64_t* reserved_bytes, int64_t* used_bytes) {
+  int dev = 0;
+  SFEM_CUDA(cudaGetDevice(&dev));
+  cudaMemPool_t pool;
+  SFEM_CUDA(cudaDeviceGetDefaultMemPool(&pool, dev));
+  uint64_t r = 0, u = 0;
+  SFEM_CUDA(cudaMemPoolGetAttribute(pool, cudaMemPoolAttrReservedMemCurrent, &r));
+  SFEM_CUDA(cudaMemPoolGetAttribute(pool, cudaMemPoolAttrUsedMemCurrent, &u));
+  if (reserved_bytes) *reserved_bytes = (int64_t)r;
+  if (used_bytes) *used_bytes = (int64_t)u;
+  return 0;
+}
+
 int sfem_mesh_destroy(sfem_mesh_t mesh) {
   delete mesh;
   return 0;
