@@ -489,6 +489,7 @@ int sfem_partition_rows_by_class(sfem_space_t sp, int nparts, int64_t* edge_boun
 
 int sfem_launches_per_assemble_ST(sfem_pattern_t pat, int kernel) {
   if (!pat) return 0;
+  if (kernel == SFEM_KERNEL_AUTO && pat->space->mesh->gdim == 2) return 1;  // k_values_tri
   if (kernel == SFEM_KERNEL_AUTO) kernel = canonical_supported(pat) ? SFEM_KERNEL_CANONICAL : SFEM_KERNEL_GENERIC;
   return kernel == SFEM_KERNEL_CANONICAL ? canonical_launches(pat) : 2;  // generic: cell geometry + row gather
 }
@@ -518,6 +519,8 @@ int sfem_assemble_ST(sfem_pattern_t pat, const double* d_eps_r, const double* d_
                      const uint8_t* d_pec_row_flags, double* d_S, double* d_T, int kernel, void* stream) {
   SFEM_CHECK(pat && d_S && d_T, "NULL argument");
   DeviceGuard dg(pat->space->mesh->device);
+  if (kernel == SFEM_KERNEL_AUTO && pat->space->mesh->gdim == 2)   // triangles: thread-per-entity kernel
+    return assemble_triangles_ST(pat, d_eps_r, d_mu_r, d_pec_row_flags, d_S, d_T, (cudaStream_t)stream);
   if (kernel == SFEM_KERNEL_AUTO) kernel = canonical_supported(pat) ? SFEM_KERNEL_CANONICAL : SFEM_KERNEL_GENERIC;
   if (kernel == SFEM_KERNEL_CANONICAL) {
     SFEM_CHECK(canonical_supported(pat), "canonical kernels are unavailable for this pattern (they need order-2 tetrahedra, manifold edges of at most 64 cells and rows of at most 255 entities); use SFEM_KERNEL_GENERIC or SFEM_KERNEL_AUTO");

@@ -274,6 +274,140 @@ k_values_generic(PatView pv, const double* __restrict__ geo, const double* __res
   }
 }
 
+// ---- triangles, S and T in one sweep: one THREAD per row entity -------------------------------------------------
+// Two triangles that share an edge share nothing else that carries a dof, so the q rows of an entity are
+// [the entity itself] + [the other entities of each incident cell]: every CSR chunk has exactly one contributing cell
+// except the diagonal block, which is summed in registers over the incident cells in ascending order (DOLFIN's order).
+// No atomics, bit-reproducible.  The 32 consecutive entities of a warp own one contiguous span of S and of T; the
+// lanes assemble it in a shared-memory tile in its FINAL layout and the warp then streams the tile out with fully
+// coalesced stores (a thread writing its own rows straight to global memory issues 32 partial sectors per store
+// instruction: 0.83 TB/s at order 2 against the tile's figure in DESIGN.md).  A warp whose span does not fit the tile
+// (non-manifold edges) writes directly.  Geometry is recomputed per (entity, cell) from the gathered vertices (2 x 2
+// Jacobian: ~25 flops); the reference tensors sit in shared memory.  PEC rows are written as unit rows (ident fused).
+// the q rows of one entity into dS / dT (a shared-memory tile or the global arrays), rs = offset of its row 0
+template <int ORDER>
+__device__ __forceinline__ void tri_entity_rows(const PatView& pv, const double* __restrict__ sM,
+                                                const double* __restrict__ sC, const double* __restrict__ coords,
+                                                const int32_t* __restrict__ cells, const double* __restrict__ eps,
+                                                const double* __restrict__ mu, const uint8_t* __restrict__ pec,
+                                                int64_t g, int64_t rs, int len, double* __restrict__ dS,
+                                                double* __restrict__ dT) {
+  constexpr int Q = ORDER, NEC = ORDER == 1 ? 3 : 4, ND = Q * NEC;
+  const int64_t i0 = pv.inc_ptr[g], i1 = pv.inc_ptr[g + 1];
+  bool pecrow[Q];
+#pragma unroll
+  for (int k = 0; k < Q; ++k) pecrow[k] = pec && pec[Q * g + k];
+  double selfS[Q][Q], selfT[Q][Q];
+#pragma unroll
+  for (int k = 0; k < Q; ++k)
+#pragma unroll
+    for (int kp = 0; kp < Q; ++kp) selfS[k][kp] = selfT[k][kp] = 0.0;
+  int self_slot = 0;
+  for (int64_t i = i0; i < i1; ++i) {
+    const int64_t c = pv.inc_cell[i];
+    const int le = pv.inc_loc[i];
+    const uint16_t* __restrict__ ps = pv.pos + (i - pv.inc_base) * NEC;
+    double gT[3], gS[1];
+    cell_geometry<2>(coords, cells + c * 3, eps ? eps[c] : 1.0, mu ? mu[c] : 1.0, gT, gS, nullptr);
+#pragma unroll
+    for (int u = 0; u < NEC; ++u) {
+      const int s = ps[u];
+      double vS[Q][Q], vT[Q][Q];
+#pragma unroll
+      for (int k = 0; k < Q; ++k)
+#pragma unroll
+        for (int kp = 0; kp < Q; ++kp) {
+          const int ij = (le * Q + k) * ND + u * Q + kp;
+          vT[k][kp] = gT[0] * sM[3 * ij] + gT[1] * sM[3 * ij + 1] + gT[2] * sM[3 * ij + 2];
+          vS[k][kp] = gS[0] * sC[ij];
+        }
+      if (u == le) {
+        self_slot = s;
+#pragma unroll
+        for (int k = 0; k < Q; ++k)
+#pragma unroll
+          for (int kp = 0; kp < Q; ++kp) { selfS[k][kp] += vS[k][kp]; selfT[k][kp] += vT[k][kp]; }
+      } else {
+#pragma unroll
+        for (int k = 0; k < Q; ++k) {
+          const int64_t o = rs + (int64_t)k * Q * len + Q * s;
+#pragma unroll
+          for (int kp = 0; kp < Q; ++kp) {
+            dS[o + kp] = pecrow[k] ? 0.0 : vS[k][kp];
+            dT[o + kp] = pecrow[k] ? 0.0 : vT[k][kp];
+          }
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < Q; ++k) {
+    const int64_t o = rs + (int64_t)k * Q * len + Q * self_slot;
+#pragma unroll
+    for (int kp = 0; kp < Q; ++kp) {
+      dS[o + kp] = pecrow[k] ? (kp == k ? 1.0 : 0.0) : selfS[k][kp];
+      dT[o + kp] = pecrow[k] ? (kp == k ? 1.0 : 0.0) : selfT[k][kp];
+    }
+  }
+}
+
+constexpr int kTriThreads = 64;
+template <int ORDER>
+__global__ void __launch_bounds__(kTriThreads)
+k_values_tri(PatView pv, const double* __restrict__ coords, const int32_t* __restrict__ cells,
+             const double* __restrict__ eps, const double* __restrict__ mu, const uint8_t* __restrict__ pec,
+             double* __restrict__ outS, double* __restrict__ outT) {
+  using El = Elem<2, ORDER>;
+  constexpr int Q = ORDER, NEC = ORDER == 1 ? 3 : 4, ND = Q * NEC;
+  constexpr int CAP = 32 * Q * Q * (2 * NEC - 1);  // values per warp tile: 32 entities x q rows x q (2 NEC - 1) columns
+  __shared__ double sM[ND * ND * 3];
+  __shared__ double sC[ND * ND];
+  __shared__ __align__(16) double tiles[kTriThreads / 32][2][CAP];
+  for (int t = threadIdx.x; t < ND * ND * 3; t += blockDim.x) sM[t] = El::mass(0, 0)[t];
+  for (int t = threadIdx.x; t < ND * ND; t += blockDim.x) sC[t] = El::curl(0, 0)[t];
+  __syncthreads();
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  const bool valid = r < pv.n_rows;
+  const unsigned vmask = __ballot_sync(0xffffffffu, valid);
+  if (vmask == 0u) return;
+  const int64_t g = pv.ent_lo + r;
+  const int64_t a = valid ? pv.ent_rowptr[r] : 0;
+  const int64_t a1 = valid ? pv.ent_rowptr[r + 1] : 0;
+  const int len = (int)(a1 - a);
+  const int64_t a_first = __shfl_sync(0xffffffffu, a, 0);
+  const int64_t a_end = __shfl_sync(0xffffffffu, a1, 31 - __clz((int)vmask));
+  const int64_t span = (int64_t)Q * Q * (a_end - a_first);
+  const bool tiled = span <= CAP;  // warp-uniform
+  const int64_t rs = (int64_t)Q * Q * (a - a_first);  // first value of row 0 in the span; row k: + k * Q * len
+  if (valid) {
+    if (tiled)
+      tri_entity_rows<ORDER>(pv, sM, sC, coords, cells, eps, mu, pec, g, rs, len, tiles[w][0], tiles[w][1]);
+    else
+      tri_entity_rows<ORDER>(pv, sM, sC, coords, cells, eps, mu, pec, g, rs, len, outS + (int64_t)Q * Q * a_first,
+                             outT + (int64_t)Q * Q * a_first);
+  }
+  if (!tiled) return;
+  __syncwarp();
+  // stream the span out: the value arrays are written once and never read here
+  double* __restrict__ gS_ = outS + (int64_t)Q * Q * a_first;
+  double* __restrict__ gT_ = outT + (int64_t)Q * Q * a_first;
+  const int n = (int)span;
+  if (Q == 2) {  // spans start at multiples of 4 values: 16-byte stores
+    const double2* tS = reinterpret_cast<const double2*>(tiles[w][0]);
+    const double2* tT = reinterpret_cast<const double2*>(tiles[w][1]);
+    for (int j = lane; j < n / 2; j += 32) {
+      __stcs(reinterpret_cast<double2*>(gS_) + j, tS[j]);
+      __stcs(reinterpret_cast<double2*>(gT_) + j, tT[j]);
+    }
+  } else {
+    for (int j = lane; j < n; j += 32) {
+      __stcs(gS_ + j, tiles[w][0][j]);
+      __stcs(gT_ + j, tiles[w][1][j]);
+    }
+  }
+}
+
 // rows that can carry ABC contributions: row entities that LIE ON an exterior facet (the tangential trace of a basis
 // function vanishes on every facet that does not contain its entity, so all other rows of S_0 are zero).
 // inc_loc = local entity of the row entity in the incident cell (tets: edges 0-5, faces 6-9; triangles: edges 0-2,
@@ -417,6 +551,27 @@ int assemble_generic(const sfem_pattern_s* pat, int form, const double* coef_a, 
   if (dim == 2 && order == 2) return launch_generic<2, 2>(pat, form, coef_a, coef_b, facet_mask, pec, out_a, out_b, st);
   set_error("unsupported (dim, order)");
   return 2;
+}
+
+// Triangles, S and M(=T) together (the fast path SFEM_KERNEL_AUTO takes in 2-D): one launch of k_values_tri.
+int assemble_triangles_ST(const sfem_pattern_s* pat, const double* eps, const double* mu, const uint8_t* pec, double* S,
+                          double* T, cudaStream_t st) {
+  const sfem_space_s* sp = pat->space;
+  const sfem_mesh_s* m = sp->mesh;
+  if (m->gdim != 2 || (sp->order != 1 && sp->order != 2)) {
+    set_error("assemble_triangles_ST: triangles of order 1 or 2 only");
+    return 2;
+  }
+  if (pat->n_rows_ent == 0) return 0;
+  PatView pv{sp->inc_ptr, sp->inc_cell, sp->inc_loc, pat->ent_rowptr, pat->ent_cols, pat->pos,
+             pat->ent_lo, pat->n_rows_ent, pat->inc_base, sp->n_ent_cell, false, nullptr, 0};
+  const unsigned grid = (unsigned)((pat->n_rows_ent + kTriThreads - 1) / kTriThreads);
+  if (sp->order == 1)
+    k_values_tri<1><<<grid, kTriThreads, 0, st>>>(pv, m->coords, m->cells, eps, mu, pec, S, T);
+  else
+    k_values_tri<2><<<grid, kTriThreads, 0, st>>>(pv, m->coords, m->cells, eps, mu, pec, S, T);
+  SFEM_CUDA(cudaGetLastError());
+  return 0;
 }
 
 }  // namespace sfem
