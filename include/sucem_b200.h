@@ -54,7 +54,8 @@ enum {
 enum {
   SFEM_KERNEL_AUTO = 0,    /* fastest available for the space                                    */
   SFEM_KERNEL_GENERIC = 1, /* row-owner gather with full reference tensors (any dim/order)       */
-  SFEM_KERNEL_CANONICAL = 2/* canonical-frame straight-line kernels (tetrahedra, order 1 and 2)  */
+  SFEM_KERNEL_CANONICAL = 2,/* canonical-frame straight-line kernels (tetrahedra, order 1 and 2) */
+  SFEM_KERNEL_ROWS = 3     /* one thread per row entity (triangles order 1-2, tetrahedra order 1) */
 };
 
 SFEM_API const char* sfem_last_error(void);

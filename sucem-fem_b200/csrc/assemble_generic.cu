@@ -408,6 +408,88 @@ k_values_tri(PatView pv, const double* __restrict__ coords, const int32_t* __res
   }
 }
 
+// ---- order-1 tetrahedra (Whitney elements), S and T in one sweep: one THREAD per edge ----------------------------
+// A row is short (1 + 3 m entries for an edge of m cells), so a thread sums its row over the incident cells in
+// ascending order (DOLFIN's order) in a lane-private stretch of the warp's shared-memory tile; the 32 consecutive edges
+// of a warp own one contiguous span of S and of T, streamed out with coalesced stores.  ~60 registers per thread,
+// so many resident warps hide the gather chain (incidence -> cell -> vertices) that bounds the lane-pair kernel
+// k_canon1_edges.  No atomics, bit-reproducible.  PEC rows are written as unit rows.  tile_cap = values per warp tile.
+constexpr int kTet1Threads = 128;
+template <bool SHARED>
+__device__ __forceinline__ void tet1_edge_row(const PatView& pv, const double* __restrict__ sM,
+                                              const double* __restrict__ sC, const double* __restrict__ coords,
+                                              const int32_t* __restrict__ cells, const double* __restrict__ eps,
+                                              const double* __restrict__ mu, const uint8_t* __restrict__ pec, int64_t g,
+                                              int64_t rs, int len, double* __restrict__ dS, double* __restrict__ dT) {
+  for (int s = 0; s < len; ++s) dS[rs + s] = dT[rs + s] = 0.0;
+  int self_slot = 0;
+  const int64_t i0 = pv.inc_ptr[g], i1 = pv.inc_ptr[g + 1];
+  for (int64_t i = i0; i < i1; ++i) {
+    const int64_t c = pv.inc_cell[i];
+    const int le = pv.inc_loc[i];
+    const uint16_t* __restrict__ ps = pv.pos + (i - pv.inc_base) * 6;
+    const unsigned long long desc = kCanonDesc[le];  // slot table is in canonical column order (pattern.cu)
+    double gT[6], gS[6];
+    cell_geometry<3>(coords, cells + c * 4, eps ? eps[c] : 1.0, mu ? mu[c] : 1.0, gT, gS, nullptr);
+#pragma unroll
+    for (int uu = 0; uu < 6; ++uu) {
+      const int s = ps[uu];
+      const int u = (int)((desc >> (8 + 4 * uu)) & 15ull);
+      const double* __restrict__ Mh = sM + (le * 6 + u) * 6;
+      const double* __restrict__ Ch = sC + (le * 6 + u) * 6;
+      double vT = 0.0, vS = 0.0;
+#pragma unroll
+      for (int p = 0; p < 6; ++p) { vT += gT[p] * Mh[p]; vS += gS[p] * Ch[p]; }
+      if (u == le) self_slot = s;
+      dS[rs + s] += vS;
+      dT[rs + s] += vT;
+    }
+  }
+  if (pec && pec[g])
+    for (int s = 0; s < len; ++s) dS[rs + s] = dT[rs + s] = (s == self_slot) ? 1.0 : 0.0;
+}
+
+__global__ void __launch_bounds__(kTet1Threads)
+k_values_tet1(PatView pv, const double* __restrict__ coords, const int32_t* __restrict__ cells,
+              const double* __restrict__ eps, const double* __restrict__ mu, const uint8_t* __restrict__ pec,
+              double* __restrict__ outS, double* __restrict__ outT, int tile_cap) {
+  extern __shared__ double smem_t1[];
+  double* sM = smem_t1;
+  double* sC = smem_t1 + 216;
+  for (int t = threadIdx.x; t < 216; t += blockDim.x) {
+    sM[t] = Elem<3, 1>::mass(0, 0)[t];
+    sC[t] = Elem<3, 1>::curl(0, 0)[t];
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  double* tS = smem_t1 + 432 + (size_t)w * 2 * tile_cap;
+  double* tT = tS + tile_cap;
+  const int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  const bool valid = r < pv.n_rows;
+  const unsigned vmask = __ballot_sync(0xffffffffu, valid);
+  if (vmask == 0u) return;
+  const int64_t g = pv.ent_lo + r;
+  const int64_t a = valid ? pv.ent_rowptr[r] : 0;
+  const int64_t a1 = valid ? pv.ent_rowptr[r + 1] : 0;
+  const int64_t a_first = __shfl_sync(0xffffffffu, a, 0);
+  const int64_t a_end = __shfl_sync(0xffffffffu, a1, 31 - __clz((int)vmask));
+  const int64_t span = a_end - a_first;
+  const bool tiled = span <= tile_cap;  // warp-uniform
+  if (valid) {
+    if (tiled)
+      tet1_edge_row<true>(pv, sM, sC, coords, cells, eps, mu, pec, g, a - a_first, (int)(a1 - a), tS, tT);
+    else
+      tet1_edge_row<false>(pv, sM, sC, coords, cells, eps, mu, pec, g, a - a_first, (int)(a1 - a), outS + a_first,
+                           outT + a_first);
+  }
+  if (!tiled) return;
+  __syncwarp();
+  for (int j = lane; j < (int)span; j += 32) {
+    __stcs(outS + a_first + j, tS[j]);
+    __stcs(outT + a_first + j, tT[j]);
+  }
+}
+
 // rows that can carry ABC contributions: row entities that LIE ON an exterior facet (the tangential trace of a basis
 // function vanishes on every facet that does not contain its entity, so all other rows of S_0 are zero).
 // inc_loc = local entity of the row entity in the incident cell (tets: edges 0-5, faces 6-9; triangles: edges 0-2,
@@ -553,23 +635,45 @@ int assemble_generic(const sfem_pattern_s* pat, int form, const double* coef_a, 
   return 2;
 }
 
-// Triangles, S and M(=T) together (the fast path SFEM_KERNEL_AUTO takes in 2-D): one launch of k_values_tri.
-int assemble_triangles_ST(const sfem_pattern_s* pat, const double* eps, const double* mu, const uint8_t* pec, double* S,
-                          double* T, cudaStream_t st) {
+// Thread-per-row-entity kernels (SFEM_KERNEL_ROWS): triangles of order 1 / 2 and order-1 tetrahedra, S and M(=T)
+// together in one launch.
+bool rows_supported(const sfem_pattern_s* pat) {
+  const sfem_space_s* sp = pat->space;
+  return sp->mesh->gdim == 2 ? (sp->order == 1 || sp->order == 2) : (sp->mesh->gdim == 3 && sp->order == 1);
+}
+
+int assemble_rows_ST(const sfem_pattern_s* pat, const double* eps, const double* mu, const uint8_t* pec, double* S,
+                     double* T, cudaStream_t st) {
   const sfem_space_s* sp = pat->space;
   const sfem_mesh_s* m = sp->mesh;
-  if (m->gdim != 2 || (sp->order != 1 && sp->order != 2)) {
-    set_error("assemble_triangles_ST: triangles of order 1 or 2 only");
+  if (!rows_supported(pat)) {
+    set_error("SFEM_KERNEL_ROWS: triangles of order 1 or 2 and tetrahedra of order 1 only");
     return 2;
   }
   if (pat->n_rows_ent == 0) return 0;
   PatView pv{sp->inc_ptr, sp->inc_cell, sp->inc_loc, pat->ent_rowptr, pat->ent_cols, pat->pos,
-             pat->ent_lo, pat->n_rows_ent, pat->inc_base, sp->n_ent_cell, false, nullptr, 0};
-  const unsigned grid = (unsigned)((pat->n_rows_ent + kTriThreads - 1) / kTriThreads);
-  if (sp->order == 1)
-    k_values_tri<1><<<grid, kTriThreads, 0, st>>>(pv, m->coords, m->cells, eps, mu, pec, S, T);
-  else
-    k_values_tri<2><<<grid, kTriThreads, 0, st>>>(pv, m->coords, m->cells, eps, mu, pec, S, T);
+             pat->ent_lo, pat->n_rows_ent, pat->inc_base, sp->n_ent_cell, pos_is_canonical(sp), nullptr, 0};
+  if (m->gdim == 3) {
+    // tile = 32 rows of the longest length, capped so that several CTAs stay resident (longer spans write directly)
+    constexpr int kWarpsT1 = kTet1Threads / 32;
+    int cap = 32 * std::max(pat->max_row_len, 1);
+    const int cap_max = (int)((96 * 1024 - 432 * 8) / (kWarpsT1 * 2 * 8));
+    cap = std::min(cap, cap_max);
+    const size_t smem = (size_t)(432 + kWarpsT1 * 2 * cap) * sizeof(double);
+    static bool attr_set[64] = {};
+    if (m->device >= 0 && m->device < 64 && !attr_set[m->device]) {
+      SFEM_CUDA(cudaFuncSetAttribute(k_values_tet1, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+      attr_set[m->device] = true;
+    }
+    const unsigned grid = (unsigned)((pat->n_rows_ent + kTet1Threads - 1) / kTet1Threads);
+    k_values_tet1<<<grid, kTet1Threads, smem, st>>>(pv, m->coords, m->cells, eps, mu, pec, S, T, cap);
+  } else {
+    const unsigned grid = (unsigned)((pat->n_rows_ent + kTriThreads - 1) / kTriThreads);
+    if (sp->order == 1)
+      k_values_tri<1><<<grid, kTriThreads, 0, st>>>(pv, m->coords, m->cells, eps, mu, pec, S, T);
+    else
+      k_values_tri<2><<<grid, kTriThreads, 0, st>>>(pv, m->coords, m->cells, eps, mu, pec, S, T);
+  }
   SFEM_CUDA(cudaGetLastError());
   return 0;
 }

@@ -173,8 +173,9 @@ int export_pattern(const sfem_pattern_s* pat, int64_t* d_rowptr, int32_t* d_cols
 int assemble_generic(const sfem_pattern_s* pat, int form, const double* coef_a, const double* coef_b,
                      const uint8_t* facet_mask, const uint8_t* pec, double* out_a, double* out_b,
                      cudaStream_t st);
-int assemble_triangles_ST(const sfem_pattern_s* pat, const double* eps, const double* mu, const uint8_t* pec, double* S,
-                          double* T, cudaStream_t st);
+int assemble_rows_ST(const sfem_pattern_s* pat, const double* eps, const double* mu, const uint8_t* pec, double* S,
+                     double* T, cudaStream_t st);
+bool rows_supported(const sfem_pattern_s* pat);
 int assemble_canonical_ST(const sfem_pattern_s* pat, const double* eps, const double* mu, const uint8_t* pec,
                           double* S, double* T, cudaStream_t st);
 bool canonical_supported(const sfem_pattern_s* pat);

@@ -10,7 +10,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get('SUCEM_B200_LIB') or os.path.join(os.path.dirname(_HERE), 'lib', 'libsucem_b200.so')
 
 FORM_MASS, FORM_STIFFNESS, FORM_ABC = 0, 1, 2
-KERNEL_AUTO, KERNEL_GENERIC, KERNEL_CANONICAL = 0, 1, 2
+KERNEL_AUTO, KERNEL_GENERIC, KERNEL_CANONICAL, KERNEL_ROWS = 0, 1, 2, 3
 
 
 class NativeError(RuntimeError):

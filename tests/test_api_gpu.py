@@ -235,6 +235,14 @@ def test_high_valence_edge_falls_back_to_generic_kernel():
         assert np.all(np.abs(T.cpu().numpy() - ref['M']) <= 1e-12 * np.abs(ref['M']) + 1e-15 * np.abs(ref['M']).max())
         with pytest.raises(N.NativeError, match='canonical'):
             pat.assemble_ST(kernel=N.KERNEL_CANONICAL)
+        # order 1 on the same fan: AUTO / ROWS = the thread-per-edge kernel; the hub edge's row (1 + 3 m entries)
+        # makes its warp's span exceed the shared-memory tile at m = 70, which takes the direct-write path
+        ref1 = fem.assemble_system(co, ce, 1)
+        pat1 = device.DeviceSpace(device.DeviceMesh(co, ce), 1).pattern()
+        for kern in (N.KERNEL_AUTO, N.KERNEL_ROWS):
+            S1, T1 = pat1.assemble_ST(kernel=kern)
+            assert np.all(np.abs(S1.cpu().numpy() - ref1['S']) <= 1e-12 * np.abs(ref1['S']) + 1e-15 * np.abs(ref1['S']).max())
+            assert np.all(np.abs(T1.cpu().numpy() - ref1['M']) <= 1e-12 * np.abs(ref1['M']) + 1e-15 * np.abs(ref1['M']).max())
     m = 12
     ang = 2 * np.pi * np.arange(m) / m
     co = np.concatenate([[[0, 0, -1.0], [0, 0, 1.0]], np.stack([np.cos(ang), np.sin(ang), 0 * ang], 1)])

@@ -350,11 +350,14 @@ def test_canonical_midsize_vs_c_oracle(dev):
 TRI_MESHES = [k for k in sorted(MESHES) if MESHES[k][0].shape[1] == 2]
 
 
-@pytest.mark.parametrize('order', [1, 2])
-@pytest.mark.parametrize('name', TRI_MESHES)
-def test_values_triangle_kernel_vs_oracle(dev, name, order):
-    """The 2-D fast path (SFEM_KERNEL_AUTO on triangles: one thread per row entity, S and T in one sweep) against the
-    oracle and the generic kernel, with PEC, default coefficients, determinism and row blocks."""
+ROWS_CASES = [(k, o) for k in TRI_MESHES for o in (1, 2)] + [(k, 1) for k in TET_MESHES]
+
+
+@pytest.mark.parametrize('name,order', ROWS_CASES)
+def test_values_rows_kernel_vs_oracle(dev, name, order):
+    """SFEM_KERNEL_ROWS (one thread per row entity, S and T in one sweep: what SFEM_KERNEL_AUTO takes on triangles and
+    on order-1 tetrahedra) against the oracle and the generic kernel, with PEC, default coefficients, determinism and
+    row blocks."""
     import torch
     from sucemfem import _native as N
     co, ce = MESHES[name]
@@ -368,17 +371,17 @@ def test_values_triangle_kernel_vs_oracle(dev, name, order):
     sp = dev.DeviceSpace(dev.DeviceMesh(co, ce), order)
     pat = sp.pattern()
     d_eps, d_mu = torch.from_numpy(eps).cuda(), torch.from_numpy(mu).cuda()
-    S, T = pat.assemble_ST(d_eps, d_mu, kernel=N.KERNEL_AUTO)
+    S, T = pat.assemble_ST(d_eps, d_mu, kernel=N.KERNEL_ROWS)
     assert close(S.cpu().numpy(), ref['S']) and close(T.cpu().numpy(), ref['M'])
     Sg, Tg = pat.assemble_ST(d_eps, d_mu, kernel=N.KERNEL_GENERIC)
     assert close(S.cpu().numpy(), Sg.cpu().numpy()) and close(T.cpu().numpy(), Tg.cpu().numpy())
-    S1, T1 = pat.assemble_ST(kernel=N.KERNEL_AUTO)
+    S1, T1 = pat.assemble_ST(kernel=N.KERNEL_ROWS)
     ref1 = fem.assemble_system(co, ce, order)
     assert close(S1.cpu().numpy(), ref1['S']) and close(T1.cpu().numpy(), ref1['M'])
     markers = torch.zeros(sp.n_facets, dtype=torch.int32, device='cuda')
     sp.mark_exterior_facets(markers, 999)
     flags = sp.pec_row_flags(markers, 999)
-    Sp, Tp = pat.assemble_ST(d_eps, d_mu, pec_flags=flags, kernel=N.KERNEL_AUTO)
+    Sp, Tp = pat.assemble_ST(d_eps, d_mu, pec_flags=flags, kernel=N.KERNEL_ROWS)
     assert close(Sp.cpu().numpy(), refp['S'], ref['S']) and close(Tp.cpu().numpy(), refp['M'], ref['M'])
     # unit rows are exact
     rows = refp['pec_dofs']
@@ -386,13 +389,16 @@ def test_values_triangle_kernel_vs_oracle(dev, name, order):
     for r_ in rows[:5]:
         seg = Sp.cpu().numpy()[rp[r_]:rp[r_ + 1]]
         assert seg.sum() == 1.0 and np.count_nonzero(seg) == 1
-    S2, T2 = pat.assemble_ST(d_eps, d_mu, pec_flags=flags, kernel=N.KERNEL_AUTO)
+    S2, T2 = pat.assemble_ST(d_eps, d_mu, pec_flags=flags, kernel=N.KERNEL_ROWS)
     assert torch.equal(S2, Sp) and torch.equal(T2, Tp)
+    if co.shape[1] == 2:      # AUTO = ROWS on triangles (tets of order 1: canonical where the pattern allows it)
+        S3, T3 = pat.assemble_ST(d_eps, d_mu, pec_flags=flags, kernel=N.KERNEL_AUTO)
+        assert torch.equal(S3, Sp) and torch.equal(T3, Tp)
     b = sp.partition(3)
     Ss, Ts = [], []
     for q in range(3):
         blk = dev.DevicePattern(sp, b[q], b[q + 1])
-        s, t = blk.assemble_ST(d_eps, d_mu, pec_flags=flags, kernel=N.KERNEL_AUTO)
+        s, t = blk.assemble_ST(d_eps, d_mu, pec_flags=flags, kernel=N.KERNEL_ROWS)
         Ss.append(s)
         Ts.append(t)
     assert torch.equal(torch.cat(Ss), Sp) and torch.equal(torch.cat(Ts), Tp)
