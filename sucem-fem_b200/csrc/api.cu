@@ -219,8 +219,10 @@ int sfem_mesh_create(int gdim, int64_t n_vertices, const double* d_coords, int64
   SFEM_CHECK(gdim == 2 || gdim == 3, "gdim must be 2 or 3");
   SFEM_CHECK(n_vertices > 0 && n_cells > 0 && d_coords && d_cells, "empty mesh or NULL arrays");
   SFEM_CHECK(n_vertices < (int64_t)2147483647, "too many vertices for int32 connectivity");
+  int dev = 0;
+  SFEM_CUDA(cudaGetDevice(&dev));
   auto* m = new sfem_mesh_s();
-  SFEM_CUDA(cudaGetDevice(&m->device));
+  m->device = dev;
   m->gdim = gdim;
   m->nv = gdim + 1;
   m->V = n_vertices;
