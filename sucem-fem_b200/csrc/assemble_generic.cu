@@ -9,6 +9,9 @@
 // geometry factors with the full pre-integrated reference tensor.  Every CSR value is written exactly once,
 // coalesced, without atomics: results are bit-reproducible.  Works for any dim/order and any local position;
 // it is the cross-check for the canonical-frame kernels in assemble_canonical.cu.
+//
+// Also here: the thread-per-row-entity kernels (SFEM_KERNEL_ROWS) -- k_values_tri (triangles of order 1 / 2, the 2-D fast
+// path) and k_values_tet1 (order-1 tetrahedra the canonical kernel refuses) -- and the S_0 row selection.
 #include <cub/cub.cuh>
 
 #include "sfem_internal.h"

@@ -127,7 +127,7 @@ struct sfem_pattern_s {
   uint4* rec = nullptr;           // [n_inc_block][2] packed 32-byte item records {relabelled vertex ids, cell,
                                   // descriptor, flags, 10 uint8 slots} (order-2 tets, rows <= 255 entities)
   bool ring_ok = false;           // edge records are in ring order (manifold edges of bounded valence)
-  int64_t* abc_rows = nullptr;    // block-relative row entities with an incident exterior-facet cell (lazily built)
+  int64_t* abc_rows = nullptr;    // block-relative row entities that lie on an exterior facet (lazily built)
   int64_t n_abc_rows = -1;
   int64_t inc_base = 0;           // = space->inc_ptr[ent_lo]
   int64_t n_inc_block = 0;
