@@ -30,6 +30,25 @@ UNIT = "tets/s"
 WORKLOAD_N = {1: 119, 2: 128, 4: 161, 8: 203}
 
 
+_JSON_OUT = None
+
+
+def claim_stdout():
+    """stdout carries the ONE JSON line and nothing else: whatever libraries print there (NCCL's version banner, ...)
+    goes to stderr from here on."""
+    global _JSON_OUT
+    if _JSON_OUT is None:
+        sys.stdout.flush()
+        _JSON_OUT = os.fdopen(os.dup(1), 'w')
+        os.dup2(2, 1)
+
+
+def emit(line):
+    out = _JSON_OUT or sys.stdout
+    out.write(json.dumps(line) + '\n')
+    out.flush()
+
+
 def algorithmic_bytes(n_cells, n_vertices, nnz, n_mat=2):
     """SURVEY 8(d) / BASELINE.md section 4: values out + connectivity + coordinates + (eps_r, mu_r)."""
     return 8 * nnz * n_mat + 16 * n_cells + 24 * n_vertices + 16 * n_cells
@@ -117,6 +136,7 @@ def run_reference(args):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
+    claim_stdout()
     from oracle import cport  # noqa: F401
     threads = os.cpu_count() or 1
     n = 32
@@ -134,7 +154,7 @@ def run_reference(args):
             "values_only": r["values_only"],
             "cpu_baseline": {"value": v, "unit": UNIT, "cores": r["max_threads"], "kind": "port", "sample": sample},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    emit(line)
 
 
 def main():
@@ -156,6 +176,7 @@ def main():
         cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', str(args.gpus),
                '--master-addr', '127.0.0.1', '--master-port', '29517'] + sys.argv
         os.execv(sys.executable, cmd)
+    claim_stdout()
     import numpy as np
     import torch
     import torch.distributed as dist
@@ -298,7 +319,7 @@ def main():
         line["clocks"] = sampler.summary()
         if line["gpu_launches"] is None:
             line["gpu_launches"] = sum(launches_per_step(kernel, pat) for pat in pats) * K
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
