@@ -84,6 +84,7 @@ class ClockSampler(threading.Thread):
                                   nv.nvmlDeviceGetCurrentClocksThrottleReasons(h),
                                   nv.nvmlDeviceGetPowerUsage(h) / 1000.0))
                 time.sleep(0.001)
+            nv.nvmlShutdown()     # nothing of the sampler stays alive next to the e2e leg
         except Exception as e:  # noqa: BLE001
             self.error = repr(e)
 
@@ -237,6 +238,7 @@ def main():
     ms_local = ms
     if sampler:
         sampler.stop_flag = True
+        sampler.join(timeout=5.0)
     per_rank_ms = [ms_local / K]
     if world > 1:
         t = torch.tensor([ms], dtype=torch.float64, device='cuda')
