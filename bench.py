@@ -356,8 +356,8 @@ def e2e_run(n, steps, rank=0, world=1):
     """The user-facing host-buffer call (sucemfem.device.HostAssemblyJob = sfem_host_job_create/run of the C ABI):
     numpy mesh + materials in, scipy-ready CSR (rowptr, cols, S, T) in page-locked host arrays out.  Everything
     between -- H2D, numbering, PEC flags, pattern, S+T values, CSR expansion, D2H -- is inside the timed region; the
-    D2H of row block k overlaps the assembly of block k+1.  The first iteration (which page-locks the output arrays, a
-    one-off a caller that repeats the call keeps) is the warm-up.  world > 1: every rank creates the job from the whole
+    D2H of row block k overlaps the assembly of block k+1.  Three untimed iterations come first (the first one page-locks the
+    output arrays, a one-off a caller that repeats the call keeps).  world > 1: every rank creates the job from the whole
     mesh and streams only the rows it owns (one edge range + one face range); no communication."""
     import numpy as np
     import torch
@@ -378,7 +378,8 @@ def e2e_run(n, steps, rank=0, world=1):
     h_co, h_ce, h_eps, h_mu = pin(co), pin(ce), pin(eps), pin(mu)
     out, out2 = {}, {}
     times, t_create = [], []
-    for it in range(steps + 1):
+    n_warm = 3      # untimed: the first one page-locks the output arrays, the next two let the host settle
+    for it in range(steps + n_warm):
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         job = device.HostAssemblyJob(h_co, h_ce, 2, h_eps, h_mu, pec='exterior')
@@ -391,7 +392,7 @@ def e2e_run(n, steps, rank=0, world=1):
             out2 = job.run_rows(ob[rank], ob[rank + 1], want=('cols', 'S', 'T'), out=out2, order=2)
         job.close()
         torch.cuda.synchronize()
-        if it > 0:
+        if it >= n_warm:
             times.append(time.perf_counter() - t0)
             t_create.append(t1 - t0)
     dt = sorted(times)[len(times) // 2]      # median step
