@@ -135,7 +135,20 @@ def gmsh_pairs():
     np.savez_compressed(os.path.join(HERE, 'gmsh_pairs.npz'), **out)
 
 
+
+def filament_example():
+    """examples/filament_source/data/dofs-2-...-100.pickle: order-2 solution of examples/filament_source/driver.py:48-98
+    on get_centred_cube(1 lambda, lambda/6) = UnitCube(9), 30186 dofs.  The stored vector satisfies the linear system
+    to 9.97e-6 -- it came out of the driver's iterative branch (scipy bicgstab, default tolerance 1e-5,
+    driver.py:93-94), so it pins the matrices and the right-hand side only to that tolerance."""
+    with open('/root/reference/examples/filament_source/data/'
+              'dofs-2-0.299792458-0.0499654096667-0.0749481145-100.pickle', 'rb') as f:
+        d = pickle.load(f, encoding='latin1')
+    np.savez_compressed(os.path.join(HERE, 'driven_order2_unitcube9_bicgstab.npz'), **{k: np.asarray(v) for k, v in d.items()})
+
+
 if __name__ == '__main__':
     prism()
     gmsh_pairs()
+    filament_example()
     main()
