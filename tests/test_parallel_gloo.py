@@ -53,7 +53,16 @@ def _worker(rank, world, port, ret):
     rp2, cl2, vl2 = parallel.gather_csr_two_class(block(eb), block(ob))
     ok2 = (np.array_equal(rp2.numpy(), ref['rowptr']) and np.array_equal(cl2.numpy(), ref['cols'])
            and np.array_equal(vl2.numpy(), ref['M']) and eb[-1] == num['E'] == ob[0] and ob[-1] == n_ent)
-    ret[rank] = bool(ok) and bool(ok2) and (hi - lo) > 0
+    # several value arrays on one pattern (S and M): the pattern is gathered once
+    def block2(b):
+        a0, a1 = 2 * b[rank], 2 * b[rank + 1]
+        s0, s1 = ref['rowptr'][a0], ref['rowptr'][a1]
+        return (torch.from_numpy(ref['rowptr'][a0:a1 + 1] - s0), torch.from_numpy(ref['cols'][s0:s1].copy()),
+                [torch.from_numpy(ref['S'][s0:s1].copy()), torch.from_numpy(ref['M'][s0:s1].copy())])
+    rp3, cl3, (vS, vM) = parallel.gather_csr_classes([block2(eb), block2(ob)])
+    ok3 = (np.array_equal(rp3.numpy(), ref['rowptr']) and np.array_equal(cl3.numpy(), ref['cols'])
+           and np.array_equal(vS.numpy(), ref['S']) and np.array_equal(vM.numpy(), ref['M']))
+    ret[rank] = bool(ok) and bool(ok2) and bool(ok3) and (hi - lo) > 0
     dist.barrier()
     dist.destroy_process_group()
 
