@@ -89,3 +89,69 @@ def test_femmesh_reader_and_converters(tmp_path):
 def test_circuit_s11():
     from sucemfem.PostProcessing.circuit import S11
     assert S11(50.0, 50.0) == 0 and np.allclose(S11([0.0, 1e30], 50.0), [-1.0, 1.0])
+
+
+class _HostSpace(object):
+    """CPU stand-in for dolfin_compat.FunctionSpace with the attributes the host-side evaluators use (mesh(),
+    dofmap().cell_dofs_array(), order); numbering from the oracle (this is a test of host logic only)."""
+
+    def __init__(self, co, ce, order):
+        from oracle import fem
+        self._co, self._ce, self.order = co, ce, order
+        self.num = fem.number_entities(ce)
+        self._cd, self.ndof = fem.cell_dofs(self.num, order)
+
+    def mesh(self):
+        return self
+
+    def coordinates(self):
+        return self._co
+
+    def cells(self):
+        return self._ce
+
+    def dofmap(self):
+        return self
+
+    def cell_dofs_array(self):
+        return self._cd
+
+
+def _interpolate_order2(V, u):
+    """Nodal dofs of a vector field u(x) in the order-2 N1curl space (SURVEY 8.1-B functionals)."""
+    co, num = V._co, V.num
+    x = np.zeros(V.ndof)
+    E = num['E']
+    for e, (a, b) in enumerate(num['edges']):
+        t = co[b] - co[a]
+        for k in range(2):
+            x[2 * e + k] = u(co[a] + (k + 1) / 3.0 * t) @ t
+    for f, (a, b, c) in enumerate(num['faces']):
+        cen = (co[a] + co[b] + co[c]) / 3.0
+        x[2 * E + 2 * f] = u(cen) @ (co[b] - co[a])
+        x[2 * E + 2 * f + 1] = u(cen) @ (co[c] - co[a])
+    return x
+
+
+def test_voltage_along_line_reference_cases():
+    """/root/reference/sucemfem/Sources/tests/test_postprocessing.py:30-77: E = (0, 0, 2z) on UnitCube(3), order 2;
+    the reference's five paths give +1, +1, -1, -1 and 0 V.  (Its complex case interpolates -z^2 at order 3; here the
+    imaginary part is -z, which the order-2 space holds exactly: -1/2.)"""
+    from oracle import meshes
+    from sucemfem.Sources.PostProcess import VoltageAlongLine, ComplexVoltageAlongLine, FieldFunction
+    co, ce = meshes.unit_cube(3)
+    V = _HostSpace(co, ce, 2)
+    u_r = _interpolate_order2(V, lambda p: np.array([0, 0, 2 * p[2]]))
+    u_i = _interpolate_order2(V, lambda p: np.array([0, 0, -p[2]]))
+    p1v_pts = (np.array([[0.5, 0.35, 0], [0.5, 0.5, 1]]), np.array([[0, 0, 0], [1, 1, 1.]]))
+    m1v_pts = (np.array([[0.25, 0.5, 1 - 3e-16], [0.5, 0.75, 3e-16]]), np.array([[1, 1, 1], [0, 0, 0.]]))
+    p0v_pts = np.array([[0, 0, 1], [1, 1, 1.]])
+    dut = VoltageAlongLine(FieldFunction(V, u_r))
+    assert abs(dut.calculate_voltage(*p1v_pts[0]) - 1) < 1e-7 and abs(dut.calculate_voltage(*p1v_pts[1]) - 1) < 1e-7
+    assert abs(dut.calculate_voltage(*m1v_pts[0]) + 1) < 1e-7 and abs(dut.calculate_voltage(*m1v_pts[1]) + 1) < 1e-7
+    assert abs(dut.calculate_voltage(*p0v_pts)) < 1e-7
+    cdut = ComplexVoltageAlongLine(V)
+    cdut.set_dofs(u_r + 1j * u_i)
+    for pts, want in ((p1v_pts[0], 1 - 0.5j), (p1v_pts[1], 1 - 0.5j), (m1v_pts[0], -(1 - 0.5j)), (m1v_pts[1], -(1 - 0.5j)),
+                      (p0v_pts, 0)):
+        assert abs(cdut.calculate_voltage(*pts) - want) < 1e-7
