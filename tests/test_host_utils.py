@@ -155,3 +155,30 @@ def test_voltage_along_line_reference_cases():
     for pts, want in ((p1v_pts[0], 1 - 0.5j), (p1v_pts[1], 1 - 0.5j), (m1v_pts[0], -(1 - 0.5j)), (m1v_pts[1], -(1 - 0.5j)),
                       (p0v_pts, 0)):
         assert abs(cdut.calculate_voltage(*pts) - want) < 1e-7
+
+
+def test_small_example_helpers():
+    """Testing.ErrorMeasures / Testing.Analytical / Testing.Paths / Utilities.Optimization: what the reference's example
+    drivers import (examples/filament_source/driver.py:25-40)."""
+    from sucemfem.Testing.ErrorMeasures import normalised_RMS, max_normalised_RMS
+    from sucemfem.Testing.Analytical import current_fillament_farfield as ff
+    from sucemfem.Testing import Paths
+    from sucemfem.Utilities import Optimization
+    from sucemfem.Consts import mu0, c0
+    a, d = np.array([1.0, -2.0, 4.0]), np.array([1.1, -2.0, 3.0])
+    assert np.isclose(normalised_RMS(a, d), 100 * (0.1 ** 2 + 0.25 ** 2))
+    assert np.isclose(max_normalised_RMS(a, d, extra_error=np.array([0, 0.4, 0])), 100 * ((0.1 / 4) ** 2 + (1 / 4) ** 2 + 0.1 ** 2))
+    # short dipole limit: |E_theta| -> w mu0 I L sin(theta) / (4 pi r); broadside value finite (the symbolic form is 0/0)
+    freq, L, I = 1e9, 1e-4, 2.0
+    th = np.deg2rad(np.array([30.0, 90.0, 140.0]))
+    v = ff.eval_E_theta(freq, L, I, th, r_val=3.0)
+    assert np.allclose(np.abs(v), 2 * np.pi * freq * mu0 * I * L * np.sin(th) / (4 * np.pi * 3.0), rtol=1e-6)
+    lam = c0 / freq
+    full = ff.eval_E_theta(freq, lam, 1.0, np.deg2rad(60.0))      # u = pi/2 * ... : pattern sin(60) sin(u)/u, u = pi cos(60)
+    u = np.pi * np.cos(np.deg2rad(60.0))
+    assert np.isclose(abs(full), 2 * np.pi * freq * mu0 * lam / (4 * np.pi) * np.sin(np.deg2rad(60.0)) * np.sin(u) / u)
+    assert isinstance(ff.eval_E_theta(freq, lam / 4, 1.0, 0.3), complex)
+    assert Paths.get_module_path_filename('x.dat', '/a/b/c.py') == '/a/b/x.dat'
+    Optimization.set_dolfin_optimisation(False)
+    assert Optimization.parameters['form_compiler'] == {'optimize': False, 'cpp_optimize': False}
+    Optimization.set_dolfin_optimisation()
