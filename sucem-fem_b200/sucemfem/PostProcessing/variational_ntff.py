@@ -12,6 +12,14 @@ from . import CalcEMFunctional
 from .surface_ntff import SurfaceNTFFForms
 
 
+def _spherical_unit_vectors(theta_deg, phi_deg):
+    """(rhat, theta_hat, phi_hat) of the spherical coordinate system at (theta, phi) given in degrees."""
+    th, ph = np.deg2rad(theta_deg), np.deg2rad(phi_deg)
+    st, ct, sp, cp = np.sin(th), np.cos(th), np.sin(ph), np.cos(ph)
+    return (np.array([st * cp, st * sp, ct], dtype=np.float64), np.array([ct * cp, ct * sp, -st], dtype=np.float64),
+            np.array([-sp, cp, 0.0], dtype=np.float64))
+
+
 class _Expr(object):
     """Vector expression cf * trig(k0 rhat . x); callable on point arrays [n,3], and eval(value, x) like dolfin's."""
 
@@ -78,32 +86,21 @@ class NTFF(object):
         self.surface_forms.set_dofs(dofs)
 
     def calc_pt(self, theta_deg, phi_deg):
-        # H-field contribution using variational calculation
-        E_H_theta, E_H_phi = self.calc_pt_E_H(theta_deg, phi_deg)
-        theta = np.deg2rad(theta_deg)
-        phi = np.deg2rad(phi_deg)
-        self.surface_forms.set_parms(theta, phi, self.k0)
+        """(E_theta, E_phi) of the far field in direction (theta, phi), normalised to radius 1: the H-field part from
+        the variational functional, the E-field part (L) from the surface integral."""
+        from_H = self.calc_pt_E_H(theta_deg, phi_deg)
+        self.surface_forms.set_parms(np.deg2rad(theta_deg), np.deg2rad(phi_deg), self.k0)
         L_theta, L_phi = self.surface_forms.assemble_L()
-        # far fields normalised to radius 1
-        r_fac = 1j * self.k0 * np.exp(-1j * self.k0) / (4 * np.pi)
-        E_theta = r_fac * (-L_phi + E_H_theta)
-        E_phi = r_fac * (L_theta + E_H_phi)
-        return (E_theta, E_phi)
+        scale = 1j * self.k0 * np.exp(-1j * self.k0) / (4 * np.pi)
+        return (scale * (from_H[0] - L_phi), scale * (from_H[1] + L_theta))
 
     def calc_pt_E_H(self, theta_deg, phi_deg):
-        theta = np.deg2rad(theta_deg)
-        phi = np.deg2rad(phi_deg)
-        rhat = np.array([np.sin(theta) * np.cos(phi), np.sin(theta) * np.sin(phi), np.cos(theta)], dtype=np.float64)
-        theta_hat = np.array([np.cos(theta) * np.cos(phi), np.cos(theta) * np.sin(phi), -np.sin(theta)], dtype=np.float64)
-        phi_hat = np.array([-np.sin(phi), np.cos(phi), 0.], dtype=np.float64)
-        E_H_theta = self.calc_ff_func(rhat, theta_hat)
-        E_H_phi = self.calc_ff_func(rhat, phi_hat)
-        return E_H_theta, E_H_phi
+        rhat, theta_hat, phi_hat = _spherical_unit_vectors(theta_deg, phi_deg)
+        return self.calc_ff_func(rhat, theta_hat), self.calc_ff_func(rhat, phi_hat)
 
     def calc_ff_func(self, rhat, ahat):
+        """Functional with the testing function interpolated from the expression for direction rhat, polarisation ahat."""
         self.testing_expression_gen.set_parms(rhat, ahat, self.k0)
-        fit_expr_r, fit_expr_i = self.testing_expression_gen.get_expression()
-        self.testing_interpolator.set_interpolant_expression(fit_expr_r, fit_expr_i)
-        g_dofs = self.testing_interpolator.calculate_interpolation()
-        self.functional.set_g_dofs(g_dofs)
+        self.testing_interpolator.set_interpolant_expression(*self.testing_expression_gen.get_expression())
+        self.functional.set_g_dofs(self.testing_interpolator.calculate_interpolation())
         return self.functional.calc_functional()

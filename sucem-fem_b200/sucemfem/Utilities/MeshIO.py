@@ -1,7 +1,11 @@
-""".femmesh reader (mirror of /root/reference/sucemfem/Utilities/MeshIO.py:28-117): BLOCK nodes / BLOCK tets / BLOCK tris
-sections with 1-based numbering; triangles are ignored."""
+""".femmesh reader (same interface as /root/reference/sucemfem/Utilities/MeshIO.py:28-117).
+
+File layout: `BLOCK <name>` / count line / one record per line / `ENDBLOCK`, 1-based numbering.  `nodes` records are
+`number x y z`, `tets` records are `number property n1 n2 n3 n4`; `tris` blocks (and anything else) are skipped.  Records
+may come in any order but every number 1..count must appear exactly once.  Tetrahedra are returned with ascending
+node numbers (UFC order).  Each block is parsed as one numpy table.
+"""
 import os
-import re
 
 import numpy as N
 
@@ -12,87 +16,81 @@ class UninitialisedException(Exception):
     pass
 
 
-def uninit_error(fn):
-    def check_fn(self):
-        try:
-            return fn(self)
-        except AttributeError:
-            raise Exception("Call read_meshfile() method of %s first" % self.__class__)
-    return check_fn
+def _blocks(lines):
+    """{block name: list of record lines} for every BLOCK ... ENDBLOCK section."""
+    out, name, body = {}, None, []
+    for raw in lines:
+        l = raw.strip()
+        if name is None:
+            if l.startswith('BLOCK '):
+                name, body = l[len('BLOCK '):].strip(), []
+        elif l.split()[:1] == ['ENDBLOCK']:
+            out[name] = body
+            name = None
+        elif l:
+            body.append(l)
+    if name is not None:
+        raise ValueError('BLOCK %s is not closed by ENDBLOCK' % name)
+    return out
+
+
+def _table(body, n_columns, what):
+    """The block's records as a float table ordered by record number (0-based row = number - 1)."""
+    count = int(body[0].split()[0])
+    tab = N.array([l.split() for l in body[1:]], dtype=N.float64).reshape(-1, n_columns)
+    if len(tab) != count:
+        raise AssertionError('%s block announces %d records and holds %d' % (what, count, len(tab)))
+    number = tab[:, 0].astype(N.int64) - 1
+    if count and not N.array_equal(N.sort(number), N.arange(count)):
+        raise AssertionError('%s numbers must be exactly 1..%d' % (what, count))
+    ordered = N.empty_like(tab)
+    ordered[number] = tab
+    return ordered
 
 
 class FemmeshReader(object):
-    block_start_re = re.compile(r'^BLOCK (.*)')
     read = False
+    _DATA = ('nodes', 'tet_nodes', 'tet_property_nos')
 
     def __init__(self, mesh_filename):
         self.mesh_filename = mesh_filename
-        self.block_parse_funs = dict(nodes=self.parse_nodes, tets=self.parse_tets, tris=lambda *x: None)
-
-    def parse_nodes(self, it):
-        self.no_nodes = int(next(it).split()[0])
-        node_check = set(range(self.no_nodes))
-        self.nodes = N.zeros((self.no_nodes, 3))
-        for i in range(self.no_nodes):
-            sp = next(it).split()
-            node_no = int(sp[0]) - 1
-            assert node_no >= 0 and node_no < self.no_nodes
-            self.nodes[node_no] = [float(x) for x in sp[1:]]
-            node_check.discard(node_no)
-        assert next(it).split()[0] == 'ENDBLOCK'
-        assert len(node_check) == 0
-
-    def parse_tets(self, it):
-        self.no_tets = int(next(it).split()[0])
-        tet_check = set(range(self.no_tets))
-        self.tet_nodes = N.zeros((self.no_tets, 4), dtype=N.int32)
-        self.tet_property_nos = N.zeros(self.no_tets, dtype=N.int32)
-        for i in range(self.no_tets):
-            sp = next(it).split()
-            tet_no = int(sp[0]) - 1
-            assert tet_no >= 0 and tet_no < self.no_tets
-            self.tet_property_nos[tet_no] = int(sp[1])
-            self.tet_nodes[tet_no] = sorted([int(x) - 1 for x in sp[2:]])
-            tet_check.discard(tet_no)
-        assert next(it).split()[0] == 'ENDBLOCK'
-        assert len(tet_check) == 0
-
-    def find_block_fun(self, l):
-        block_match = self.block_start_re.match(l)
-        if not block_match:
-            return None
-        return self.block_parse_funs[block_match.groups()[0].strip()]
 
     def read_meshfile(self):
         with open(self.mesh_filename) as fo:
-            for l in fo:
-                bfun = self.find_block_fun(l)
-                if bfun:
-                    bfun(fo)
+            blocks = _blocks(fo)
+        if 'nodes' in blocks:
+            t = _table(blocks['nodes'], 4, 'nodes')
+            self.no_nodes, self.nodes = len(t), N.ascontiguousarray(t[:, 1:4])
+        if 'tets' in blocks:
+            t = _table(blocks['tets'], 6, 'tets')
+            self.no_tets = len(t)
+            self.tet_property_nos = t[:, 1].astype(N.int32)
+            self.tet_nodes = N.sort(t[:, 2:6].astype(N.int32) - 1, axis=1)
         self.read = True
 
-    @uninit_error
+    def _need(self, name):
+        if not hasattr(self, name):
+            raise Exception("Call read_meshfile() method of %s first" % self.__class__)
+        return getattr(self, name)
+
     def get_mesh_filename(self):
+        self._need('nodes')
         return os.path.basename(self.mesh_filename)
 
-    @uninit_error
     def get_mesh_dirname(self):
+        self._need('nodes')
         return os.path.dirname(self.mesh_filename)
 
-    @uninit_error
     def get_tet_nodes(self):
-        return self.tet_nodes
+        return self._need('tet_nodes')
 
-    @uninit_error
     def get_tet_property_nos(self):
-        return self.tet_property_nos
+        return self._need('tet_property_nos')
 
-    @uninit_error
     def get_nodes(self):
-        return self.nodes
+        return self._need('nodes')
 
 
 def femmesh_2_dolfin_mesh(femmesh_file):
     """Convert a femmesh file to a mesh object"""
-    femmesh_reader = FemmeshReader(femmesh_file)
-    return MeshConverters.femmesh_reader_2_dolfin_mesh(femmesh_reader)
+    return MeshConverters.femmesh_reader_2_dolfin_mesh(FemmeshReader(femmesh_file))
