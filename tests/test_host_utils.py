@@ -3,6 +3,8 @@ matrices.  Bodies follow the reference's tests (file:line in the docstrings)."""
 import os
 
 import numpy as np
+
+from conftest import GOLDEN
 import scipy.sparse
 
 
@@ -116,6 +118,12 @@ class _HostSpace(object):
     def cell_dofs_array(self):
         return self._cd
 
+    def geometry(self):
+        return self
+
+    def dim(self):
+        return self._co.shape[1]
+
 
 def _interpolate_order2(V, u):
     """Nodal dofs of a vector field u(x) in the order-2 N1curl space (SURVEY 8.1-B functionals)."""
@@ -182,3 +190,37 @@ def test_small_example_helpers():
     Optimization.set_dolfin_optimisation(False)
     assert Optimization.parameters['form_compiler'] == {'optimize': False, 'cpp_optimize': False}
     Optimization.set_dolfin_optimisation()
+
+
+def test_sources_on_host_match_oracle_and_reference_fixture():
+    """The product's sources (Sources.point_source / fillament_current_source: generated basis polynomials, covariant
+    Piola map, lowest-cell point location) against the oracle's independent basis on a jittered mesh at orders 1 and 2,
+    and against the reference's filament fixture (sucemfem/Sources/tests/test_fillament_source.py:62-69) -- on the CPU,
+    with the dof map taken from the oracle instead of the device."""
+    from oracle import fem, meshes
+    from sucemfem.Sources.point_source import calc_pointsource_contrib
+    from sucemfem.Sources.fillament_current_source import FillamentCurrentSource
+    co, ce = meshes.unit_cube(3)
+    rng = np.random.default_rng(2)
+    co = co + 0.03 * rng.standard_normal(co.shape)
+    for order in (1, 2):
+        V = _HostSpace(co, ce, order)
+        for pt in (np.array([0.31, 0.52, 0.47]), np.array([0.8, 0.15, 0.66])):
+            val = np.array([0.3, -1.2, 2.0])
+            dn, v = calc_pointsource_contrib(V, pt, val)
+            dn_o, v_o = fem.point_source_contrib(co, ce, V._cd, order, pt, val)
+            assert np.array_equal(dn, dn_o) and np.allclose(v, v_o, rtol=1e-12, atol=1e-14)
+    # the reference's own filament fixture (order 2, get_centred_cube mesh)
+    g = np.load(os.path.join(GOLDEN, 'fillament_source_order2.npz'))
+    co, ce = meshes.centred_cube(g['domain_size'], float(g['max_edge_len']))
+    V = _HostSpace(co, ce, int(g['order']))
+    src = FillamentCurrentSource()
+    src.set_function_space(V)
+    src.set_no_integration_points(int(g['no_integration_points']))
+    src.set_source_endpoints(np.asarray(g['source_endpoints']))
+    src.set_value(float(g['I']))
+    dn, v = src.get_contribution()
+    big = np.abs(g['rhs_contribs']) > 1e-12        # the other 48 stored dofs carry round-off only (SURVEY 8.2 f2)
+    got = dict(zip(np.asarray(dn).tolist(), v))
+    assert big.sum() == 26
+    assert all(np.isclose(got[int(d)], x, rtol=1e-10, atol=1e-12) for d, x in zip(g['dofnos'][big], g['rhs_contribs'][big]))
