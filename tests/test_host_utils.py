@@ -124,6 +124,28 @@ class _HostSpace(object):
     def dim(self):
         return self._co.shape[1]
 
+    # -- what the O(boundary) surface functionals ask of V.device_space (PostProcessing/_facets.py) ---------------
+    @property
+    def device_space(self):
+        return _HostDeviceSpace(self)
+
+
+class _HostDeviceSpace(object):
+    def __init__(self, V):
+        self._V = V
+        self.n_facets = V.num['F']
+        self.mesh = type('M', (), {'device': 'cpu'})()
+
+    def cell_entities(self):
+        import torch
+        return torch.from_numpy(self._V.num['cell_edges']), torch.from_numpy(self._V.num['cell_faces'])
+
+    def mark_exterior_facets(self, markers, value):
+        import torch
+        from oracle import fem
+        markers[torch.from_numpy(fem.exterior_facet_mask(self._V._ce, self._V.num))] = value
+        return markers
+
 
 def _interpolate_order2(V, u):
     """Nodal dofs of a vector field u(x) in the order-2 N1curl space (SURVEY 8.1-B functionals)."""
@@ -224,3 +246,27 @@ def test_sources_on_host_match_oracle_and_reference_fixture():
     got = dict(zip(np.asarray(dn).tolist(), v))
     assert big.sum() == 26
     assert all(np.isclose(got[int(d)], x, rtol=1e-10, atol=1e-12) for d, x in zip(g['dofnos'][big], g['rhs_contribs'][big]))
+
+
+def test_surface_functionals_on_host_known_answers():
+    """The O(boundary) host functionals on the CPU (numbering from the oracle instead of the device):
+    SurfaceFlux = 26.3586862457 (/root/reference/sucemfem/PostProcessing/tests/test_power_flux.py:35-55) and the surface
+    NTFF at the reference's six directions (test_ntff.py:80-110, rtol=1e-12, atol=1e-7)."""
+    from oracle import meshes
+    from sucemfem.PostProcessing import power_flux, surface_ntff
+    c0 = 299792458
+    g = np.load(os.path.join(GOLDEN, 'driven_order2_unitcube3.npz'))
+    V = _HostSpace(g['mesh_coordinates'], g['mesh_cells'], int(g['order']))
+    DUT = power_flux.SurfaceFlux(V)
+    DUT.set_k0(2 * np.pi * float(g['freq']) / c0)
+    DUT.set_dofs(g['x'])
+    assert abs(DUT.calc_flux() - float(g['known_answer_surface_flux'])) < 5e-8
+    g = np.load(os.path.join(GOLDEN, 'ntff_order2_unitcube5.npz'))
+    x = np.load(os.path.join(GOLDEN, 'driven_order2_unitcube5.npz'))['x']
+    co, ce = meshes.centred_cube(g['domain_size'], float(g['max_edge_len']))
+    V = _HostSpace(co, ce, int(g['order']))
+    DUT = surface_ntff.NTFF(V)
+    DUT.set_frequency(float(g['freq']))
+    DUT.set_dofs(x)
+    actual = [DUT.calc_pt(th, ph) for th, ph in zip(g['surface_theta_deg'], g['surface_phi_deg'])]
+    assert np.allclose(actual, g['surface_E_ff'], rtol=1e-12, atol=1e-7)
