@@ -134,3 +134,42 @@ def test_dielectric_loaded_cavity_from_gmsh(tmp_path, name, order):
         rp, cl, v = ep.system_matrices[key].data()
         assert np.array_equal(rp, ref['rowptr']) and np.array_equal(cl, ref['cols'])
         assert np.all(np.abs(v - ref[key]) <= 1e-12 * np.abs(ref[key]) + 1e-15 * np.abs(ref[key]).max())
+
+
+class _OracleNumbering(object):
+    """CPU stand-in for the device numbering behind dolfin_compat.Mesh._numbering() (test of host logic only)."""
+
+    def __init__(self, cells):
+        import torch
+        from oracle import fem
+        num = fem.number_entities(cells)
+        self.n_edges = num['E']
+        self.n_facets = num['F'] if num['dim'] == 3 else num['E']
+        ce = torch.from_numpy(num['cell_edges'])
+        self._ent = (ce, torch.from_numpy(num['cell_faces']) if num['dim'] == 3 else None)
+
+    def cell_entities(self):
+        return self._ent
+
+
+@pytest.mark.parametrize('name', ['sample_mesh', 'patch'])
+def test_convert_writes_the_reference_xml_files_cpu(tmp_path, monkeypatch, name):
+    """GmshIO.convert() end to end on the CPU (the facet numbering comes from the oracle instead of the device): the
+    written mesh / physical_region / facet_region XML files read back as the reference's own files."""
+    from sucemfem.Utilities import GmshIO
+    from sucemfem import dolfin_compat as dolfin
+    monkeypatch.setattr(dolfin.Mesh, '_numbering', lambda self: _OracleNumbering(self.cells()))
+    msh = _msh(tmp_path, name)
+    xml = os.path.join(str(tmp_path), name + '.xml')
+    gm, written = GmshIO.convert(msh, xml)
+    base = os.path.splitext(xml)[0]
+    assert xml in written and base + '_facet_region.xml' in written
+    mesh = dolfin.Mesh(xml)
+    assert np.array_equal(mesh.cells(), GOLD[name + '__cells']) and np.array_equal(mesh.coordinates(), gm.coordinates)
+    mf = dolfin.MeshFunction('uint', mesh, base + '_facet_region.xml')
+    assert mf.dim() == gm.dim - 1 and np.array_equal(mf.array(), GOLD[name + '__facet_region'])
+    if name == 'patch':
+        pf = dolfin.MeshFunction('uint', mesh, base + '_physical_region.xml')
+        assert pf.dim() == 3 and np.array_equal(pf.array(), GOLD[name + '__physical_region'])
+    else:
+        assert base + '_physical_region.xml' not in written or gm.has_physical_regions()
