@@ -31,19 +31,6 @@ cudaError_t dev_malloc_bytes(void** p, size_t bytes, cudaStream_t st) {
 namespace {
 inline unsigned grid_for(int64_t n, int bs = 256) { return (unsigned)((n + bs - 1) / bs); }
 
-struct DeviceGuard {
-  int prev = -1;
-  explicit DeviceGuard(int dev) {
-    cudaGetDevice(&prev);
-    if (prev != dev) cudaSetDevice(dev);
-  }
-  ~DeviceGuard() {
-    int cur = -1;
-    cudaGetDevice(&cur);
-    if (cur != prev && prev >= 0) cudaSetDevice(prev);
-  }
-};
-
 // UnitCube / UnitSquare of DOLFIN 1.0: vertex id = ix + (nx+1) iy + (nx+1)(ny+1) iz; cube
 // (ix,iy,iz), x fastest, emits six tets in a fixed order, each vertex-sorted.
 __global__ void k_fill_coords(int nx, int ny, int nz, double sx, double sy, double sz, double tx, double ty,

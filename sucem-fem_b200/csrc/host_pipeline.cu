@@ -51,19 +51,6 @@ __global__ void k_block_bounds(const int64_t* __restrict__ rowptr_all, const int
   out[3 * p + 2] = inc_ptr[b];
 }
 
-struct DeviceGuard {
-  int prev = -1;
-  explicit DeviceGuard(int dev) {
-    cudaGetDevice(&prev);
-    if (prev != dev) cudaSetDevice(dev);
-  }
-  ~DeviceGuard() {
-    int cur = -1;
-    cudaGetDevice(&cur);
-    if (cur != prev && prev >= 0) cudaSetDevice(prev);
-  }
-};
-
 }  // namespace
 }  // namespace sfem
 

@@ -47,6 +47,21 @@ inline void dev_free(void* p, cudaStream_t st) {
   if (p) cudaFreeAsync(p, st);
 }
 
+// Makes `dev` the current device for the lifetime of the guard (every entry point that launches or allocates runs on
+// the device its handle was created on, whatever the caller's current device is).
+struct DeviceGuard {
+  int prev = -1;
+  explicit DeviceGuard(int dev) {
+    cudaGetDevice(&prev);
+    if (prev != dev) cudaSetDevice(dev);
+  }
+  ~DeviceGuard() {
+    int cur = -1;
+    cudaGetDevice(&cur);
+    if (cur != prev && prev >= 0) cudaSetDevice(prev);
+  }
+};
+
 // Local topology of the UFC reference cells.
 // tet edges e0=(2,3) e1=(1,3) e2=(1,2) e3=(0,3) e4=(0,2) e5=(0,1); faces f_i opposite v_i
 // triangle edges e_i opposite v_i

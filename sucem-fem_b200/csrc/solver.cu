@@ -322,6 +322,7 @@ extern "C" {
 int sfem_matvec(sfem_pattern_t pat, int n_mats, const double* const* d_values, const double* coef_re_im,
                 int complex_vectors, const double* d_x, double* d_y, void* stream) {
   SFEM_CHECK(pat && d_values && d_x && d_y, "NULL argument");
+  DeviceGuard dg(pat->device);
   MatvecArgs a;
   SFEM_TRY(fill_args(pat, n_mats, d_values, coef_re_im, &a));
   if (!complex_vectors)
@@ -335,6 +336,7 @@ int sfem_bicgstab(sfem_pattern_t pat, int n_mats, const double* const* d_values,
   SFEM_CHECK(pat && d_values && d_b && d_x, "NULL argument");
   SFEM_CHECK(pat->ent_lo == 0 && pat->ent_hi == pat->space->n_ent, "the solver needs the pattern of all rows");
   SFEM_CHECK(preconditioner == 0 || preconditioner == 1, "preconditioner: 0 none, 1 diagonal");
+  DeviceGuard dg(pat->device);
   cudaStream_t st = (cudaStream_t)stream;
   MatvecArgs a;
   SFEM_TRY(fill_args(pat, n_mats, d_values, coef_re_im, &a));
@@ -413,11 +415,13 @@ int sfem_bicgstab(sfem_pattern_t pat, int n_mats, const double* const* d_values,
       if ((rc = matvec(shat, t)) != 0) break;
       cplx_t ts, tt;
       if ((rc = dots(t, s, t, t, &ts, &tt)) != 0) break;
+      if (tt.real() == 0.0 || !std::isfinite(tt.real()) || !std::isfinite(std::abs(ts))) { rc = -11; break; }
       omega = ts / tt;
       k_update_xr<<<g, 256, 0, st>>>(x, phat, shat, r, s, t, d2(alpha), d2(omega), n);
       rho = rho_new;
       if ((rc = dots(r, r, nullptr, nullptr, &rr, nullptr)) != 0) break;
       res = std::sqrt(rr.real());
+      if (!std::isfinite(res)) { rc = -11; break; }  // NaN / Inf: no later `res <= target` test could ever succeed
       if (res <= target) break;
     }
   } while (false);

@@ -1,5 +1,8 @@
 """Boundary condition base class with nil contributions
 (mirror of /root/reference/sucemfem/BoundaryConditions/base_boundary_condition.py:24-112)."""
+# Interface (module, class, method and argument names) after the file of cemagg/sucem-fem cited above:
+# Copyright (C) 2011 Stellenbosch University, authors Neilen Marais, Evan Lezar; GNU GPL v3 or later
+# (see NOTICE.md at the repository root).  The implementation below is this repository's own.
 from .. import Forms
 
 

@@ -1,4 +1,7 @@
 """Collection of boundary conditions (mirror of /root/reference/sucemfem/BoundaryConditions/container.py:24-69)."""
+# Interface (module, class, method and argument names) after the file of cemagg/sucem-fem cited above:
+# Copyright (C) 2011 Stellenbosch University, authors Neilen Marais; GNU GPL v3 or later
+# (see NOTICE.md at the repository root).  The implementation below is this repository's own.
 from .. import Forms
 
 

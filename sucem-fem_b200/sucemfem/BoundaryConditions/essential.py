@@ -6,6 +6,9 @@ here the constrained dofs (closure of the marked facets) are flagged on the devi
 either as a separate step (apply) or fused into the value kernels (SystemMatrices).  Only the zero boundary value
 (PEC) acts on matrices, which is all the matrix path of the reference uses.
 """
+# Interface (module, class, method and argument names) after the file of cemagg/sucem-fem cited above:
+# Copyright (C) 2011 Stellenbosch University, authors Neilen Marais, Evan Lezar; GNU GPL v3 or later
+# (see NOTICE.md at the repository root).  The implementation below is this repository's own.
 import numpy as np
 import torch
 

@@ -1,4 +1,7 @@
 """Physical constants (mirror of /root/reference/sucemfem/Consts.py:27-31; the values are definitions)."""
+# Interface (module, class, method and argument names) after the file of cemagg/sucem-fem cited above:
+# Copyright (C) 2011 Stellenbosch University, authors Neilen Marais; GNU GPL v3 or later
+# (see NOTICE.md at the repository root).  The implementation below is this repository's own.
 import numpy as N
 
 pi = N.pi

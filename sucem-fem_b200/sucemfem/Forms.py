@@ -4,6 +4,9 @@ The reference builds UFL expressions that FFC compiles; here a bilinear form is 
 {kind, function_space, coefficient} that sucemfem.dolfin_compat.assemble / SystemMatrices hand to the CUDA
 kernels.  NullForm is the additive identity, as in the reference.
 """
+# Interface (module, class, method and argument names) after the file of cemagg/sucem-fem cited above:
+# Copyright (C) 2011 Stellenbosch University, authors Neilen Marais; GNU GPL v3 or later
+# (see NOTICE.md at the repository root).  The implementation below is this repository's own.
 
 
 class NullForm(object):

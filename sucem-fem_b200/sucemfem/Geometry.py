@@ -1,6 +1,9 @@
 """Mesh-entity marking helpers (mirror of /root/reference/sucemfem/Geometry.py:24-118): boundary edges and the cells
 connected to them.  The reference walks DOLFIN's connectivity with Python iterators; here the entity numbering comes
 from the device (K1) and the marking is a couple of array operations."""
+# Interface (module, class, method and argument names) after the file of cemagg/sucem-fem cited above:
+# Copyright (C) 2011 Stellenbosch University, authors Neilen Marais; GNU GPL v3 or later
+# (see NOTICE.md at the repository root).  The implementation below is this repository's own.
 import numpy as np
 import torch
 

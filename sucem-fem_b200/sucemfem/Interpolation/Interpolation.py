@@ -5,6 +5,9 @@ dof functionals on the expression for every dof in the closure of an exterior fa
 un-normalised tangential point evaluations of SURVEY 8.1-B: edge (a<b), k = 0,1: u(x_a + (k+1)/3 (x_b - x_a)).(x_b - x_a)
 (order 1: the mid point); face (a<b<c), k = 0,1: u(centroid).t_k, t_0 = x_b - x_a, t_1 = x_c - x_a.
 """
+# Interface (module, class, method and argument names) after the file of cemagg/sucem-fem cited above:
+# Copyright (C) 2011 Stellenbosch University, authors Neilen Marais; GNU GPL v3 or later
+# (see NOTICE.md at the repository root).  The implementation below is this repository's own.
 import numpy as np
 import torch
 

@@ -3,6 +3,9 @@
 The reference expands region numbers with a Python list comprehension over all cells (Materials.py:145-146); here
 the look-up runs on the device (sfem_expand_material) and the result stays in HBM for the assembly kernels.
 """
+# Interface (module, class, method and argument names) after the file of cemagg/sucem-fem cited above:
+# Copyright (C) 2011 Stellenbosch University, authors Neilen Marais; GNU GPL v3 or later
+# (see NOTICE.md at the repository root).  The implementation below is this repository's own.
 import numpy as np
 import torch
 

@@ -5,6 +5,9 @@ reference assembles two scalar UFL forms; here the functional is g^T (S_dom - k0
 same device kernels as the system matrices (coefficients masked to the sub-domain) and the product taken by the fused
 two-matrix SpMV (sfem_matvec) -- SURVEY 8.2 row f4.
 """
+# Interface (module, class, method and argument names) after the file of cemagg/sucem-fem cited above:
+# Copyright (C) 2011 Stellenbosch University, authors Neilen Marais; GNU GPL v3 or later
+# (see NOTICE.md at the repository root).  The implementation below is this repository's own.
 import numpy as N
 import torch
 

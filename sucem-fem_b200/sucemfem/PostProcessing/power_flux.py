@@ -4,6 +4,9 @@ SurfaceFlux integrates the Poynting vector over the exterior facets (host, O(bou
 generated nodal polynomials); VariationalSurfaceFlux evaluates the same quantity through the EM functional over the skin
 of cells connected to the boundary (device matrices + SpMV, see PostProcessing.CalcEMFunctional).
 """
+# Interface (module, class, method and argument names) after the file of cemagg/sucem-fem cited above:
+# Copyright (C) 2011 Stellenbosch University, authors Neilen Marais; GNU GPL v3 or later
+# (see NOTICE.md at the repository root).  The implementation below is this repository's own.
 import numpy as np
 import torch
 

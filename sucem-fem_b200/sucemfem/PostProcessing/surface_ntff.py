@@ -5,6 +5,9 @@ N = int n x H e^{j k0 r'.rhat} ds,  L = -int n x E e^{j k0 r'.rhat} ds,  H = j c
 Host evaluation over the exterior facets (O(boundary) work) with a collapsed Gauss-Jacobi rule; the integrand is not
 polynomial, the default rule (6 x 6 points) reproduces the reference's shipped far fields to 2e-8.
 """
+# Interface (module, class, method and argument names) after the file of cemagg/sucem-fem cited above:
+# Copyright (C) 2011 Stellenbosch University, authors Neilen Marais; GNU GPL v3 or later
+# (see NOTICE.md at the repository root).  The implementation below is this repository's own.
 import numpy as np
 
 from ..Consts import Z0, c0

@@ -2,6 +2,9 @@
 the H-field contribution comes from the EM functional g^T (S - k0^2 M) E over the skin of boundary cells (device
 matrices + fused SpMV, see CalcEMFunctional) with g the boundary interpolant of 1j/k0 rhat x (ahat x rhat) e^{j k0 rhat.r'};
 the E-field contribution (L) from the surface integral."""
+# Interface (module, class, method and argument names) after the file of cemagg/sucem-fem cited above:
+# Copyright (C) 2011 Stellenbosch University, authors Neilen Marais; GNU GPL v3 or later
+# (see NOTICE.md at the repository root).  The implementation below is this repository's own.
 import numpy as np
 
 from ..Consts import c0

@@ -1,6 +1,9 @@
 """Driven problem terminated by a first-order ABC
 (mirror of /root/reference/sucemfem/ProblemConfigurations/EMDrivenProblem.py:33-91):
 A = S - k0**2*M + 1j*k0*S_0."""
+# Interface (module, class, method and argument names) after the file of cemagg/sucem-fem cited above:
+# Copyright (C) 2011 Stellenbosch University, authors Neilen Marais; GNU GPL v3 or later
+# (see NOTICE.md at the repository root).  The implementation below is this repository's own.
 import numpy as N
 
 from .. import Forms

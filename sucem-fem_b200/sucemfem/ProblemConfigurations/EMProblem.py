@@ -1,5 +1,8 @@
 """Base class wiring mesh, order, materials, boundary conditions and the system matrices
 (mirror of /root/reference/sucemfem/ProblemConfigurations/EMProblem.py:31-145)."""
+# Interface (module, class, method and argument names) after the file of cemagg/sucem-fem cited above:
+# Copyright (C) 2011 Stellenbosch University, authors Neilen Marais, Evan Lezar; GNU GPL v3 or later
+# (see NOTICE.md at the repository root).  The implementation below is this repository's own.
 from .. import Forms
 from .. import Materials
 from .. import SystemMatrices

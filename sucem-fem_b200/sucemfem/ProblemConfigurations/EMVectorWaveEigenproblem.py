@@ -7,6 +7,9 @@ reference passes an already shift-inverted operator to ARPACK's shift-invert mod
 k^2 > sigma closest to sigma and returns them shifted (its example scripts undo the shift by hand,
 /root/reference/examples/resonant_cavity/driver.py:66); solve_problem() here returns k^2 itself, the convention of
 /root/reference/functional_tests/test_EigenProblems.py:104."""
+# Interface (module, class, method and argument names) after the file of cemagg/sucem-fem cited above:
+# Copyright (C) 2011 Stellenbosch University, authors Neilen Marais; GNU GPL v3 or later
+# (see NOTICE.md at the repository root).  The implementation below is this repository's own.
 import numpy as np
 
 from .. import Forms

@@ -6,6 +6,9 @@ functions at the point.  Here the dofs come from the device dof map (sfem_space_
 the host from the generated nodal-basis polynomials (sucemfem/_generated_basis.py, tools/gen_tables.py) with the
 covariant Piola map phi = J^-T phihat.  Sources are O(#points) work and outside the assembly hot path.
 """
+# Interface (module, class, method and argument names) after the file of cemagg/sucem-fem cited above:
+# Copyright (C) 2011 Stellenbosch University, authors Neilen Marais; GNU GPL v3 or later
+# (see NOTICE.md at the repository root).  The implementation below is this repository's own.
 import numpy as N
 
 from .current_source import CurrentSource

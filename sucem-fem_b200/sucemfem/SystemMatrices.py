@@ -5,6 +5,9 @@ MatrixClass() instance assembled from the form with the essential boundary condi
 mass and the stiffness form of one function space are requested it fills them with ONE fused launch of the S+T
 kernels, PEC rows included, instead of two assemblies followed by two ident passes.
 """
+# Interface (module, class, method and argument names) after the file of cemagg/sucem-fem cited above:
+# Copyright (C) 2011 Stellenbosch University, authors Neilen Marais; GNU GPL v3 or later
+# (see NOTICE.md at the repository root).  The implementation below is this repository's own.
 from . import Forms
 from . import dolfin_compat as dolfin
 from . import _native as N

@@ -1,4 +1,7 @@
 """Matrix converters (mirror of /root/reference/sucemfem/Utilities/Converters.py:27-52)."""
+# Interface (module, class, method and argument names) after the file of cemagg/sucem-fem cited above:
+# Copyright (C) 2011 Stellenbosch University, authors Evan Lezar; GNU GPL v3 or later
+# (see NOTICE.md at the repository root).  The implementation below is this repository's own.
 import numpy as np
 
 

@@ -6,6 +6,9 @@ Same classes, methods and logging as the reference.  The system matrix may be
     preconditioner or the reference's 'diagonal' one); or
   * a scipy sparse matrix (what get_LHS_matrix() returns): the solvers call scipy exactly as the reference does.
 """
+# Interface (module, class, method and argument names) after the file of cemagg/sucem-fem cited above:
+# Copyright (C) 2011 Stellenbosch University, authors Evan Lezar, Neilen Marais; GNU GPL v3 or later
+# (see NOTICE.md at the repository root).  The implementation below is this repository's own.
 from time import time
 
 import numpy as np
@@ -36,8 +39,8 @@ class SystemSolverBase(object):
 
     def _callback(self, xk):
         self._callback_count += 1
-        if type(xk) is float:
-            res = xk
+        if np.ndim(xk) == 0:      # GMRES hands its callback the (preconditioned, relative) residual norm, not x_k
+            res = float(xk)
         else:
             res = calculate_residual(self._A, xk, self._b)
         self._timestamp(self._callback_count, res=res)
@@ -97,6 +100,26 @@ class SystemSolverBase(object):
             print(k)
             print(self._logging_data[k])
 
+    def plot_convergence(self, x_is_time=False, show_plot=False, label=None, style='-'):
+        """Residual history against the iteration number or the elapsed time (LinalgSolvers.py:192-236); returns the
+        (x, residual) arrays it plots, so it is usable without a display."""
+        ids, res, t = self._logging_data['id'], self._logging_data['res'], self._logging_data['time']
+        keep = [i for i, k in enumerate(ids) if isinstance(k, (int, np.integer))]
+        x = np.array([t[i] - t[0] for i in keep]) if x_is_time else np.array([ids[i] for i in keep])
+        y = np.array([res[i] for i in keep])
+        try:
+            import matplotlib.pyplot as plt
+            plt.semilogy(x, y, style, label=label)
+            plt.xlabel('time (s)' if x_is_time else 'iteration')
+            plt.ylabel('residual')
+            if label:
+                plt.legend()
+            if show_plot:
+                plt.show()
+        except ImportError:
+            pass
+        return x, y
+
     def print_timing_info(self):
         print('solve time:', self._get_elapsed_time('solve::begin', 'solve::end'))
         print('preconditioner time:', self._get_elapsed_time('preconditioner::start', 'preconditioner::end'))
@@ -125,7 +148,7 @@ class GMRESSolver(SystemSolverBase):
 
     def _call_solver(self):
         A = self._A.to_scipy() if self._on_device else self._A
-        return scipy.sparse.linalg.gmres(A, self._b, M=self._M, callback=self._callback)
+        return scipy.sparse.linalg.gmres(A, self._b, M=self._M, callback=self._callback, callback_type='pr_norm')
 
 
 class UMFPACKSolver(SystemSolverBase):

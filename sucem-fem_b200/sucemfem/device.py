@@ -253,7 +253,7 @@ class DevicePattern(object):
             flat += [complex(c).real, complex(c).imag]
         co = (C.c_double * len(flat))(*flat)
         pre = {None: 0, 'none': 0, 'diagonal': 1}[preconditioner.lower() if isinstance(preconditioner, str) else None]
-        maxiter = 10 * self.space.ndof if maxiter is None else int(maxiter)      # scipy's default
+        maxiter = min(10 * self.space.ndof if maxiter is None else int(maxiter), 2 ** 31 - 1)   # scipy's default; c_int
         it, rr = C.c_int(0), C.c_double(0.0)
         with torch.cuda.device(dev):
             rc = N.lib.sfem_bicgstab(self.handle, len(values), vp, co, _ptr(b), _ptr(x), pre, float(rtol), maxiter,

@@ -17,10 +17,10 @@ def test_get_LHS_matrix_reference_fixture():
     InscribedTet with a first-order ABC at 1e8 Hz; the dense LHS must match LHS_matrix.npy with the reference's own
     tolerance rtol=1e-10, atol=3e-15."""
     from sucemfem import dolfin_compat as dolfin
-    from sucemfem.Testing import Meshes
+    from oracle import meshes as omeshes
     from sucemfem.BoundaryConditions import ABCBoundaryCondition, BoundaryConditions
     from sucemfem.ProblemConfigurations import EMDrivenProblem
-    mesh = Meshes.InscribedTet().get_dolfin_mesh()
+    mesh = dolfin.Mesh(coordinates=omeshes.inscribed_tet()[0], cells=omeshes.inscribed_tet()[1])
     material_mesh_func = dolfin.MeshFunction('uint', mesh, 3)
     material_mesh_func.set_all(0)
     materials = {0: dict(eps_r=1, mu_r=1)}
@@ -279,7 +279,7 @@ def _driven_problem(mesh, order, sources, freq):
 def test_get_RHS_reference_fixture():
     """/root/reference/sucemfem/ProblemConfigurations/tests/test_EMDrivenProblem.py:74-82: point dipole [2,-1,3] at the
     origin of InscribedTet, order 1; RHS vs RHS_vector.pickle with the reference's rtol=1e-12, atol=1e-16."""
-    from sucemfem.Testing import Meshes
+    from oracle import meshes as omeshes
     from sucemfem.Sources import point_source, current_source
     g = np.load(os.path.join(GOLDEN, 'driven_order1_inscribedtet.npz'))
     srcs = current_source.CurrentSources()
@@ -287,7 +287,9 @@ def test_get_RHS_reference_fixture():
     dipole.set_position(np.array([0, 0, 0.]))
     dipole.set_value(np.array([2, -1, 3.]))
     srcs.add_source(dipole)
-    dp = _driven_problem(Meshes.InscribedTet().get_dolfin_mesh(), 1, srcs, 1e8)
+    from sucemfem import dolfin_compat as dolfin
+    co, ce = omeshes.inscribed_tet()
+    dp = _driven_problem(dolfin.Mesh(coordinates=co, cells=ce), 1, srcs, 1e8)
     assert np.allclose(dp.get_RHS(), g['RHS'], rtol=1e-12, atol=1e-16)
 
 
