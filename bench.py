@@ -169,6 +169,9 @@ def main():
     ap.add_argument('--order', type=int, default=2, help='basis order (debug; the bench line is order 2)')
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--no-cpu', action='store_true')
+    ap.add_argument('--check', dest='check', action='store_true', default=True,
+                    help='after the timed region compare sampled rows of the timed matrices with the CPU oracle (default)')
+    ap.add_argument('--no-check', dest='check', action='store_false')
     args = ap.parse_args()
     if args.impl == 'reference':
         return run_reference(args)
@@ -282,6 +285,10 @@ def main():
             "setup_ms": setup_ms, "roofline": roofline, "gpu_launches": None,
             "per_rank_ms_per_step": [round(x, 3) for x in per_rank_ms]}
 
+    # ---- correctness of what was just timed: sampled rows of S and T of every block of this rank vs the CPU oracle ----
+    if args.check and args.order == 2:
+        line.update(check_timed_matrices(n, space, pats, vals, flags, eps, mu, rank, world))
+
     # ---- e2e through the public API with HOST buffers (rank-local; N=1 only measures the full pipeline) ---
     if not args.no_e2e:
         line["gpu_launches"] = sum(launches_per_step(kernel, pat) for pat in pats) * K
@@ -325,6 +332,51 @@ def main():
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def check_timed_matrices(n, space, pats, vals, flags, eps, mu, rank, world):
+    """--check (default): the S and T arrays the timed loop left behind are compared, for a sample of rows of every row
+    block of this rank (head, tail, the rows around every multiple of 2^28 in the value index -- the 2^31 / 2^32
+    offsets -- and random ones), with the reference algorithm run on the host for exactly those rows (oracle/rowcheck.py;
+    the oracle is the checker here, never the thing measured).  Pattern columns bit-exact, values to 1e-12 relative.
+    Returns {"checked": bool, "check": {...}}; with N > 1 `checked` is the AND over all ranks."""
+    import torch
+    import torch.distributed as dist
+    t0 = time.perf_counter()
+    info = {"rows": 0, "entries": 0, "max_rel_err": 0.0}
+    ok, err = True, None
+    try:
+        from oracle import rowcheck
+        orc = rowcheck.CubeOracle(n)
+        assert (orc.E, orc.F) == (space.n_edges, space.n_faces), 'entity counts differ'
+        h_eps, h_mu = eps.cpu().numpy(), mu.cpu().numpy()
+        for k, (pat, (S, T)) in enumerate(zip(pats, vals)):
+            rowptr, cols = pat.csr()
+            r = rowcheck.check_block(orc, rowptr, cols, S, T, pat.row_begin, pat.n_rows, pat.nnz, flags, h_eps, h_mu,
+                                     20000 // len(pats), 'rank %d block %d' % (rank, k), seed=rank)
+            info["rows"] += r["rows"]
+            info["entries"] += r["entries"]
+            info["max_rel_err"] = max(info["max_rel_err"], r["max_rel_err"])
+            pat._csr = None
+            del rowptr, cols
+    except AssertionError as e:
+        ok, err = False, str(e)[:300]
+    if world > 1:
+        t = torch.tensor([1.0 if ok else 0.0, float(info["rows"]), float(info["entries"])], dtype=torch.float64, device='cuda')
+        mx = torch.tensor([info["max_rel_err"]], dtype=torch.float64, device='cuda')
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        tmin = t[:1].clone()
+        dist.all_reduce(tmin, op=dist.ReduceOp.MIN)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        ok = float(tmin.item()) == 1.0
+        info = {"rows": int(t[1].item()), "entries": int(t[2].item()), "max_rel_err": float(mx.item())}
+    info.update({"rtol": 1e-12, "pattern": "bit-exact", "seconds": round(time.perf_counter() - t0, 1),
+                 "what": "sampled rows of the timed S and T (all blocks of all ranks) vs oracle/cpu_assemble.c:oc_assemble_rows "
+                         "on the oracle's own first-appearance numbering; rows at head, tail, around every 2^28-th value "
+                         "index and random"})
+    if err:
+        info["error"] = err
+    return {"checked": ok, "check": info}
 
 
 def host_memory_available():

@@ -235,6 +235,187 @@ void oc_apply_ident(const int64_t* rowptr, const int32_t* cols, double* vals, co
   }
 }
 
+/* ---- first-appearance numbering in ONE serial pass with a hash map ---------------------------------------------
+ * What DOLFIN 1.0's TopologyComputation does when FunctionSpace triggers mesh.init(d)
+ * (/root/reference/sucemfem/ProblemConfigurations/EMProblem.py:100-105): visit the cells in index order
+ * and, within a cell, the local entities in UFC order; an entity that has not been seen yet gets the next number.
+ * Same result as oc_number_entities (sort-based), O(C) time: the oracle for bench-size meshes (10^7..10^8 cells). */
+typedef struct { int64_t k0; int32_t k1; int32_t val; } hslot_t;
+
+static inline uint64_t mix64(uint64_t x) {
+  x ^= x >> 33; x *= 0xff51afd7ed558ccdULL; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ULL; x ^= x >> 33;
+  return x;
+}
+
+static int64_t number_class_hash(const int32_t* cells, int64_t C, int nloc, int nvk, const int* topo, int64_t V,
+                                 int64_t expected, int32_t* out) {
+  uint64_t cap = 1; while ((int64_t)cap < 2 * expected + 16) cap <<= 1;
+  hslot_t* tab = (hslot_t*)malloc(sizeof(hslot_t) * cap);
+  if (!tab) return -1;
+  for (uint64_t i = 0; i < cap; ++i) tab[i].val = -1;
+  int64_t next = 0;
+  for (int64_t c = 0; c < C; ++c) {
+    const int32_t* cv = cells + c * 4;
+    for (int l = 0; l < nloc; ++l) {
+      const int64_t k0 = (int64_t)cv[topo[l * nvk]] * V + cv[topo[l * nvk + 1]];
+      const int32_t k1 = nvk == 3 ? cv[topo[l * nvk + 2]] : 0;
+      uint64_t h = mix64((uint64_t)k0 * 0x9e3779b97f4a7c15ULL + (uint64_t)(uint32_t)k1) & (cap - 1);
+      while (tab[h].val >= 0 && !(tab[h].k0 == k0 && tab[h].k1 == k1)) h = (h + 1) & (cap - 1);
+      if (tab[h].val < 0) {
+        if (next >= (int64_t)(cap >> 1) + (int64_t)(cap >> 2)) { free(tab); return -2; }  /* expected was too small */
+        tab[h].k0 = k0; tab[h].k1 = k1; tab[h].val = (int32_t)next++;
+      }
+      out[c * nloc + l] = tab[h].val;
+    }
+  }
+  free(tab);
+  return next;
+}
+
+/* expected_edges / expected_faces: upper estimates of the entity counts (<= 0: 6 C / 4 C, always enough) */
+int oc_number_entities_hash(const int32_t* cells, int64_t C, int64_t V, int64_t expected_edges, int64_t expected_faces,
+                            int32_t* cell_edges, int32_t* cell_faces, int64_t* nE, int64_t* nF) {
+  *nE = number_class_hash(cells, C, 6, 2, &TET_EDGES[0][0], V, expected_edges > 0 ? expected_edges : 6 * C, cell_edges);
+  *nF = number_class_hash(cells, C, 4, 3, &TET_FACES[0][0], V, expected_faces > 0 ? expected_faces : 4 * C, cell_faces);
+  return (*nE < 0 || *nF < 0) ? 1 : 0;
+}
+
+/* ---- the reference algorithm restricted to a SAMPLE of rows (bench-size parity) --------------------------------
+ * Same arithmetic and the same order as oc_pattern + oc_assemble_cells + oc_apply_ident, but only the rows listed in
+ * rows[] (global dof numbers, ascending) are kept: pattern row = sorted union of the dofs of the cells that contain
+ * the row's dof; values = element-tensor rows added in ascending cell order by binary-search insertion; rows flagged
+ * in pec (uint8 per sampled row, may be NULL) become unit rows.  Order 2 tetrahedra; dofs from the entity tables
+ * (SURVEY 8.1-D), so no [C][20] dof array is needed at 5e7 cells.
+ * Call 1 (out_cols == NULL): fills out_rowptr[nrows+1] (offsets into the sample's own arrays), returns its nnz.
+ * Call 2: fills out_cols / out_S / out_M. */
+static inline void cell_dofs20(const int32_t* ce, const int32_t* cf, int64_t c, int64_t E, int64_t* d) {
+  int u, k;
+  for (u = 0; u < 6; ++u) for (k = 0; k < 2; ++k) d[2 * u + k] = 2 * (int64_t)ce[c * 6 + u] + k;
+  for (u = 0; u < 4; ++u) for (k = 0; k < 2; ++k) d[12 + 2 * u + k] = 2 * E + 2 * (int64_t)cf[c * 4 + u] + k;
+}
+static int cmp_i64_(const void* a, const void* b) {
+  int64_t x = *(const int64_t*)a, y = *(const int64_t*)b;
+  return x < y ? -1 : (x > y);
+}
+static inline int64_t find_row(const int64_t* rows, int64_t n, int64_t r) {
+  int64_t lo = 0, hi = n - 1;
+  while (lo <= hi) { int64_t mid = (lo + hi) >> 1; if (rows[mid] < r) lo = mid + 1; else if (rows[mid] > r) hi = mid - 1; else return mid; }
+  return -1;
+}
+
+int64_t oc_assemble_rows(const double* coords, const int32_t* cells, int64_t C, const int32_t* cell_edges,
+                         const int32_t* cell_faces, int64_t E, int64_t F, const double* Mhat, const double* Chat,
+                         const double* eps, const double* mu, int64_t nrows, const int64_t* rows, const uint8_t* pec,
+                         int64_t* out_rowptr, int64_t* out_cols, double* out_S, double* out_M) {
+  const int nd = 20;
+  const int64_t ndof = 2 * E + 2 * F;
+  /* flag bytes: which dofs are sampled (a cell is looked at only if one of its 20 dofs is) */
+  uint8_t* flag = (uint8_t*)calloc(ndof, 1);
+  int64_t i, c; int a, b, d, j;
+  for (i = 0; i < nrows; ++i) flag[rows[i]] = 1;
+  if (!out_cols) {
+    /* count pass: candidates per row, then sort-unique */
+    int64_t* cnt = (int64_t*)calloc(nrows + 1, sizeof(int64_t));
+    for (c = 0; c < C; ++c) {
+      int64_t dd[20]; cell_dofs20(cell_edges, cell_faces, c, E, dd);
+      for (j = 0; j < nd; ++j) if (flag[dd[j]]) cnt[find_row(rows, nrows, dd[j]) + 1] += nd;
+    }
+    for (i = 0; i < nrows; ++i) cnt[i + 1] += cnt[i];
+    int64_t* cand = (int64_t*)malloc(sizeof(int64_t) * (cnt[nrows] + 1));
+    int64_t* fill = (int64_t*)malloc(sizeof(int64_t) * (nrows + 1));
+    memcpy(fill, cnt, sizeof(int64_t) * (nrows + 1));
+    for (c = 0; c < C; ++c) {
+      int64_t dd[20]; cell_dofs20(cell_edges, cell_faces, c, E, dd);
+      for (j = 0; j < nd; ++j) if (flag[dd[j]]) {
+        int64_t r = find_row(rows, nrows, dd[j]);
+        memcpy(cand + fill[r], dd, sizeof(int64_t) * nd); fill[r] += nd;
+      }
+    }
+    out_rowptr[0] = 0;
+    for (i = 0; i < nrows; ++i) {
+      int64_t m = cnt[i + 1] - cnt[i], u = 0, k;
+      qsort(cand + cnt[i], m, sizeof(int64_t), cmp_i64_);
+      for (k = 0; k < m; ++k) if (k == 0 || cand[cnt[i] + k] != cand[cnt[i] + k - 1]) ++u;
+      out_rowptr[i + 1] = out_rowptr[i] + u;
+    }
+    free(fill); free(cand); free(cnt); free(flag);
+    return out_rowptr[nrows];
+  }
+  /* fill pass: columns (same sort-unique), then the cell loop */
+  {
+    int64_t* cnt = (int64_t*)calloc(nrows + 1, sizeof(int64_t));
+    for (c = 0; c < C; ++c) {
+      int64_t dd[20]; cell_dofs20(cell_edges, cell_faces, c, E, dd);
+      for (j = 0; j < nd; ++j) if (flag[dd[j]]) cnt[find_row(rows, nrows, dd[j]) + 1] += nd;
+    }
+    for (i = 0; i < nrows; ++i) cnt[i + 1] += cnt[i];
+    int64_t* cand = (int64_t*)malloc(sizeof(int64_t) * (cnt[nrows] + 1));
+    int64_t* fill = (int64_t*)malloc(sizeof(int64_t) * (nrows + 1));
+    memcpy(fill, cnt, sizeof(int64_t) * (nrows + 1));
+    for (c = 0; c < C; ++c) {
+      int64_t dd[20]; cell_dofs20(cell_edges, cell_faces, c, E, dd);
+      for (j = 0; j < nd; ++j) if (flag[dd[j]]) {
+        int64_t r = find_row(rows, nrows, dd[j]);
+        memcpy(cand + fill[r], dd, sizeof(int64_t) * nd); fill[r] += nd;
+      }
+    }
+    for (i = 0; i < nrows; ++i) {
+      int64_t m = cnt[i + 1] - cnt[i], u = 0, k;
+      qsort(cand + cnt[i], m, sizeof(int64_t), cmp_i64_);
+      for (k = 0; k < m; ++k) if (k == 0 || cand[cnt[i] + k] != cand[cnt[i] + k - 1]) out_cols[out_rowptr[i] + u++] = cand[cnt[i] + k];
+    }
+    free(fill); free(cand); free(cnt);
+  }
+  memset(out_S, 0, sizeof(double) * out_rowptr[nrows]);
+  memset(out_M, 0, sizeof(double) * out_rowptr[nrows]);
+  for (c = 0; c < C; ++c) {
+    int64_t dd[20]; cell_dofs20(cell_edges, cell_faces, c, E, dd);
+    int any = 0;
+    for (j = 0; j < nd; ++j) any |= flag[dd[j]];
+    if (!any) continue;
+    const int32_t* cv = cells + c * 4;
+    double J[3][3], Ji[3][3], G[3][3], Gi[3][3];
+    for (d = 0; d < 3; ++d) for (a = 0; a < 3; ++a) J[d][a] = coords[(int64_t)cv[a + 1] * 3 + d] - coords[(int64_t)cv[0] * 3 + d];
+    double c00 = J[1][1] * J[2][2] - J[1][2] * J[2][1], c01 = J[1][2] * J[2][0] - J[1][0] * J[2][2],
+           c02 = J[1][0] * J[2][1] - J[1][1] * J[2][0];
+    double det = J[0][0] * c00 + J[0][1] * c01 + J[0][2] * c02, id = 1.0 / det;
+    Ji[0][0] = c00 * id; Ji[1][0] = c01 * id; Ji[2][0] = c02 * id;
+    Ji[0][1] = (J[0][2] * J[2][1] - J[0][1] * J[2][2]) * id;
+    Ji[1][1] = (J[0][0] * J[2][2] - J[0][2] * J[2][0]) * id;
+    Ji[2][1] = (J[0][1] * J[2][0] - J[0][0] * J[2][1]) * id;
+    Ji[0][2] = (J[0][1] * J[1][2] - J[0][2] * J[1][1]) * id;
+    Ji[1][2] = (J[0][2] * J[1][0] - J[0][0] * J[1][2]) * id;
+    Ji[2][2] = (J[0][0] * J[1][1] - J[0][1] * J[1][0]) * id;
+    double ad = fabs(det), sm = ad * (eps ? eps[c] : 1.0), ss = 1.0 / (ad * (mu ? mu[c] : 1.0));
+    for (a = 0; a < 3; ++a) for (b = 0; b < 3; ++b) {
+      double gi = 0, gg = 0;
+      for (d = 0; d < 3; ++d) { gi += Ji[a][d] * Ji[b][d]; gg += J[d][a] * J[d][b]; }
+      Gi[a][b] = gi * sm; G[a][b] = gg * ss;
+    }
+    for (i = 0; i < nd; ++i) {
+      if (!flag[dd[i]]) continue;
+      const int64_t r = find_row(rows, nrows, dd[i]);
+      for (j = 0; j < nd; ++j) {
+        double m = 0, s = 0;
+        for (a = 0; a < 3; ++a) for (b = 0; b < 3; ++b) {
+          m += Gi[a][b] * Mhat[(a * 3 + b) * nd * nd + i * nd + j];
+          s += G[a][b] * Chat[(a * 3 + b) * nd * nd + i * nd + j];
+        }
+        int64_t lo = out_rowptr[r], hi = out_rowptr[r + 1] - 1;
+        while (lo < hi) { int64_t mid = (lo + hi) >> 1; if (out_cols[mid] < dd[j]) lo = mid + 1; else hi = mid; }
+        out_S[lo] += s; out_M[lo] += m;
+      }
+    }
+  }
+  if (pec)
+    for (i = 0; i < nrows; ++i) if (pec[i]) {
+      int64_t k;
+      for (k = out_rowptr[i]; k < out_rowptr[i + 1]; ++k) { out_S[k] = out_cols[k] == rows[i] ? 1.0 : 0.0; out_M[k] = out_S[k]; }
+    }
+  free(flag);
+  return out_rowptr[nrows];
+}
+
 int oc_max_threads(void) {
 #ifdef _OPENMP
   return omp_get_max_threads();

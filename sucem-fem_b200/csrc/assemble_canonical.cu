@@ -81,8 +81,14 @@ __device__ __forceinline__ unsigned flags_of(const Slots& it) { return (it.w1 >>
 __device__ __forceinline__ unsigned desc_index(const Slots& it) { return it.w1 & 0xffu; }
 
 // last hop of the gather chain: coordinates + coefficients, from the record (vertex ids already relabelled)
+// SFEM_WHATIF_* macros: timing-only experiments (wrong results) that bound what a lever could give; never defined in the
+// shipped library (tools/whatif_gpu.sh builds them into lib/variants/).
+template <bool EDGE = false>
 __device__ __forceinline__ void gather_item(const CanonArgs& p, uint4 ra, uint4 rb, Item& it) {
   it.w1 = rb.y; it.w2 = rb.z; it.w3 = rb.w;
+#if defined(SFEM_WHATIF_COORDS)
+  if (EDGE) { ra.x &= 1023u; ra.y &= 1023u; ra.z &= 1023u; ra.w &= 1023u; rb.x &= 1023u; }
+#endif
   const uint32_t v[4] = {ra.x, ra.y, ra.z, ra.w};
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
@@ -165,6 +171,9 @@ struct Fix {
 // Faces: an ordered pair out of (v0, v1, w = -(v0 + v1)), three selector bits per face (swap, w0, w1).
 template <int U, bool DM = false>
 __device__ __forceinline__ double2 fix_columns(const Fix& f, double v0, double v1) {
+#if defined(SFEM_WHATIF_NOFIX)
+  return make_double2(v0, v1);
+#endif
   if constexpr (U < 6 && DM) {
     const unsigned sign = ((unsigned)(f.desc >> 32) << (15 - U)) & 0x80000000u;  // descriptor bit 48 + U -> bit 31
     const double sm = __hiloint2double(__double2hiint(v1) ^ (int)sign, __double2loint(v1));
@@ -336,8 +345,13 @@ __device__ __forceinline__ void edge_pass(const CanonArgs& p, const unsigned lon
   const bool valid = m.i0 <= m.i1 && m.a1 > m.a;
   const int len = (int)(m.a1 - m.a);
   const uint4* __restrict__ rec = p.rec;
+#if defined(SFEM_WHATIF_REC)
+#define SFEM_RI(x) ((x) & 8191)
+#else
+#define SFEM_RI(x) (x)
+#endif
   uint4 rfa = make_uint4(0, 0, 0, 0), rfb = rfa;
-  if (nf < nf_end) { rfa = rec[2 * nf]; rfb = rec[2 * nf + 1]; }
+  if (nf < nf_end) { rfa = rec[2 * SFEM_RI(nf)]; rfb = rec[2 * SFEM_RI(nf) + 1]; }
   // the previous pass's bulk store must have finished reading the tile before it is overwritten
   tile_store_wait(lane);
   double2* row0 = tile + off;
@@ -369,21 +383,26 @@ __device__ __forceinline__ void edge_pass(const CanonArgs& p, const unsigned lon
     if (s + 1 < nsteps) {
       // this lane's next item of the pass (record two ahead)
       if (i + 2 < m.i1) {
-        if (i + 4 < m.i1) { rc2a = rec[2 * (i + 4)]; rc2b = rec[2 * (i + 4) + 1]; }
-        gather_item(p, rc1a, rc1b, cur);
+        if (i + 4 < m.i1) { rc2a = rec[2 * SFEM_RI(i + 4)]; rc2b = rec[2 * SFEM_RI(i + 4) + 1]; }
+        gather_item<true>(p, rc1a, rc1b, cur);
       }
     } else {
       // last step: the first item of the next pass, and the record of its second item
       if (nf < nf_end) {
-        if (nf + 2 < nf_end) { rc2a = rec[2 * (nf + 2)]; rc2b = rec[2 * (nf + 2) + 1]; }
+        if (nf + 2 < nf_end) { rc2a = rec[2 * SFEM_RI(nf + 2)]; rc2b = rec[2 * SFEM_RI(nf + 2) + 1]; }
         keep_opaque(rfa);  // loaded at the start of the pass; first use here
         keep_opaque(rfb);
-        gather_item(p, rfa, rfb, cur);
+        gather_item<true>(p, rfa, rfb, cur);
       }
     }
     __syncwarp();
     // 0 / 1 weights of the two possible carries (exact: x * 1 + y = x + y, x * 0 + y = y for finite x)
     const double mg = (has_prev && h) ? 1.0 : 0.0, ms = (has_prev && !h) ? 1.0 : 0.0;
+#if defined(SFEM_WHATIF_NOCONFLICT)
+#define SFEM_SLOT(K, U) ((U) * 32 + lane - off - (K) * len + (K) * 320)
+#else
+#define SFEM_SLOT(K, U) slot_of<U>(sl)
+#endif
 #define SFEM_RING_ROW(K, FN)                                                                       \
     {                                                                                              \
       double2 n3 = make_double2(0.0, 0.0), n1 = n3, n8 = n3;                                       \
@@ -403,20 +422,20 @@ __device__ __forceinline__ void edge_pass(const CanonArgs& p, const unsigned lon
         /* or of the previous step (even lane, weight ms); weights are 0 / 1, at most one of them is 1 */ \
         r = fix_columns<4, true>(fx, o[8], o[9]);                                                        \
         r.x = fma(g3.x, mg, fma(saved[K][0].x, ms, r.x)); r.y = fma(g3.y, mg, fma(saved[K][0].y, ms, r.y)); \
-        row[slot_of<4>(sl)] = r;                                                                  \
+        row[SFEM_SLOT(K, 4)] = r;                                                                  \
         r = fix_columns<2, true>(fx, o[4], o[5]);                                                        \
         r.x = fma(g1.x, mg, fma(saved[K][1].x, ms, r.x)); r.y = fma(g1.y, mg, fma(saved[K][1].y, ms, r.y)); \
-        row[slot_of<2>(sl)] = r;                                                                  \
+        row[SFEM_SLOT(K, 2)] = r;                                                                  \
         r = fix_columns<9>(fx, o[18], o[19]);                                                      \
         r.x = fma(g8.x, mg, fma(saved[K][2].x, ms, r.x)); r.y = fma(g8.y, mg, fma(saved[K][2].y, ms, r.y)); \
-        row[slot_of<9>(sl)] = r;                                                                  \
-        row[slot_of<0>(sl)] = fix_columns<0, true>(fx, o[0], o[1]);                                     \
-        row[slot_of<7>(sl)] = fix_columns<7>(fx, o[14], o[15]);                                   \
-        row[slot_of<6>(sl)] = fix_columns<6>(fx, o[12], o[13]);                                   \
+        row[SFEM_SLOT(K, 9)] = r;                                                                  \
+        row[SFEM_SLOT(K, 0)] = fix_columns<0, true>(fx, o[0], o[1]);                                     \
+        row[SFEM_SLOT(K, 7)] = fix_columns<7>(fx, o[14], o[15]);                                   \
+        row[SFEM_SLOT(K, 6)] = fix_columns<6>(fx, o[12], o[13]);                                   \
         if (!has_next) {                                                                           \
-          double2* q3 = row + slot_of<3>(sl);                                                     \
-          double2* q1 = row + slot_of<1>(sl);                                                     \
-          double2* q8 = row + slot_of<8>(sl);                                                     \
+          double2* q3 = row + SFEM_SLOT(K, 3);                                                     \
+          double2* q1 = row + SFEM_SLOT(K, 1);                                                     \
+          double2* q8 = row + SFEM_SLOT(K, 8);                                                     \
           if (wrap) {                                                                              \
             const double2 t3 = *q3, t1 = *q1, t8 = *q8;                                            \
             n3.x += t3.x; n3.y += t3.y; n1.x += t1.x; n1.y += t1.y; n8.x += t8.x; n8.y += t8.y;    \
@@ -434,6 +453,7 @@ __device__ __forceinline__ void edge_pass(const CanonArgs& p, const unsigned lon
       SFEM_RING_ROW(1, canon_edge_curl_k1)
     }
 #undef SFEM_RING_ROW
+#undef SFEM_SLOT
     rc1a = rc2a; rc1b = rc2b;
   }
   // the row edge's own block: both lanes' partial sums, stored by the even lane
@@ -474,7 +494,7 @@ __global__ void __launch_bounds__(kThreadsEdges, SFEM_EDGE_CTAS) k_canon_edges(C
     if (i < m.i1) {
       const uint4 ra = p.rec[2 * i], rb = p.rec[2 * i + 1];
       if (i + 2 < m.i1) { rc1a = p.rec[2 * (i + 2)]; rc1b = p.rec[2 * (i + 2) + 1]; }
-      gather_item(p, ra, rb, cur);
+      gather_item<true>(p, ra, rb, cur);
     }
   }
 #pragma unroll 1
