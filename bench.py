@@ -343,7 +343,7 @@ def check_timed_matrices(n, space, pats, vals, flags, eps, mu, rank, world):
     import torch
     import torch.distributed as dist
     t0 = time.perf_counter()
-    info = {"rows": 0, "entries": 0, "max_rel_err": 0.0}
+    info = {"rows": 0, "entries": 0, "max_err_over_tol": 0.0}
     ok, err = True, None
     try:
         from oracle import rowcheck
@@ -356,20 +356,20 @@ def check_timed_matrices(n, space, pats, vals, flags, eps, mu, rank, world):
                                      20000 // len(pats), 'rank %d block %d' % (rank, k), seed=rank)
             info["rows"] += r["rows"]
             info["entries"] += r["entries"]
-            info["max_rel_err"] = max(info["max_rel_err"], r["max_rel_err"])
+            info["max_err_over_tol"] = max(info["max_err_over_tol"], r["max_err_over_tol"])
             pat._csr = None
             del rowptr, cols
     except AssertionError as e:
         ok, err = False, str(e)[:300]
     if world > 1:
         t = torch.tensor([1.0 if ok else 0.0, float(info["rows"]), float(info["entries"])], dtype=torch.float64, device='cuda')
-        mx = torch.tensor([info["max_rel_err"]], dtype=torch.float64, device='cuda')
+        mx = torch.tensor([info["max_err_over_tol"]], dtype=torch.float64, device='cuda')
         dist.all_reduce(mx, op=dist.ReduceOp.MAX)
         tmin = t[:1].clone()
         dist.all_reduce(tmin, op=dist.ReduceOp.MIN)
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
         ok = float(tmin.item()) == 1.0
-        info = {"rows": int(t[1].item()), "entries": int(t[2].item()), "max_rel_err": float(mx.item())}
+        info = {"rows": int(t[1].item()), "entries": int(t[2].item()), "max_err_over_tol": float(mx.item())}
     info.update({"rtol": 1e-12, "pattern": "bit-exact", "seconds": round(time.perf_counter() - t0, 1),
                  "what": "sampled rows of the timed S and T (all blocks of all ranks) vs oracle/cpu_assemble.c:oc_assemble_rows "
                          "on the oracle's own first-appearance numbering; rows at head, tail, around every 2^28-th value "

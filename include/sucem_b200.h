@@ -170,6 +170,10 @@ SFEM_API int sfem_bicgstab(sfem_pattern_t pat, int n_mats, const double* const* 
                   const double* d_b, double* d_x, int preconditioner, double rtol, int maxiter, int* iterations,
                   double* relres, void* stream);
 
+/* Sustained fp64 FMA rate of the current device in TFLOP/s (8 independent DFMA chains per thread on every SM): the
+ * denominator of the fp64 roofline bench.py reports; no counterpart in the reference (measurement support). */
+SFEM_API int sfem_measure_fp64_peak(double* tflops, void* stream);
+
 /* ---- host-buffer entry points: the whole path with HOST arrays in and out --------------------------------------
  * What a host consumer gets from the reference today: FunctionSpace(mesh, family, order) (EMProblem.py:100-105),
  * assemble(M), assemble(S) [, assemble(S_0)] + apply_essential (SystemMatrices.py:54-55) and A.data()

@@ -421,11 +421,7 @@ int sfem_pattern_destroy(sfem_pattern_t pat) {
   if (!pat) return 0;
   DeviceGuard dg(pat->device);
   cudaStream_t st = pat->stream;
-  dev_free(pat->ent_rowptr, st);
-  dev_free(pat->ent_cols, st);
-  dev_free(pat->pos, st);
-  dev_free(pat->rec, st);
-  dev_free(pat->abc_rows, st);
+  sfem::free_pattern_buffers(pat, st);
   delete pat;
   return 0;
 }

@@ -522,6 +522,290 @@ __global__ void __launch_bounds__(kThreadsEdges, SFEM_EDGE_CTAS) k_canon_edges(C
   tile_store_wait(lane);
 }
 
+// ---- edges, lane per item: ONE LANE PER (edge, cell) ITEM, no loop over the cells of an edge ---------------------
+// A warp takes a BATCH of whole consecutive edges with at most 32 items and kE2TileChunks chunks of output
+// (pattern.cu: k_e2_batches); lane j owns item j of the batch, items of an edge sit on consecutive lanes in ring order.
+//   * what two neighbouring cells of a ring contribute to their three common column entities goes from the lane of
+//     the previous cell to the lane of the next one by ONE indexed shuffle (source = lane - 1, or the last lane of
+//     the ring for the first cell of a closed ring): every CSR slot is stored exactly once, closed rings included,
+//     and nothing is carried from step to step -- there are no steps;
+//   * the row edge's own block is a segmented suffix sum over the lanes of the edge (shuffles), stored by its first lane;
+//   * the item is gathered ONCE for S and T; records, aux words, vertex coordinates and coefficients of the batches
+//     ahead arrive through cp.async in per-warp shared-memory stages instead of registers (records two batches ahead,
+//     coordinates one), so the prefetch costs no registers and no scoreboard stalls.
+struct Edge2Args {
+  const double* __restrict__ coords4;
+  const double* __restrict__ eps;
+  const double* __restrict__ mu;
+  const uint4* __restrict__ rec;  // [nbatch][32][2]
+  const uint4* __restrict__ aux;  // [nbatch][32]
+  const uint8_t* __restrict__ pec;
+  double* __restrict__ S;
+  double* __restrict__ T;
+  int64_t ent_lo;
+  int64_t nbatch;
+};
+
+#ifndef SFEM_E2_WARPS
+#define SFEM_E2_WARPS 4
+#endif
+#ifndef SFEM_E2_CTAS
+#define SFEM_E2_CTAS 3
+#endif
+constexpr int kE2Warps = SFEM_E2_WARPS;
+// SFEM_E2_COORDS_SMEM = 1: vertex coordinates and coefficients of the next batch arrive through cp.async in a per-warp
+// shared-memory stage (no registers, 12 warps per SM); 0: plain loads into registers one batch ahead (8-10 warps per SM).
+#ifndef SFEM_E2_COORDS_SMEM
+#define SFEM_E2_COORDS_SMEM 1
+#endif
+// per-warp shared memory: tile | [coordinates + coefficients stage [9][32] x 16 B] | 2 x (records [2][32] + aux [32]) x 16 B
+constexpr int kE2StageCoords = SFEM_E2_COORDS_SMEM ? 9 * 32 : 0;  // uint4 units
+constexpr int kE2StageRec = 3 * 32;                    // uint4 units per ping-pong half
+constexpr int kE2WarpSmem = (kE2TileChunks + kE2StageCoords + 2 * kE2StageRec) * 16;
+
+__device__ __forceinline__ void cp_async16(void* sdst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(sdst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async16_ca(void* sdst, const void* gsrc) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(sdst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async8_ca(void* sdst, const void* gsrc) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(sdst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+__device__ __forceinline__ double2 shfl_idx(double2 v, int src) {
+  return make_double2(__shfl_sync(0xffffffffu, v.x, src), __shfl_sync(0xffffffffu, v.y, src));
+}
+__device__ __forceinline__ double2 shfl_down2(double2 v, int d) {
+  return make_double2(__shfl_down_sync(0xffffffffu, v.x, d), __shfl_down_sync(0xffffffffu, v.y, d));
+}
+
+// records + aux words of batch b -> one ping-pong half of the warp's record stage (coalesced: 4 wavefronts per copy)
+__device__ __forceinline__ void e2_issue_records(const Edge2Args& p, uint4* recst, int64_t b, int lane) {
+  const uint4* r = p.rec + (b * 32 + lane) * 2;
+  cp_async16(recst + lane, r);
+  cp_async16(recst + 32 + lane, r + 1);
+  cp_async16(recst + 64 + lane, p.aux + b * 32 + lane);
+}
+// coordinates and coefficients of the item whose record sits in `recst` -> the coordinate stage (cp.async) ...
+__device__ __forceinline__ void e2_issue_coords(const Edge2Args& p, const uint4* recst, uint4* cst, int lane) {
+  const uint4 ra = recst[lane];
+  const int cell = (int)recst[32 + lane].x;
+  if (cell >= 0) {
+    const unsigned v[4] = {ra.x, ra.y, ra.z, ra.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const double* x = p.coords4 + (size_t)v[k] * 4;
+      cp_async16_ca(cst + (2 * k) * 32 + lane, x);
+      cp_async16_ca(cst + (2 * k + 1) * 32 + lane, x + 2);
+    }
+    double* c = reinterpret_cast<double*>(cst + 8 * 32 + lane);
+    cp_async8_ca(c, p.mu + cell);
+    cp_async8_ca(c + 1, p.eps + cell);
+  }
+}
+__device__ __forceinline__ void e2_read_coords(const uint4* cst, Item& it, int lane) {
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const double2 xy = reinterpret_cast<const double2*>(cst)[(2 * k) * 32 + lane];
+    const double2 z = reinterpret_cast<const double2*>(cst)[(2 * k + 1) * 32 + lane];
+    it.X[3 * k] = xy.x; it.X[3 * k + 1] = xy.y; it.X[3 * k + 2] = z.x;
+  }
+  const double2 c = reinterpret_cast<const double2*>(cst)[8 * 32 + lane];
+  it.cmu = c.x; it.ceps = c.y;
+}
+// ... or -> registers (consumed one batch later)
+__device__ __forceinline__ void e2_gather_coords(const Edge2Args& p, const uint4* recst, Item& it, int lane) {
+  const uint4 ra = recst[lane];
+  const int cell = (int)recst[32 + lane].x;
+  if (cell >= 0) {
+    const unsigned v[4] = {ra.x, ra.y, ra.z, ra.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const double2* x = reinterpret_cast<const double2*>(p.coords4 + (size_t)v[k] * 4);
+      const double2 xy = x[0];
+      const double z = p.coords4[(size_t)v[k] * 4 + 2];
+      it.X[3 * k] = xy.x; it.X[3 * k + 1] = xy.y; it.X[3 * k + 2] = z;
+    }
+    it.cmu = p.mu[cell];
+    it.ceps = p.eps[cell];
+  }
+}
+
+template <bool MASS>
+__device__ __forceinline__ void edge2_pass(double2* __restrict__ tile, int lane, bool active, const Slots& sl,
+                                           unsigned pk, const double (&gm)[6], const Fix& fx, int src, double wprev,
+                                           bool open_end, unsigned pecraw, int mmax, double* __restrict__ gdst,
+                                           unsigned span) {
+  const int off = (int)(pk & 511u), len = (int)((pk >> 9) & 255u), pos = (int)((pk >> 17) & 31u),
+            rem = (int)((pk >> 22) & 31u);
+  // the previous pass's bulk store must have finished reading the tile before it is overwritten
+  tile_store_wait(lane);
+  double2* row0 = tile + off;
+  double2 self[2];
+  double o[20];
+#define SFEM_E2_ROW(K, FN)                                                                            \
+  {                                                                                                   \
+    double2 n3 = make_double2(0.0, 0.0), n1 = n3, n8 = n3;                                            \
+    if (active) {                                                                                     \
+      FN(gm, o);                                                                                      \
+      n3 = fix_columns<3, true>(fx, o[6], o[7]);                                                      \
+      n1 = fix_columns<1, true>(fx, o[2], o[3]);                                                      \
+      n8 = fix_columns<8>(fx, o[16], o[17]);                                                          \
+    }                                                                                                 \
+    /* the next-side blocks of the previous cell of the ring (weight 0: none) */                      \
+    const double2 g3 = shfl_idx(n3, src), g1 = shfl_idx(n1, src), g8 = shfl_idx(n8, src);             \
+    self[K] = make_double2(0.0, 0.0);                                                                 \
+    if (active) {                                                                                     \
+      double2* row = row0 + K * len;                                                                  \
+      double2 r;                                                                                      \
+      self[K] = fix_columns<5>(fx, o[10], o[11]);                                                     \
+      r = fix_columns<4, true>(fx, o[8], o[9]);                                                       \
+      r.x = fma(g3.x, wprev, r.x); r.y = fma(g3.y, wprev, r.y);                                       \
+      row[slot_of<4>(sl)] = r;                                                                        \
+      r = fix_columns<2, true>(fx, o[4], o[5]);                                                       \
+      r.x = fma(g1.x, wprev, r.x); r.y = fma(g1.y, wprev, r.y);                                       \
+      row[slot_of<2>(sl)] = r;                                                                        \
+      r = fix_columns<9>(fx, o[18], o[19]);                                                           \
+      r.x = fma(g8.x, wprev, r.x); r.y = fma(g8.y, wprev, r.y);                                       \
+      row[slot_of<9>(sl)] = r;                                                                        \
+      row[slot_of<0>(sl)] = fix_columns<0, true>(fx, o[0], o[1]);                                     \
+      row[slot_of<7>(sl)] = fix_columns<7>(fx, o[14], o[15]);                                         \
+      row[slot_of<6>(sl)] = fix_columns<6>(fx, o[12], o[13]);                                         \
+      if (open_end) {                                                                                 \
+        row[slot_of<3>(sl)] = n3;                                                                     \
+        row[slot_of<1>(sl)] = n1;                                                                     \
+        row[slot_of<8>(sl)] = n8;                                                                     \
+      }                                                                                               \
+    }                                                                                                 \
+  }
+  if (MASS) {
+    SFEM_E2_ROW(0, canon_edge_mass_k0)
+    SFEM_E2_ROW(1, canon_edge_mass_k1)
+  } else {
+    SFEM_E2_ROW(0, canon_edge_curl_k0)
+    SFEM_E2_ROW(1, canon_edge_curl_k1)
+  }
+#undef SFEM_E2_ROW
+  // the row edge's own block: suffix sum over the lanes of the edge (fixed order: bit-reproducible)
+#pragma unroll 1
+  for (int d = 1; d < mmax; d <<= 1) {
+    const double wd = d <= rem ? 1.0 : 0.0;
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const double2 t = shfl_down2(self[k], d);
+      self[k].x = fma(t.x, wd, self[k].x);
+      self[k].y = fma(t.y, wd, self[k].y);
+    }
+  }
+  const int self_slot = slot_of<5>(sl);
+  if (active && pos == 0) {
+    row0[self_slot] = self[0];
+    row0[len + self_slot] = self[1];
+  }
+  unsigned pr = pecraw;
+  keep_opaque(pr);  // loaded at the start of the batch; first use here
+  if (__any_sync(0xffffffffu, pr != 0u)) {
+    // row-only ident fused: the lanes of a constrained edge clear its rows, the first one sets the unit entries
+    const unsigned pecbits = decode_pecraw(pr);
+    __syncwarp();
+    const int m = pos + rem + 1;
+#pragma unroll
+    for (int k = 0; k < 2; ++k)
+      if ((pecbits >> k) & 1u)
+        for (int s = pos; s < len; s += m) row0[k * len + s] = make_double2(0.0, 0.0);
+    __syncwarp();
+    if (pos == 0) {
+      if (pecbits & 1u) row0[self_slot] = make_double2(1.0, 0.0);
+      if (pecbits & 2u) row0[len + self_slot] = make_double2(0.0, 1.0);
+    }
+  }
+  tile_store_issue(tile, gdst, span * 16u, lane);
+}
+
+#ifdef SFEM_E2_MAXREG
+__global__ void __maxnreg__(SFEM_E2_MAXREG) k_canon_edges2(Edge2Args p) {
+#else
+__global__ void __launch_bounds__(kE2Warps * 32, SFEM_E2_CTAS) k_canon_edges2(Edge2Args p) {
+#endif
+  extern __shared__ uint4 smem4[];
+  __shared__ unsigned long long s_desc[16];
+  __shared__ unsigned s_fsel[16];
+  stage_lut(s_desc, s_fsel);
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  uint4* base = smem4 + (size_t)w * (kE2WarpSmem / 16);
+  double2* tile = reinterpret_cast<double2*>(base);
+  uint4* cst = base + kE2TileChunks;
+  uint4* recst = cst + kE2StageCoords;
+  const int64_t nb = p.nbatch;
+  const int64_t W = (int64_t)gridDim.x * kE2Warps;
+  int64_t b = blockIdx.x * (int64_t)kE2Warps + w;
+  if (b >= nb) return;
+  // prologue: records of the first batch, then its coordinates together with the records of the second one
+  Item cur;
+  e2_issue_records(p, recst, b, lane);
+  cp_async_commit();
+  cp_async_wait_all();
+#if SFEM_E2_COORDS_SMEM
+  e2_issue_coords(p, recst, cst, lane);
+#else
+  e2_gather_coords(p, recst, cur, lane);
+#endif
+  if (b + W < nb) e2_issue_records(p, recst + kE2StageRec, b + W, lane);
+  cp_async_commit();
+  int ps = 0;
+#pragma unroll 1
+  for (; b < nb; b += W, ps ^= 1) {
+#if SFEM_E2_COORDS_SMEM
+    cp_async_wait_all();  // coordinates of this batch, records of the next one
+#endif
+    uint4* rcur = recst + ps * kE2StageRec;
+    const uint4 rb = rcur[32 + lane];
+    const uint4 ax = rcur[64 + lane];
+    const bool active = (int)rb.x >= 0;
+    Slots sl;
+    sl.w1 = rb.y; sl.w2 = rb.z; sl.w3 = rb.w;
+    // geometry of both forms from the coordinates gathered one batch ago
+    double gS[6], gT[6];
+    Fix fx;
+    fx.desc = 0ull; fx.fsel = 0u;
+    unsigned pecraw = 0u;
+    if (active) {
+#if SFEM_E2_COORDS_SMEM
+      e2_read_coords(cst, cur, lane);
+#endif
+      canon_geometry<false>(cur, gS);
+      canon_geometry<true>(cur, gT);
+      fx.desc = s_desc[desc_index(sl)];
+      fx.fsel = s_fsel[desc_index(sl)];
+      if (p.pec) pecraw = *reinterpret_cast<const unsigned short*>(p.pec + 2 * (p.ent_lo + (int64_t)ax.x));
+    }
+    // the item buffer is free again: coordinates of the next batch (its records have landed), records of the one after
+#if SFEM_E2_COORDS_SMEM
+    if (b + W < nb) e2_issue_coords(p, recst + (ps ^ 1) * kE2StageRec, cst, lane);
+#else
+    cp_async_wait_all();
+    if (b + W < nb) e2_gather_coords(p, recst + (ps ^ 1) * kE2StageRec, cur, lane);
+#endif
+    if (b + 2 * W < nb) e2_issue_records(p, rcur, b + 2 * W, lane);
+    cp_async_commit();
+    const unsigned flags = active ? flags_of(sl) : 0u;
+    const unsigned pk = ax.y;
+    const int delta = (int)(pk >> 27);
+    const bool has_prev = flags & 1u;
+    const int src = has_prev ? lane - 1 : lane + delta;
+    const double wprev = (has_prev || delta) ? 1.0 : 0.0;
+    const bool open_end = !(flags & 2u) && !(flags & 4u);
+    const int mmax = __reduce_max_sync(0xffffffffu, active ? (int)(((pk >> 17) & 31u) + ((pk >> 22) & 31u) + 1u) : 0);
+    const unsigned a_first = __shfl_sync(0xffffffffu, ax.z, 0), span = __shfl_sync(0xffffffffu, ax.w, 0);
+    edge2_pass<false>(tile, lane, active, sl, pk, gS, fx, src, wprev, open_end, pecraw, mmax, p.S + 4 * (size_t)a_first, span);
+    edge2_pass<true>(tile, lane, active, sl, pk, gT, fx, src, wprev, open_end, pecraw, mmax, p.T + 4 * (size_t)a_first, span);
+  }
+  tile_store_wait(lane);
+}
+
 // ---- faces: a PAIR of lanes per face, one lane per incident cell; the tile is store-only -------------------------
 // Entities of the shared face (canonical 2,4,5 = its edges, 9 = itself) look alike from both cells (identity
 // fix-up): the odd lane hands its values over by shuffle and the even lane stores the sums.
@@ -846,7 +1130,7 @@ bool canonical_supported(const sfem_pattern_s* pat) {
   if (pat->space->order == 1) return canonical1_supported(pat);
   // order-2 tets, packed records built (rows <= 255 entities), edges in ring order (manifold, <= 64 cells), faces
   // between at most two cells, and the edge kernel's tiles (16 edges x 2 rows per warp) must fit in shared memory
-  const size_t edge_smem = (size_t)(kThreadsEdges / 32) * 16 * 2 * pat->max_row_len_edges * sizeof(double2);
+  const size_t edge_smem = pat->rec_e2 ? 0 : (size_t)(kThreadsEdges / 32) * 16 * 2 * pat->max_row_len_edges * sizeof(double2);
   return pat->space->mesh->gdim == 3 && pat->space->order == 2 && pat->rec != nullptr && pat->ring_ok &&
          pat->max_row_len_other <= 16 && edge_smem <= 200 * 1024;
 }
@@ -895,7 +1179,16 @@ int assemble_canonical_ST(const sfem_pattern_s* pat, const double* eps, const do
     SFEM_CUDA(cudaGetLastError());
     return 0;
   }
-  if (n_edge_rows > 0) {
+  if (n_edge_rows > 0 && pat->rec_e2) {
+    Edge2Args q;
+    q.coords4 = sp->coords4; q.eps = eps; q.mu = mu; q.rec = pat->rec_e2; q.aux = pat->aux_e2; q.pec = pec;
+    q.S = S; q.T = T; q.ent_lo = pat->ent_lo; q.nbatch = pat->n_batch_e2;
+    const size_t smem = (size_t)kE2Warps * kE2WarpSmem;
+    SFEM_CUDA(cudaFuncSetAttribute(k_canon_edges2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int64_t nblocks = (q.nbatch + kE2Warps - 1) / kE2Warps;
+    const unsigned grid = (unsigned)std::min<int64_t>(nblocks, (int64_t)num_sms * SFEM_E2_CTAS);  // persistent
+    k_canon_edges2<<<grid, kE2Warps * 32, smem, st>>>(q);
+  } else if (n_edge_rows > 0) {
     p.r_begin = 0; p.r_end = n_edge_rows;
     p.tile_chunks = 16 * 2 * pat->max_row_len_edges;
     const size_t smem = (size_t)(kThreadsEdges / 32) * p.tile_chunks * sizeof(double2);

@@ -311,8 +311,7 @@ int sfem_space_assemble_rows_to_host(sfem_space_t sp, int64_t ent_lo, int64_t en
     if (rc == 0 && h_S0) rc = sfem_assemble(&pat, SFEM_FORM_ABC, nullptr, nullptr, d_pec_row_flags, s.S0, SFEM_KERNEL_AUTO, st);
     if (rc == 0) rc = export_pattern(&pat, s.rowptr, s.cols, st, off);
     // the block's pattern is dead once its kernels are queued (stream-ordered frees)
-    dev_free(pat.ent_rowptr, st); dev_free(pat.ent_cols, st); dev_free(pat.pos, st); dev_free(pat.rec, st);
-    dev_free(pat.abc_rows, st);
+    free_pattern_buffers(&pat, st);
     if (rc != 0) break;
     RUN_CUDA(cudaEventRecord(s.filled, st));
     RUN_CUDA(cudaStreamWaitEvent(cp, s.filled, 0));

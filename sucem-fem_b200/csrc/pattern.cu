@@ -11,6 +11,8 @@
 // edges -- in ring order -- in k_edge_ring).
 #include <cub/cub.cuh>
 
+#include <cstdlib>
+
 #include "sfem_internal.h"
 
 #define SFEM_TABLE static __device__ const
@@ -18,6 +20,12 @@
 
 namespace sfem {
 namespace {
+
+// SFEM_EDGE_KERNEL=1 selects the lane-pair edge kernel of round 1 (A/B measurements); default: lane per item
+int edge_kernel_version() {
+  const char* e = getenv("SFEM_EDGE_KERNEL");
+  return (e && e[0] == '1') ? 1 : 2;
+}
 
 constexpr int kWarpsPerBlock = 4;
 constexpr int kCap = 1024;  // candidates per row entity (valence * entities per cell)
@@ -122,7 +130,11 @@ constexpr int kMaxRing = 64;
 __global__ void k_edge_ring(SpaceView sv, const int32_t* __restrict__ cells, const int64_t* __restrict__ inc_ptr,
                             const int32_t* __restrict__ inc_cell, const uint8_t* __restrict__ inc_loc, int64_t ent_lo,
                             int64_t n_edge_rows, int64_t inc_base, const int64_t* __restrict__ ent_rowptr,
-                            const int32_t* __restrict__ ent_cols, uint8_t* __restrict__ rec, int* __restrict__ bad) {
+                            const int32_t* __restrict__ ent_cols, uint8_t* __restrict__ rec, int* __restrict__ bad,
+                            const int64_t* __restrict__ e2_slot0, const uint32_t* __restrict__ e2_tileoff,
+                            const uint2* __restrict__ e2_hdr, uint4* __restrict__ aux_e2) {
+  // e2_slot0 != nullptr: batched layout of the lane-per-item kernel -- the records of edge row r start at item slot
+  // e2_slot0[r] of `rec` (batch = slot / 32), and every record gets an aux entry
   const int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (r >= n_edge_rows) return;
   const int64_t g = ent_lo + r;
@@ -157,6 +169,10 @@ __global__ void k_edge_ring(SpaceView sv, const int32_t* __restrict__ cells, con
     }
   const int64_t a = ent_rowptr[r];
   const int len = (int)(ent_rowptr[r + 1] - a);
+  const int64_t slot0 = e2_slot0 ? e2_slot0[r] : i0 - inc_base;
+  uint2 hdr = make_uint2(0u, 0u);
+  unsigned tileoff = 0u;
+  if (e2_slot0) { hdr = e2_hdr[slot0 >> 5]; tileoff = e2_tileoff[r]; }
   unsigned long long visited = 0ull;
   int pos = 0;
   while (pos < m) {
@@ -186,7 +202,11 @@ __global__ void k_edge_ring(SpaceView sv, const int32_t* __restrict__ cells, con
       const int64_t c = inc_cell[i0 + cur];
       const int t = inc_loc[i0 + cur];
       const unsigned long long desc = kRingDesc[2 * t + swap];
-      uint8_t* q = rec + (i0 - inc_base + pos) * 32;
+      uint8_t* q = rec + (slot0 + pos) * 32;
+      if (aux_e2)  // packed: tile offset (9 bits), row length (8), position in the edge (5), items after it (5),
+                   // lane distance to the last cell of a closed ring (5, first cell only; patched below)
+        aux_e2[slot0 + pos] = make_uint4((unsigned)r, tileoff | ((unsigned)len << 9) | ((unsigned)pos << 17) |
+                                                          ((unsigned)(m - 1 - pos) << 22), hdr.x, hdr.y);
       for (int k = 0; k < 4; ++k)
         reinterpret_cast<int32_t*>(q)[k] = cells[c * 4 + (int)((desc >> (2 * k)) & 3ull)];
       reinterpret_cast<int32_t*>(q)[4] = (int32_t)c;
@@ -206,7 +226,52 @@ __global__ void k_edge_ring(SpaceView sv, const int32_t* __restrict__ cells, con
       entry = exitv;
       cur = nxt;
     }
+    if (aux_e2 && closed && pos - first_pos > 1) aux_e2[slot0 + first_pos].y |= (unsigned)(pos - first_pos - 1) << 27;
   }
+}
+
+// Batches of the lane-per-item edge kernel: consecutive whole edges with at most 32 (edge, cell) items and at most
+// kE2TileChunks chunks of output.  Greedy packing is a serial recurrence, so the edge rows are cut into independent
+// segments of kE2Seg edges (a batch never crosses a segment boundary); one thread walks a segment.  Pass 1 counts the
+// batches of each segment; pass 2 (after the scan) writes, per edge, its first item slot and its tile offset and, per
+// batch, {first entity chunk of the span, span in 16-byte chunks}.
+constexpr int kE2Seg = 512;
+template <bool WRITE>
+__global__ void k_e2_batches(const int64_t* __restrict__ inc_ptr, const int64_t* __restrict__ ent_rowptr, int64_t ent_lo,
+                             int64_t n_edge_rows, int32_t* __restrict__ seg_nb, const int64_t* __restrict__ seg_b0,
+                             int64_t* __restrict__ slot0, uint32_t* __restrict__ tileoff, uint2* __restrict__ hdr,
+                             int* __restrict__ bad) {
+  const int64_t seg = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  const int64_t r0 = seg * kE2Seg;
+  if (r0 >= n_edge_rows) return;
+  const int64_t r1 = min(r0 + (int64_t)kE2Seg, n_edge_rows);
+  int items = 0, chunks = 0;
+  int64_t nb = 0, b = WRITE ? seg_b0[seg] - 1 : -1;
+  int64_t a_first = 0;
+  int64_t ip = inc_ptr[ent_lo + r0], rp = ent_rowptr[r0];
+  for (int64_t r = r0; r < r1; ++r) {
+    const int64_t ip1 = inc_ptr[ent_lo + r + 1], rp1 = ent_rowptr[r + 1];
+    const int m = (int)(ip1 - ip), c2 = 2 * (int)(rp1 - rp);
+    if (m > 32 || m < 1 || c2 > kE2TileChunks) {
+      atomicMax(bad, 1);
+      return;
+    }
+    if (nb == 0 || items + m > 32 || chunks + c2 > kE2TileChunks) {
+      if (WRITE && nb > 0) hdr[b] = make_uint2((unsigned)a_first, (unsigned)chunks);
+      ++nb; ++b;
+      items = 0; chunks = 0;
+      a_first = rp;
+    }
+    if (WRITE) {
+      slot0[r] = b * 32 + items;
+      tileoff[r] = (uint32_t)chunks;
+    }
+    items += m;
+    chunks += c2;
+    ip = ip1; rp = rp1;
+  }
+  if (WRITE) hdr[b] = make_uint2((unsigned)a_first, (unsigned)chunks);
+  else seg_nb[seg] = (int32_t)nb;
 }
 
 __global__ void k_len_to_i64(const int32_t* __restrict__ len, int64_t* __restrict__ out, int64_t n) {
@@ -320,14 +385,61 @@ int fill_pattern(sfem_pattern_s* pat, cudaStream_t st) {
                                                           pat->inc_base, nullptr, pat->ent_rowptr, pat->ent_cols,
                                                           pat->pos, reinterpret_cast<uint8_t*>(pat->rec), overflow);
   pat->ring_ok = false;
+  bool use_e2 = false;
+  int64_t* e2_slot0 = nullptr;
+  uint32_t* e2_tileoff = nullptr;
+  uint2* e2_hdr = nullptr;
+  if (pat->rec && n_edge_rows > 0 && sp->order == 2 && edge_kernel_version() == 2 && pat->nnz_ent < (1ll << 32)) {
+    // batches of the lane-per-item edge kernel (falls back to the lane-pair layout when an edge has more than 32 cells)
+    const int64_t nseg = (n_edge_rows + kE2Seg - 1) / kE2Seg;
+    int32_t* seg_nb = nullptr;
+    int64_t* seg_b0 = nullptr;
+    SFEM_CUDA(dev_malloc(&seg_nb, (nseg + 1) * 4, st));
+    SFEM_CUDA(dev_malloc(&seg_b0, (nseg + 1) * 8, st));
+    SFEM_CUDA(cudaMemsetAsync(seg_nb, 0, (nseg + 1) * 4, st));
+    k_e2_batches<false><<<grid_for(nseg, 64), 64, 0, st>>>(sp->inc_ptr, pat->ent_rowptr, pat->ent_lo, n_edge_rows, seg_nb,
+                                                           nullptr, nullptr, nullptr, nullptr, overflow);
+    size_t tb = 0;
+    SFEM_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tb, seg_nb, seg_b0, (int)(nseg + 1), st));
+    void* tmp = nullptr;
+    SFEM_CUDA(dev_malloc(&tmp, tb + 16, st));
+    SFEM_CUDA(cub::DeviceScan::ExclusiveSum(tmp, tb, seg_nb, seg_b0, (int)(nseg + 1), st));
+    int h_bad = 0;
+    int64_t h_nb = 0;
+    SFEM_CUDA(cudaMemcpyAsync(&h_bad, overflow, 4, cudaMemcpyDeviceToHost, st));
+    SFEM_CUDA(cudaMemcpyAsync(&h_nb, seg_b0 + nseg, 8, cudaMemcpyDeviceToHost, st));
+    SFEM_CUDA(cudaStreamSynchronize(st));
+    dev_free(tmp, st);
+    if (h_bad == 0) {
+      use_e2 = true;
+      pat->n_batch_e2 = h_nb;
+      SFEM_CUDA(dev_malloc(&pat->rec_e2, h_nb * 32 * 32, st));
+      SFEM_CUDA(dev_malloc(&pat->aux_e2, h_nb * 32 * 16, st));
+      SFEM_CUDA(cudaMemsetAsync(pat->rec_e2, 0xff, h_nb * 32 * 32, st));  // padding slots: cell = -1
+      SFEM_CUDA(cudaMemsetAsync(pat->aux_e2, 0, h_nb * 32 * 16, st));
+      SFEM_CUDA(dev_malloc(&e2_slot0, n_edge_rows * 8, st));
+      SFEM_CUDA(dev_malloc(&e2_tileoff, n_edge_rows * 4, st));
+      SFEM_CUDA(dev_malloc(&e2_hdr, h_nb * 8, st));
+      k_e2_batches<true><<<grid_for(nseg, 64), 64, 0, st>>>(sp->inc_ptr, pat->ent_rowptr, pat->ent_lo, n_edge_rows, nullptr,
+                                                            seg_b0, e2_slot0, e2_tileoff, e2_hdr, overflow);
+    } else {
+      SFEM_CUDA(cudaMemsetAsync(overflow, 0, 4, st));
+    }
+    dev_free(seg_nb, st);
+    dev_free(seg_b0, st);
+  }
   if (pat->rec && n_edge_rows > 0) {
-    k_edge_ring<<<grid_for(n_edge_rows, 128), 128, 0, st>>>(sv, sp->mesh->cells, sp->inc_ptr, sp->inc_cell, sp->inc_loc,
-                                                            pat->ent_lo, n_edge_rows, pat->inc_base, pat->ent_rowptr,
-                                                            pat->ent_cols, reinterpret_cast<uint8_t*>(pat->rec), overflow);
+    k_edge_ring<<<grid_for(n_edge_rows, 128), 128, 0, st>>>(
+        sv, sp->mesh->cells, sp->inc_ptr, sp->inc_cell, sp->inc_loc, pat->ent_lo, n_edge_rows, pat->inc_base,
+        pat->ent_rowptr, pat->ent_cols, reinterpret_cast<uint8_t*>(use_e2 ? pat->rec_e2 : pat->rec), overflow, e2_slot0,
+        e2_tileoff, e2_hdr, pat->aux_e2);
     int h_bad = 0;
     SFEM_CUDA(cudaMemcpyAsync(&h_bad, overflow, 4, cudaMemcpyDeviceToHost, st));
     SFEM_CUDA(cudaStreamSynchronize(st));
     pat->ring_ok = h_bad == 0;
+    dev_free(e2_slot0, st);
+    dev_free(e2_tileoff, st);
+    dev_free(e2_hdr, st);
   } else if (pat->rec) {
     pat->ring_ok = true;
   }
@@ -365,6 +477,16 @@ int build_pattern_block(sfem_pattern_s* pat, const int64_t* rowptr_all, int64_t 
   pat->max_row_len_other = max_len_other;
   pat->max_row_len = std::max(max_len_edges, max_len_other);
   return fill_pattern(pat, st);
+}
+
+void free_pattern_buffers(sfem_pattern_s* pat, cudaStream_t st) {
+  dev_free(pat->ent_rowptr, st); pat->ent_rowptr = nullptr;
+  dev_free(pat->ent_cols, st); pat->ent_cols = nullptr;
+  dev_free(pat->pos, st); pat->pos = nullptr;
+  dev_free(pat->rec, st); pat->rec = nullptr;
+  dev_free(pat->rec_e2, st); pat->rec_e2 = nullptr;
+  dev_free(pat->aux_e2, st); pat->aux_e2 = nullptr;
+  dev_free(pat->abc_rows, st); pat->abc_rows = nullptr;
 }
 
 int export_pattern(const sfem_pattern_s* pat, int64_t* d_rowptr, int32_t* d_cols, cudaStream_t st, int64_t nnz_base) {

@@ -142,6 +142,12 @@ struct sfem_pattern_s {
   uint4* rec = nullptr;           // [n_inc_block][2] packed 32-byte item records {relabelled vertex ids, cell,
                                   // descriptor, flags, 10 uint8 slots} (order-2 tets, rows <= 255 entities)
   bool ring_ok = false;           // edge records are in ring order (manifold edges of bounded valence)
+  // order-2 tets, lane-per-item edge kernel (k_canon_edges2): the edge records live in BATCHES of 32 item slots (whole
+  // edges, at most kE2TileChunks 16-byte chunks of output per batch), padded with cell = -1
+  uint4* rec_e2 = nullptr;        // [n_batch_e2][32][2] packed item records in ring order
+  uint4* aux_e2 = nullptr;        // [n_batch_e2][32] {edge row, packed (tile offset, row length, position, remaining,
+                                  // ring-closing lane distance), first entity chunk of the batch's span, span chunks}
+  int64_t n_batch_e2 = 0;
   int64_t* abc_rows = nullptr;    // block-relative row entities that lie on an exterior facet (lazily built)
   int64_t n_abc_rows = -1;
   int64_t inc_base = 0;           // = space->inc_ptr[ent_lo]
@@ -177,6 +183,10 @@ inline SpaceView make_view(const sfem_space_s* s) {
 // tets: the slot table is stored in canonical column order (see pattern.cu / assemble_canonical.cu)
 inline bool pos_is_canonical(const sfem_space_s* s) { return s->mesh->gdim == 3; }
 
+// frees every device buffer of a pattern (stream-ordered); the struct itself stays
+void free_pattern_buffers(sfem_pattern_s* pat, cudaStream_t st);
+// output chunks (16 B) per warp tile of the lane-per-item edge kernel: a batch never exceeds it
+constexpr int kE2TileChunks = 448;
 int build_numbering(sfem_space_s* sp, cudaStream_t st);
 int build_pattern(sfem_pattern_s* pat, cudaStream_t st);
 int count_pattern_rows(const sfem_space_s* sp, int64_t ent_lo, int64_t ent_hi, cudaStream_t st, int64_t** rowptr_out,

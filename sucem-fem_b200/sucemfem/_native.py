@@ -61,6 +61,7 @@ def _load():
         'sfem_space_assemble_rows_to_host': (i32, [vp, i64, i64, vp, vp, vp, vp, vp, vp, vp, vp, i32, vp]),
         'sfem_space_count_nnz': (i32, [vp, vp, P(i64)]),
         'sfem_space_assemble_to_host': (i32, [vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, vp]),
+        'sfem_measure_fp64_peak': (i32, [P(dbl), vp]),
         'sfem_host_alloc': (i32, [C.c_size_t, P(vp)]),
         'sfem_host_free': (i32, [vp]),
     }

@@ -327,6 +327,33 @@ def test_values_canonical_vs_oracle(dev, name, order):
     assert torch.equal(torch.cat(Ss), Sp)
 
 
+@pytest.mark.parametrize('order', [1, 2])
+def test_every_value_slot_is_written(dev, order):
+    """The value kernels are store-only (no zero-fill of S / T beforehand): every CSR slot must be written by a kernel.
+    Outputs pre-filled with NaN must come back NaN-free and equal to an assembly into fresh arrays -- for the whole
+    pattern and for row blocks, with every kernel id.  (compute-sanitizer's initcheck cannot show this: it does not
+    track the bulk-copy engine's global writes, profiles/r02_sanitizer.md.)"""
+    import torch
+    from sucemfem import _native as N
+    co, ce = meshes.unit_cube(5, 4, 3)
+    m = dev.DeviceMesh(co, ce)
+    sp = dev.DeviceSpace(m, order)
+    markers = torch.zeros(sp.n_facets, dtype=torch.int32, device='cuda')
+    sp.mark_exterior_facets(markers, 999)
+    flags = sp.pec_row_flags(markers, 999)
+    b = sp.partition(3)
+    for lo, hi in [(0, -1)] + [(b[q], b[q + 1]) for q in range(3)]:
+        pat = dev.DevicePattern(sp, lo, hi)
+        for kernel in (N.KERNEL_AUTO, N.KERNEL_CANONICAL, N.KERNEL_GENERIC):
+            for pec in (None, flags):
+                S0, T0 = pat.assemble_ST(pec_flags=pec, kernel=kernel)
+                S = torch.full((pat.nnz,), float('nan'), dtype=torch.float64, device='cuda')
+                T = torch.full((pat.nnz,), float('nan'), dtype=torch.float64, device='cuda')
+                pat.assemble_ST(pec_flags=pec, S=S, T=T, kernel=kernel)
+                assert not torch.isnan(S).any() and not torch.isnan(T).any()
+                assert torch.equal(S, S0) and torch.equal(T, T0)
+
+
 def test_canonical_midsize_vs_c_oracle(dev):
     """UnitCube(12) order 2 (10 368 tets, 3.0 M non-zeros) against the C restatement of the reference algorithm."""
     import torch

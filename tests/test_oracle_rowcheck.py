@@ -47,7 +47,7 @@ def test_sampled_rows_equal_full_assembly_and_geometric_pec():
     want = orc.rows(rows, eps, mu, flag[rows])
     idx = np.concatenate([np.arange(A.rowptr[r], A.rowptr[r + 1]) for r in rows])
     info = rowcheck.compare(want, A.cols[idx], S[idx], M[idx])
-    assert info['max_rel_err'] == 0.0 and info['rows'] == len(rows)
+    assert info['max_err_over_tol'] == 0.0 and info['rows'] == len(rows)
     with pytest.raises(AssertionError):
         bad = S[idx].copy()
         bad[len(bad) // 2] *= 1 + 1e-11
