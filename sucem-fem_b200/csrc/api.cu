@@ -301,6 +301,7 @@ int sfem_space_destroy(sfem_space_t sp) {
   dev_free(sp->cell_extmask, st);
   dev_free(sp->coords4, st);
   dev_free(sp->ones, st);
+  dev_free(sp->coef2, st);
   dev_free(sp->rowptr_all, st);
   if (sp->drain) {
     cudaStreamSynchronize(sp->drain);

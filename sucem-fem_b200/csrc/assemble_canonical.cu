@@ -193,6 +193,9 @@ __device__ __forceinline__ void tile_store_issue(const double2* tile, double* gd
   // make the generic-proxy writes of every lane visible to the async proxy, then one lane issues the copy
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   __syncwarp();
+#if defined(SFEM_WHATIF_NOBULK)
+  bytes = 0;
+#endif
   if (lane == 0 && bytes > 0) {
     const unsigned src = (unsigned)__cvta_generic_to_shared(tile);
 #ifndef SFEM_NO_STORE_HINT
@@ -537,6 +540,7 @@ struct Edge2Args {
   const double* __restrict__ coords4;
   const double* __restrict__ eps;
   const double* __restrict__ mu;
+  const double2* __restrict__ coef2;  // [C] (mu_r, eps_r) packed per call (one 16-byte gather per item)
   const uint4* __restrict__ rec;  // [nbatch][32][2]
   const uint4* __restrict__ aux;  // [nbatch][32]
   const uint8_t* __restrict__ pec;
@@ -589,31 +593,58 @@ __device__ __forceinline__ void e2_issue_records(const Edge2Args& p, uint4* recs
   cp_async16(recst + 32 + lane, r + 1);
   cp_async16(recst + 64 + lane, p.aux + b * 32 + lane);
 }
-// coordinates and coefficients of the item whose record sits in `recst` -> the coordinate stage (cp.async) ...
+// Vertex data of the item whose record sits in `recst` -> the coordinate stage (cp.async).  A relabelled cell is
+// (a, b, entry, exit) with (a, b) the row edge, and consecutive cells of a ring share a face: the exit vertex of one is
+// the entry vertex of the next.  So an EDGE with m cells needs 2 + m (+1 for an open fan) vertices, not 4 m:
+//   rows 0-3 of the stage: a, b (xy | z)   copied by the FIRST lane of the edge only, read by all its lanes
+//   rows 4-5: entry vertex                 copied only where a chain starts without a predecessor (open fans)
+//   rows 6-7: exit vertex                  every lane; the next cell of the ring reads it as its entry vertex
+//   row  8:   (mu_r, eps_r) of the cell
+// Every copy of a gathered address costs one shared-memory wavefront per returned sector (~15 per instruction for 32
+// distinct vertices), which made the shared-memory pipe the limiter of this kernel; sharing cuts them by more than half.
 __device__ __forceinline__ void e2_issue_coords(const Edge2Args& p, const uint4* recst, uint4* cst, int lane) {
   const uint4 ra = recst[lane];
-  const int cell = (int)recst[32 + lane].x;
+  const uint4 rb = recst[32 + lane];
+  const unsigned pk = recst[64 + lane].y;
+  const int cell = (int)rb.x;
   if (cell >= 0) {
+#if defined(SFEM_WHATIF_COORDS)
+    const unsigned v[4] = {ra.x & 1023u, ra.y & 1023u, ra.z & 1023u, ra.w & 1023u};
+#else
     const unsigned v[4] = {ra.x, ra.y, ra.z, ra.w};
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const double* x = p.coords4 + (size_t)v[k] * 4;
-      cp_async16_ca(cst + (2 * k) * 32 + lane, x);
-      cp_async16_ca(cst + (2 * k + 1) * 32 + lane, x + 2);
+#endif
+    const bool first = ((pk >> 17) & 31u) == 0u;                       // first lane of its edge
+    const bool chain_start = !((rb.y >> 8) & 1u) && (pk >> 27) == 0u;  // no predecessor in the ring
+    if (first) {
+      const double* xa = p.coords4 + (size_t)v[0] * 4;
+      const double* xb = p.coords4 + (size_t)v[1] * 4;
+      cp_async16_ca(cst + lane, xa);
+      cp_async16_ca(cst + 32 + lane, xa + 2);
+      cp_async16_ca(cst + 64 + lane, xb);
+      cp_async16_ca(cst + 96 + lane, xb + 2);
     }
-    double* c = reinterpret_cast<double*>(cst + 8 * 32 + lane);
-    cp_async8_ca(c, p.mu + cell);
-    cp_async8_ca(c + 1, p.eps + cell);
+    if (chain_start) {
+      const double* xe = p.coords4 + (size_t)v[2] * 4;
+      cp_async16_ca(cst + 128 + lane, xe);
+      cp_async16_ca(cst + 160 + lane, xe + 2);
+    }
+    const double* xx = p.coords4 + (size_t)v[3] * 4;
+    cp_async16_ca(cst + 192 + lane, xx);
+    cp_async16_ca(cst + 224 + lane, xx + 2);
+    cp_async16_ca(cst + 256 + lane, p.coef2 + cell);
   }
 }
-__device__ __forceinline__ void e2_read_coords(const uint4* cst, Item& it, int lane) {
-#pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    const double2 xy = reinterpret_cast<const double2*>(cst)[(2 * k) * 32 + lane];
-    const double2 z = reinterpret_cast<const double2*>(cst)[(2 * k + 1) * 32 + lane];
-    it.X[3 * k] = xy.x; it.X[3 * k + 1] = xy.y; it.X[3 * k + 2] = z.x;
-  }
-  const double2 c = reinterpret_cast<const double2*>(cst)[8 * 32 + lane];
+// first: first lane of this lane's edge; src: lane of the previous cell of the ring (has_pred) or this lane
+__device__ __forceinline__ void e2_read_coords(const uint4* cst, Item& it, int lane, int first, int src, bool has_pred) {
+  const double2* c2 = reinterpret_cast<const double2*>(cst);
+  const int e0 = has_pred ? 192 + src : 128 + lane;
+  const double2 axy = c2[first], az = c2[32 + first], bxy = c2[64 + first], bz = c2[96 + first];
+  const double2 exy = c2[e0], ez = c2[e0 + 32], xxy = c2[192 + lane], xz = c2[224 + lane];
+  it.X[0] = axy.x; it.X[1] = axy.y; it.X[2] = az.x;
+  it.X[3] = bxy.x; it.X[4] = bxy.y; it.X[5] = bz.x;
+  it.X[6] = exy.x; it.X[7] = exy.y; it.X[8] = ez.x;
+  it.X[9] = xxy.x; it.X[10] = xxy.y; it.X[11] = xz.x;
+  const double2 c = c2[256 + lane];
   it.cmu = c.x; it.ceps = c.y;
 }
 // ... or -> registers (consumed one batch later)
@@ -646,6 +677,11 @@ __device__ __forceinline__ void edge2_pass(double2* __restrict__ tile, int lane,
   double2* row0 = tile + off;
   double2 self[2];
   double o[20];
+#if defined(SFEM_WHATIF_NOCONFLICT)
+#define SFEM_E2_SLOT(U) (((U) * 32 + lane) - off)
+#else
+#define SFEM_E2_SLOT(U) slot_of<U>(sl)
+#endif
 #define SFEM_E2_ROW(K, FN)                                                                            \
   {                                                                                                   \
     double2 n3 = make_double2(0.0, 0.0), n1 = n3, n8 = n3;                                            \
@@ -664,20 +700,20 @@ __device__ __forceinline__ void edge2_pass(double2* __restrict__ tile, int lane,
       self[K] = fix_columns<5>(fx, o[10], o[11]);                                                     \
       r = fix_columns<4, true>(fx, o[8], o[9]);                                                       \
       r.x = fma(g3.x, wprev, r.x); r.y = fma(g3.y, wprev, r.y);                                       \
-      row[slot_of<4>(sl)] = r;                                                                        \
+      row[SFEM_E2_SLOT(4)] = r;                                                                        \
       r = fix_columns<2, true>(fx, o[4], o[5]);                                                       \
       r.x = fma(g1.x, wprev, r.x); r.y = fma(g1.y, wprev, r.y);                                       \
-      row[slot_of<2>(sl)] = r;                                                                        \
+      row[SFEM_E2_SLOT(2)] = r;                                                                        \
       r = fix_columns<9>(fx, o[18], o[19]);                                                           \
       r.x = fma(g8.x, wprev, r.x); r.y = fma(g8.y, wprev, r.y);                                       \
-      row[slot_of<9>(sl)] = r;                                                                        \
-      row[slot_of<0>(sl)] = fix_columns<0, true>(fx, o[0], o[1]);                                     \
-      row[slot_of<7>(sl)] = fix_columns<7>(fx, o[14], o[15]);                                         \
-      row[slot_of<6>(sl)] = fix_columns<6>(fx, o[12], o[13]);                                         \
+      row[SFEM_E2_SLOT(9)] = r;                                                                        \
+      row[SFEM_E2_SLOT(0)] = fix_columns<0, true>(fx, o[0], o[1]);                                     \
+      row[SFEM_E2_SLOT(7)] = fix_columns<7>(fx, o[14], o[15]);                                         \
+      row[SFEM_E2_SLOT(6)] = fix_columns<6>(fx, o[12], o[13]);                                         \
       if (open_end) {                                                                                 \
-        row[slot_of<3>(sl)] = n3;                                                                     \
-        row[slot_of<1>(sl)] = n1;                                                                     \
-        row[slot_of<8>(sl)] = n8;                                                                     \
+        row[SFEM_E2_SLOT(3)] = n3;                                                                     \
+        row[SFEM_E2_SLOT(1)] = n1;                                                                     \
+        row[SFEM_E2_SLOT(8)] = n8;                                                                     \
       }                                                                                               \
     }                                                                                                 \
   }
@@ -689,6 +725,7 @@ __device__ __forceinline__ void edge2_pass(double2* __restrict__ tile, int lane,
     SFEM_E2_ROW(1, canon_edge_curl_k1)
   }
 #undef SFEM_E2_ROW
+#undef SFEM_E2_SLOT
   // the row edge's own block: suffix sum over the lanes of the edge (fixed order: bit-reproducible)
 #pragma unroll 1
   for (int d = 1; d < mmax; d <<= 1) {
@@ -767,14 +804,25 @@ __global__ void __launch_bounds__(kE2Warps * 32, SFEM_E2_CTAS) k_canon_edges2(Ed
     const bool active = (int)rb.x >= 0;
     Slots sl;
     sl.w1 = rb.y; sl.w2 = rb.z; sl.w3 = rb.w;
+    const unsigned flags = active ? flags_of(sl) : 0u;
+    const unsigned pk = ax.y;
+    const int delta = (int)(pk >> 27);
+    const bool has_prev = flags & 1u;
+    const int src = has_prev ? lane - 1 : lane + delta;
+    const bool has_pred = has_prev || delta;
+    const double wprev = has_pred ? 1.0 : 0.0;
+    const bool open_end = !(flags & 2u) && !(flags & 4u);
     // geometry of both forms from the coordinates gathered one batch ago
     double gS[6], gT[6];
     Fix fx;
     fx.desc = 0ull; fx.fsel = 0u;
     unsigned pecraw = 0u;
+#if SFEM_E2_COORDS_SMEM
+    __syncwarp();  // the stage is read across lanes
+#endif
     if (active) {
 #if SFEM_E2_COORDS_SMEM
-      e2_read_coords(cst, cur, lane);
+      e2_read_coords(cst, cur, lane, lane - (int)((pk >> 17) & 31u), src, has_pred);
 #endif
       canon_geometry<false>(cur, gS);
       canon_geometry<true>(cur, gT);
@@ -784,6 +832,7 @@ __global__ void __launch_bounds__(kE2Warps * 32, SFEM_E2_CTAS) k_canon_edges2(Ed
     }
     // the item buffer is free again: coordinates of the next batch (its records have landed), records of the one after
 #if SFEM_E2_COORDS_SMEM
+    __syncwarp();  // every lane has read the stage
     if (b + W < nb) e2_issue_coords(p, recst + (ps ^ 1) * kE2StageRec, cst, lane);
 #else
     cp_async_wait_all();
@@ -791,13 +840,6 @@ __global__ void __launch_bounds__(kE2Warps * 32, SFEM_E2_CTAS) k_canon_edges2(Ed
 #endif
     if (b + 2 * W < nb) e2_issue_records(p, rcur, b + 2 * W, lane);
     cp_async_commit();
-    const unsigned flags = active ? flags_of(sl) : 0u;
-    const unsigned pk = ax.y;
-    const int delta = (int)(pk >> 27);
-    const bool has_prev = flags & 1u;
-    const int src = has_prev ? lane - 1 : lane + delta;
-    const double wprev = (has_prev || delta) ? 1.0 : 0.0;
-    const bool open_end = !(flags & 2u) && !(flags & 4u);
     const int mmax = __reduce_max_sync(0xffffffffu, active ? (int)(((pk >> 17) & 31u) + ((pk >> 22) & 31u) + 1u) : 0);
     const unsigned a_first = __shfl_sync(0xffffffffu, ax.z, 0), span = __shfl_sync(0xffffffffu, ax.w, 0);
     edge2_pass<false>(tile, lane, active, sl, pk, gS, fx, src, wprev, open_end, pecraw, mmax, p.S + 4 * (size_t)a_first, span);
@@ -1141,6 +1183,12 @@ int canonical_launches(const sfem_pattern_s* pat) {
   return (pat->ent_lo < E ? 1 : 0) + (pat->ent_hi > E ? 1 : 0);
 }
 
+// (mu_r, eps_r) of every cell side by side: one 16-byte gather per item instead of two 8-byte ones
+__global__ void k_pack_coef(const double* __restrict__ mu, const double* __restrict__ eps, double2* __restrict__ out, int64_t n) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < n) out[i] = make_double2(mu ? mu[i] : 1.0, eps ? eps[i] : 1.0);
+}
+
 __global__ void k_fill_ones(double* a, int64_t n) {
   int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (i < n) a[i] = 1.0;
@@ -1150,6 +1198,8 @@ int assemble_canonical_ST(const sfem_pattern_s* pat, const double* eps, const do
                           double* S, double* T, cudaStream_t st) {
   sfem_space_s* sp = pat->space;
   const sfem_mesh_s* m = sp->mesh;
+  const double* eps_in = eps;
+  const double* mu_in = mu;
   if (!eps || !mu) {  // default coefficients: the kernels always read a per-cell array
     if (!sp->ones) {
       SFEM_CUDA(dev_malloc(&sp->ones, m->C * sizeof(double), st));
@@ -1180,8 +1230,10 @@ int assemble_canonical_ST(const sfem_pattern_s* pat, const double* eps, const do
     return 0;
   }
   if (n_edge_rows > 0 && pat->rec_e2) {
+    if (!sp->coef2) SFEM_CUDA(dev_malloc(&sp->coef2, m->C * sizeof(double2), st));
+    k_pack_coef<<<(unsigned)((m->C + 255) / 256), 256, 0, st>>>(mu_in, eps_in, sp->coef2, m->C);
     Edge2Args q;
-    q.coords4 = sp->coords4; q.eps = eps; q.mu = mu; q.rec = pat->rec_e2; q.aux = pat->aux_e2; q.pec = pec;
+    q.coords4 = sp->coords4; q.eps = eps; q.mu = mu; q.coef2 = sp->coef2; q.rec = pat->rec_e2; q.aux = pat->aux_e2; q.pec = pec;
     q.S = S; q.T = T; q.ent_lo = pat->ent_lo; q.nbatch = pat->n_batch_e2;
     const size_t smem = (size_t)kE2Warps * kE2WarpSmem;
     SFEM_CUDA(cudaFuncSetAttribute(k_canon_edges2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
