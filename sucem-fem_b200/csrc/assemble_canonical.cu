@@ -273,6 +273,10 @@ __device__ __forceinline__ void stage_lut(unsigned long long* s_desc, unsigned* 
 #ifndef SFEM_FACE_THREADS
 #define SFEM_FACE_THREADS 128
 #endif
+// tiles per warp of the face kernel: 2 = S and T in separate tiles (a pass never waits for the bulk copy before it)
+#ifndef SFEM_FACE_TILES
+#define SFEM_FACE_TILES 2
+#endif
 constexpr int kThreadsEdges = SFEM_EDGE_THREADS;  // warps x 16 edges; CTAs per SM are bounded by tiles and registers
 constexpr int kThreadsFaces = SFEM_FACE_THREADS;  // warps x 16 faces
 
@@ -551,10 +555,14 @@ struct Edge2Args {
 };
 
 #ifndef SFEM_E2_WARPS
-#define SFEM_E2_WARPS 4
+#define SFEM_E2_WARPS 5
 #endif
 #ifndef SFEM_E2_CTAS
-#define SFEM_E2_CTAS 3
+#define SFEM_E2_CTAS 2
+#endif
+// tiles per warp: 2 = S and T in separate tiles, so a pass never waits for the bulk copy of the pass before it
+#ifndef SFEM_E2_TILES
+#define SFEM_E2_TILES 2
 #endif
 constexpr int kE2Warps = SFEM_E2_WARPS;
 // SFEM_E2_COORDS_SMEM = 1: vertex coordinates and coefficients of the next batch arrive through cp.async in a per-warp
@@ -565,7 +573,7 @@ constexpr int kE2Warps = SFEM_E2_WARPS;
 // per-warp shared memory: tile | [coordinates + coefficients stage [9][32] x 16 B] | 2 x (records [2][32] + aux [32]) x 16 B
 constexpr int kE2StageCoords = SFEM_E2_COORDS_SMEM ? 9 * 32 : 0;  // uint4 units
 constexpr int kE2StageRec = 3 * 32;                    // uint4 units per ping-pong half
-constexpr int kE2WarpSmem = (kE2TileChunks + kE2StageCoords + 2 * kE2StageRec) * 16;
+constexpr int kE2WarpSmem = (SFEM_E2_TILES * kE2TileChunks + kE2StageCoords + 2 * kE2StageRec) * 16;
 
 __device__ __forceinline__ void cp_async16(void* sdst, const void* gsrc) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(sdst)), "l"(gsrc) : "memory");
@@ -672,8 +680,14 @@ __device__ __forceinline__ void edge2_pass(double2* __restrict__ tile, int lane,
                                            unsigned span) {
   const int off = (int)(pk & 511u), len = (int)((pk >> 9) & 255u), pos = (int)((pk >> 17) & 31u),
             rem = (int)((pk >> 22) & 31u);
-  // the previous pass's bulk store must have finished reading the tile before it is overwritten
+  // the bulk store that last read this tile must have finished reading it before it is overwritten: with one tile
+  // that is the copy of the pass before, with two tiles the one before that (at most one group may still be reading)
+#if SFEM_E2_TILES == 2
+  if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+  __syncwarp();
+#else
   tile_store_wait(lane);
+#endif
   double2* row0 = tile + off;
   double2 self[2];
   double o[20];
@@ -774,7 +788,7 @@ __global__ void __launch_bounds__(kE2Warps * 32, SFEM_E2_CTAS) k_canon_edges2(Ed
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   uint4* base = smem4 + (size_t)w * (kE2WarpSmem / 16);
   double2* tile = reinterpret_cast<double2*>(base);
-  uint4* cst = base + kE2TileChunks;
+  uint4* cst = base + SFEM_E2_TILES * kE2TileChunks;
   uint4* recst = cst + kE2StageCoords;
   const int64_t nb = p.nbatch;
   const int64_t W = (int64_t)gridDim.x * kE2Warps;
@@ -843,7 +857,7 @@ __global__ void __launch_bounds__(kE2Warps * 32, SFEM_E2_CTAS) k_canon_edges2(Ed
     const int mmax = __reduce_max_sync(0xffffffffu, active ? (int)(((pk >> 17) & 31u) + ((pk >> 22) & 31u) + 1u) : 0);
     const unsigned a_first = __shfl_sync(0xffffffffu, ax.z, 0), span = __shfl_sync(0xffffffffu, ax.w, 0);
     edge2_pass<false>(tile, lane, active, sl, pk, gS, fx, src, wprev, open_end, pecraw, mmax, p.S + 4 * (size_t)a_first, span);
-    edge2_pass<true>(tile, lane, active, sl, pk, gT, fx, src, wprev, open_end, pecraw, mmax, p.T + 4 * (size_t)a_first, span);
+    edge2_pass<true>(tile + (SFEM_E2_TILES - 1) * kE2TileChunks, lane, active, sl, pk, gT, fx, src, wprev, open_end, pecraw, mmax, p.T + 4 * (size_t)a_first, span);
   }
   tile_store_wait(lane);
 }
@@ -856,7 +870,12 @@ __device__ __forceinline__ void face_pass(const CanonArgs& p, double2* __restric
                                           bool active, unsigned pecbits, int len, int off, int span, const Slots& it,
                                           const double (&gm)[6], const Fix& fx, double* __restrict__ out_first) {
   const int h = lane & 1;
+#if SFEM_FACE_TILES == 2
+  if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+  __syncwarp();
+#else
   tile_store_wait(lane);
+#endif
   double2* row0 = tile + off;
   double o[20];
 #define SFEM_FACE_ROW(K, FN)                                                                              \
@@ -927,7 +946,7 @@ __global__ void __launch_bounds__(kThreadsFaces, SFEM_FACE_CTAS) k_canon_faces(C
   __shared__ unsigned s_fsel[16];
   stage_lut(s_desc, s_fsel);
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  double2* tile = smem + (size_t)w * p.tile_chunks;
+  double2* tile = smem + (size_t)w * SFEM_FACE_TILES * p.tile_chunks;
   const int64_t nb = (p.r_end - p.r_begin + 15) / 16;
   const int64_t W = (int64_t)gridDim.x * (kThreadsFaces / 32);
   int64_t b = blockIdx.x * (int64_t)(kThreadsFaces / 32) + w;
@@ -983,7 +1002,8 @@ __global__ void __launch_bounds__(kThreadsFaces, SFEM_FACE_CTAS) k_canon_faces(C
     const int span = (int)(2 * (a_end - a_first));
     const int off = (int)(2 * (a - a_first));
     face_pass<false>(p, tile, lane, valid, active, pecbits, len, off, span, sl, gS, fx, p.S + 4 * a_first);
-    face_pass<true>(p, tile, lane, valid, active, pecbits, len, off, span, sl, gT, fx, p.T + 4 * a_first);
+    face_pass<true>(p, tile + (SFEM_FACE_TILES - 1) * p.tile_chunks, lane, valid, active, pecbits, len, off, span, sl, gT, fx,
+                    p.T + 4 * a_first);
     r1a = r2a; r1b = r2b;
     i0 = i1; i1 = i2; i2 = i3;
     a = an; a1 = a1n;
@@ -1255,7 +1275,7 @@ int assemble_canonical_ST(const sfem_pattern_s* pat, const double* eps, const do
     SFEM_CHECK(pat->max_row_len_other <= 16, "a face is shared by more than two cells: not a valid tetrahedral mesh");
     p.r_begin = n_edge_rows; p.r_end = n_rows;
     p.tile_chunks = 16 * 2 * 16;
-    const size_t smem = (size_t)(kThreadsFaces / 32) * p.tile_chunks * sizeof(double2);
+    const size_t smem = (size_t)(kThreadsFaces / 32) * SFEM_FACE_TILES * p.tile_chunks * sizeof(double2);
     SFEM_CUDA(cudaFuncSetAttribute(k_canon_faces, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int64_t nblocks = (n_rows - n_edge_rows + kThreadsFaces / 2 - 1) / (kThreadsFaces / 2);
     const unsigned grid = (unsigned)std::min<int64_t>(nblocks, (int64_t)num_sms * SFEM_FACE_CTAS);
