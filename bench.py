@@ -54,6 +54,34 @@ def algorithmic_bytes(n_cells, n_vertices, nnz, n_mat=2):
     return 8 * nnz * n_mat + 16 * n_cells + 24 * n_vertices + 16 * n_cells
 
 
+def cube_counts(n):
+    """Closed-form sizes of UnitCube(n) with N1curl order 2 (the GPU arm asserts them)."""
+    E, F = 7 * n ** 3 + 9 * n ** 2 + 3 * n, 12 * n ** 3 + 6 * n ** 2
+    return {"tets": 6 * n ** 3, "vertices": (n + 1) ** 3, "ndof": 2 * E + 2 * F, "nnz": 1660 * n ** 3 + 348 * n ** 2 + 12 * n}
+
+
+def workload_config(n, world, kernel="auto"):
+    """`config` of the JSON line: identical for the GPU arm and for --impl reference (same workload; the CPU arm times
+    a bounded sample of it, described in its cpu_baseline.sample)."""
+    c = cube_counts(n)
+    return {"workload": "UnitCube(%d) N1curl order-2 S+T, PEC on all exterior faces, per-cell eps_r~U[1,16) "
+                        "mu_r~U[1,2)" % n, "tets": c["tets"], "ndof": c["ndof"], "nnz_per_matrix": c["nnz"],
+            "partition": "rows by DOF-entity ownership (one edge range + one face range per rank, each "
+                         "balanced by incidence count), %d rank(s), ghost cells duplicated" % world,
+            "l2": "outputs per step (%.1f GB over all ranks) exceed L2; no flush needed" % (16e-9 * c["nnz"]),
+            "kernel": kernel}
+
+
+def kernel_build_id():
+    """Short hash of the value-kernel sources: profiles/traffic.json is only quoted for the build it was captured on."""
+    import hashlib
+    h = hashlib.sha1()
+    for f in ('assemble_canonical.cu', 'pattern.cu', 'generated/canonical_rows.inc'):
+        with open(os.path.join(ROOT, 'sucem-fem_b200', 'csrc', f), 'rb') as fh:
+            h.update(fh.read())
+    return h.hexdigest()[:12]
+
+
 def peak_hbm():
     try:
         with open(os.path.join(ROOT, 'MEASURED_PEAKS.json')) as f:
@@ -103,13 +131,23 @@ class ClockSampler(threading.Thread):
                 "power_w_max": max((r[2] for r in self.rows), default=None)}
 
 
-def cpu_port_run(n, threads, steps, warmup=0):
+def slab_layers(n, target_tets):
+    """z-layers of UnitCube(n) that make a CPU sample of about target_tets tetrahedra."""
+    return max(2, min(n, int(round(target_tets / (6.0 * n * n)))))
+
+
+def cpu_port_run(n, threads, steps, warmup=0, nz=None):
     """C restatement of the reference algorithm on the host cores.  One step = the reference's whole path for one
     problem, host mesh in -> host CSR out: entity numbering + dof map (FunctionSpace), sparsity pattern + tensor init,
-    the cell loop for S and M, row-only ident on the PEC rows.  Returns a dict of rates (tets/s) and times."""
+    the cell loop for S and M, row-only ident on the PEC rows.  nz: only the first nz of the n z-layers of UnitCube(n)
+    (a bounded sample of the workload: same cross-section, same cell shapes).  Returns a dict of rates (tets/s) and times."""
     import numpy as np
     from oracle import cport, fem, meshes
-    co, ce = meshes.unit_cube(n)
+    if nz is None or nz >= n:
+        co, ce = meshes.unit_cube(n)
+    else:
+        co, ce = meshes.unit_cube(n, n, nz)
+        co[:, 2] *= float(nz) / n
     rng = np.random.default_rng(1234)
     eps, mu = rng.uniform(1, 16, len(ce)), rng.uniform(1, 2, len(ce))
     num = fem.number_entities(ce)                     # (untimed) only to list the PEC rows for the ident step
@@ -129,31 +167,34 @@ def cpu_port_run(n, threads, steps, warmup=0):
             t_vals.append(t2 - t1)
     dt, dv = sum(t_full) / len(t_full), sum(t_vals) / len(t_vals)
     return {"full": len(ce) / dt, "values_only": len(ce) / dv, "s_per_step": dt, "cells": len(ce),
-            "max_threads": A.max_threads()}
+            "threads": int(threads)}
 
 
 def run_reference(args):
-    """--impl reference: the reference's own algorithm on the host cores (oracle port; DOLFIN is not installable)."""
+    """--impl reference: the reference's own algorithm on the host cores (oracle port; DOLFIN is not installable).
+    Same config as the GPU arm; each step is a bounded sample of that workload (a slab of ~0.7 M tets of the same
+    cube) so that the run ends within minutes."""
     rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
     if rank != 0:
         return
     claim_stdout()
     from oracle import cport  # noqa: F401
     threads = os.cpu_count() or 1
-    n = 32
-    r = cpu_port_run(n, threads, max(args.steps, 1), min(args.warmup, 1))
+    n = args.n or WORKLOAD_N.get(max(world, args.gpus), 119)
+    nz = slab_layers(n, 700e3)
+    r = cpu_port_run(n, threads, max(args.steps, 1), min(args.warmup, 1), nz=nz)
     v = r["full"]
-    sample = ("UnitCube(%d) order 2, %d tets/step, host mesh in -> host CSR (S, M) out: numbering + dof map + pattern "
-              "(OpenMP over rows) + cell loop (OpenMP over cells, atomics; S and M in one sweep) + PEC ident; C "
-              "restatement of the reference algorithm (DOLFIN 1.0 is not installable here); cell loop + ident alone: "
-              "%.0f tets/s" % (n, r["cells"], r["values_only"]))
+    sample = ("the first %d of the %d z-layers of UnitCube(%d), order 2: %d tets/step, host mesh in -> host CSR (S, M) out: "
+              "numbering + dof map + pattern (OpenMP over rows) + cell loop (OpenMP over cells, atomics; S and M in one "
+              "sweep) + PEC ident; C restatement of the reference algorithm (DOLFIN 1.0 is not installable here), %d "
+              "threads; cell loop + ident alone: %.0f tets/s" % (nz, n, n, r["cells"], threads, r["values_only"]))
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": r["s_per_step"] * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "UnitCube(%d) order-2 S+T PEC, bounded CPU sample of the GPU arm's workload; same scope "
-                                   "as the GPU arm's e2e (host mesh in, host CSR out)" % n},
+            "config": workload_config(n, max(world, args.gpus)),
             "values_only": r["values_only"],
-            "cpu_baseline": {"value": v, "unit": UNIT, "cores": r["max_threads"], "kind": "port", "sample": sample},
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     emit(line)
 
@@ -172,6 +213,8 @@ def main():
     ap.add_argument('--check', dest='check', action='store_true', default=True,
                     help='after the timed region compare sampled rows of the timed matrices with the CPU oracle (default)')
     ap.add_argument('--no-check', dest='check', action='store_false')
+    ap.add_argument('--no-extras', action='store_true',
+                    help='skip the extra single-GPU measurements (config 5 streamed through one GPU, UnitCube(150), ...)')
     args = ap.parse_args()
     if args.impl == 'reference':
         return run_reference(args)
@@ -184,6 +227,7 @@ def main():
     import numpy as np
     import torch
     import torch.distributed as dist
+    import ctypes as C
     from sucemfem import device, _native as N
     rank = int(os.environ.get('RANK', '0'))
     local = int(os.environ.get('LOCAL_RANK', '0'))
@@ -258,30 +302,42 @@ def main():
     share = n_rows / float(space.ndof)
     b_alg = algorithmic_bytes(C_total * share, mesh.num_vertices * share, nnz)
     achieved = b_alg / (ms_local / K * 1e-3) / 1e9
-    traffic = None
-    try:  # DRAM bytes per step from the committed ncu capture of this workload (profiles/), if it is this workload
+    traffic, traffic_note = None, "no ncu capture of this build and workload is committed"
+    try:  # DRAM bytes per step from the committed ncu capture (profiles/), only if it is this workload AND this build
         with open(os.path.join(ROOT, 'profiles', 'traffic.json')) as f:
             tj = json.load(f)
-        if tj.get('n') == n and world == 1:
-            traffic = tj['dram_bytes_per_step']
+        if tj.get('n') == n and world == 1 and args.order == 2 and tj.get('kernel_build') == kernel_build_id():
+            traffic, traffic_note = tj['dram_bytes_per_step'], "ncu DRAM bytes of the same launches (%s)" % tj.get('source')
+        elif tj.get('kernel_build') != kernel_build_id():
+            traffic_note = "profiles/traffic.json was captured on another build of the value kernels: not quoted"
     except Exception:
         pass
+    fp64_peak = C.c_double(0.0)
+    N.check(N.lib.sfem_measure_fp64_peak(C.byref(fp64_peak), None))
+    torch.cuda.synchronize()
+    flop_per_tet = 5200.0 if args.order == 2 else 430.0   # algorithmic flops of S+T per tetrahedron
+    fp64_achieved = flop_per_tet * C_total * share / (ms_local / K * 1e-3) / 1e12
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": b_alg,
-                "kernel_ms": ms_local / K,
-                "note": "one step = the launches of one sfem_assemble_ST call (k_canon_edges + k_canon_faces), timed "
-                        "back to back with CUDA events on the launching stream; achieved = algorithmic bytes of the "
-                        "step / step time; traffic = ncu DRAM bytes of the same two launches"}
+                "traffic": traffic, "traffic_note": traffic_note, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": b_alg, "kernel_ms": ms_local / K,
+                "fp64_peak_tflops": fp64_peak.value, "fp64_achieved_tflops": fp64_achieved,
+                "fp64_frac": fp64_achieved / fp64_peak.value if fp64_peak.value > 0 else None,
+                "fp64_note": "algorithmic %.0f FLOP per tet (SURVEY 8d) x tets / step time against the DFMA rate measured "
+                             "in this run (sfem_measure_fp64_peak); the kernels execute ~1.8x that (row-owner gather: no "
+                             "use of the element matrices' symmetry, geometry per (entity, cell))" % flop_per_tet,
+                "note": "one step = the launches of one sfem_assemble_ST call (k_pack_coef + k_canon_edges2 + "
+                        "k_canon_faces), timed back to back with CUDA events on the launching stream; achieved = "
+                        "algorithmic bytes of the step / step time"}
 
+    cfg = workload_config(n, world, {0: "auto", 1: "generic", 2: "canonical"}[kernel])
+    if args.order == 2 and not args.n:
+        cc = cube_counts(n)
+        assert (C_total, space.ndof) == (cc["tets"], cc["ndof"]), 'closed-form workload sizes differ from the device'
+        assert world > 1 or nnz == cc["nnz"], 'closed-form nnz differs from the device pattern'
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "UnitCube(%d) N1curl order-2 S+T, PEC on all exterior faces, per-cell eps_r~U[1,16) "
-                                   "mu_r~U[1,2)" % n, "tets": C_total, "ndof": space.ndof, "nnz_per_matrix_this_rank": nnz,
-                       "partition": "rows by DOF-entity ownership (one edge range + one face range per rank, each "
-                                    "balanced by incidence count), %d rank(s), ghost cells duplicated" % world,
-                       "l2": "outputs per step (%.1f GB) exceed L2; no flush needed" % (16e-9 * nnz),
-                       "kernel": {0: "auto", 1: "generic", 2: "canonical"}[kernel]},
+            "dtype": "f64", "data": "synthetic", "config": cfg,
+            "nnz_per_matrix_this_rank": nnz,
             "setup_ms": setup_ms, "roofline": roofline, "gpu_launches": None,
             "per_rank_ms_per_step": [round(x, 3) for x in per_rank_ms]}
 
@@ -290,11 +346,10 @@ def main():
         line.update(check_timed_matrices(n, space, pats, vals, flags, eps, mu, rank, world))
 
     # ---- e2e through the public API with HOST buffers (rank-local; N=1 only measures the full pipeline) ---
+    line["gpu_launches"] = sum(launches_per_step(kernel, pat) for pat in pats) * K
+    del pats, vals, flags, markers, eps, mu, space, mesh     # the resident benchmark's buffers are not needed any more
+    _free_device()
     if not args.no_e2e:
-        line["gpu_launches"] = sum(launches_per_step(kernel, pat) for pat in pats) * K
-        del pats, vals, flags, markers, eps, mu, space, mesh     # the resident benchmark's buffers are not needed any more
-        torch.cuda.empty_cache()
-        N.check(N.lib.sfem_release_cached_memory())
         try:
             e2e = e2e_run(n, min(K, 9), rank, world)
         except Exception as e:  # noqa: BLE001   (e.g. not enough page-lockable host memory for this rank's share)
@@ -316,18 +371,22 @@ def main():
         line["e2e"] = e2e
     # ---- CPU baseline (rank 0, N=1): bounded sample, 1 thread = what sucemfem + DOLFIN 1.0 run ------------
     if rank == 0 and world == 1 and not args.no_cpu:
-        r1 = cpu_port_run(24, 1, 2)
-        rall = cpu_port_run(24, r1["max_threads"], 2, 1)
+        nz1, nzall = slab_layers(n, 80e3), slab_layers(n, 700e3)
+        r1 = cpu_port_run(n, 1, 2, nz=nz1)
+        threads = os.cpu_count() or 1
+        rall = cpu_port_run(n, threads, 2, 1, nz=nzall)
         line["cpu_baseline"] = {"value": r1["values_only"], "unit": UNIT, "cores": 1, "kind": "port",
-                                "sample": "UnitCube(24) order 2 (%d tets) x2 runs, serial cell loop + binary-search insertion "
-                                          "+ ident on a prebuilt pattern (the scope of `value`); with numbering + pattern "
-                                          "(the scope of `e2e`): %.0f tets/s; same code with %d OpenMP threads: %.0f / %.0f "
-                                          "tets/s" % (r1["cells"], r1["full"], r1["max_threads"], rall["values_only"],
-                                                      rall["full"])}
+                                "sample": "the first %d of the %d z-layers of UnitCube(%d), order 2 (%d tets) x2 runs, serial "
+                                          "cell loop + binary-search insertion + ident on a prebuilt pattern (the scope of "
+                                          "`value`); with numbering + pattern (the scope of `e2e`): %.0f tets/s; same code with "
+                                          "%d OpenMP threads on the first %d layers (%d tets): %.0f / %.0f tets/s"
+                                          % (nz1, n, n, r1["cells"], r1["full"], threads, nzall, rall["cells"],
+                                             rall["values_only"], rall["full"])}
+    # ---- extra single-GPU measurements (N=1): the stated target and the other kernels north_star names ----------------
+    if rank == 0 and world == 1 and not args.no_extras and not args.n and args.order == 2:
+        line["extras"] = run_extras(peak)
     if rank == 0:
         line["clocks"] = sampler.summary()
-        if line["gpu_launches"] is None:
-            line["gpu_launches"] = sum(launches_per_step(kernel, pat) for pat in pats) * K
         emit(line)
     if world > 1:
         dist.barrier()
@@ -377,6 +436,145 @@ def check_timed_matrices(n, space, pats, vals, flags, eps, mu, rank, world):
     if err:
         info["error"] = err
     return {"checked": ok, "check": info}
+
+
+def _free_device():
+    import gc
+    import torch
+    from sucemfem import _native as N
+    gc.collect()
+    torch.cuda.empty_cache()
+    N.check(N.lib.sfem_release_cached_memory())
+
+
+def _time_steps(step, steps, warmup=1):
+    import torch
+    for _ in range(warmup):
+        step()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / steps
+
+
+def extra_streamed_cube(n, peak, n_parts=8, steps=3):
+    """UnitCube(n) order-2 S+T on ONE GPU when S+T do not fit in HBM (n = 203 = BASELINE config 5: 2 x 111 GB): the
+    row blocks of the n_parts-way class partition (n_parts edge ranges + n_parts face ranges) are assembled one after the
+    other into a ring of two (S, T) buffer pairs and overwritten two blocks later.  All patterns stay resident (set-up,
+    timed separately); a step = the S and T values of ALL rows, exactly the work of the multi-GPU step on one device."""
+    import torch
+    from sucemfem import device
+    t0 = time.perf_counter()
+    mesh = device.DeviceMesh.unit(n, n, n)
+    space = device.DeviceSpace(mesh, 2)
+    torch.cuda.synchronize()
+    t_num = time.perf_counter()
+    eb, ob = space.partition_by_class(n_parts)
+    pats = []
+    for k in range(n_parts):
+        pats.append(device.DevicePattern(space, eb[k], eb[k + 1]))
+        pats.append(device.DevicePattern(space, ob[k], ob[k + 1]))
+    torch.cuda.synchronize()
+    t_pat = time.perf_counter()
+    markers = torch.zeros(space.n_facets, dtype=torch.int32, device='cuda')
+    space.mark_exterior_facets(markers, 999)
+    flags = space.pec_row_flags(markers, 999)
+    g = torch.Generator(device='cuda')
+    g.manual_seed(1234)
+    C_total = mesh.num_cells
+    eps = 1.0 + 15.0 * torch.rand(C_total, dtype=torch.float64, device='cuda', generator=g)
+    mu = 1.0 + torch.rand(C_total, dtype=torch.float64, device='cuda', generator=g)
+    cap = max(p.nnz for p in pats)
+    ring = [(torch.empty(cap, dtype=torch.float64, device='cuda'), torch.empty(cap, dtype=torch.float64, device='cuda'))
+            for _ in range(2)]
+    nnz = sum(p.nnz for p in pats)
+
+    def step():
+        for k, pat in enumerate(pats):
+            S, T = ring[k % 2]
+            pat.assemble_ST(eps, mu, flags, S[:pat.nnz], T[:pat.nnz])
+
+    ms = _time_steps(step, steps)
+    b_alg = algorithmic_bytes(C_total, mesh.num_vertices, nnz)
+    used = torch.cuda.memory_allocated()
+    res = {"workload": "UnitCube(%d) order-2 S+T PEC on ONE B200, %d row blocks assembled into a ring of two (S, T) buffer "
+                       "pairs (values overwritten two blocks later; patterns of all blocks resident)" % (n, len(pats)),
+           "tets": C_total, "nnz_per_matrix": nnz, "ms_per_step": ms, "value": C_total / (ms * 1e-3), "unit": UNIT,
+           "roofline_frac": b_alg / (ms * 1e-3) / 1e9 / peak, "achieved_GBps": b_alg / (ms * 1e-3) / 1e9,
+           "numbering_s": round(t_num - t0, 3), "pattern_fill_s": round(t_pat - t_num, 3),
+           "ring_bytes": 4 * cap * 8, "torch_allocated_bytes": used}
+    del pats, ring, flags, markers, eps, mu, space, mesh
+    _free_device()
+    return res
+
+
+def extra_resident(n, order, peak, gdim=3, abc=False, steps=5):
+    """Resident single-GPU step of another workload: tets of order 1 / 2 (optionally with the ABC matrix S_0 and no PEC:
+    BASELINE config 4) or triangles (gdim = 2, UnitSquare(n))."""
+    import torch
+    from sucemfem import device, _native as N
+    mesh = device.DeviceMesh.unit(n, n, n if gdim == 3 else 0)
+    space = device.DeviceSpace(mesh, order)
+    pat = device.DevicePattern(space, 0, -1)
+    flags = None
+    if not abc:
+        markers = torch.zeros(space.n_facets, dtype=torch.int32, device='cuda')
+        space.mark_exterior_facets(markers, 999)
+        flags = space.pec_row_flags(markers, 999)
+    g = torch.Generator(device='cuda')
+    g.manual_seed(1234)
+    C_total = mesh.num_cells
+    eps = 1.0 + 15.0 * torch.rand(C_total, dtype=torch.float64, device='cuda', generator=g)
+    mu = 1.0 + torch.rand(C_total, dtype=torch.float64, device='cuda', generator=g)
+    S, T = pat.new_values(), pat.new_values()
+    S0 = pat.new_abc_values() if abc else None
+
+    def step():
+        pat.assemble_ST(eps, mu, flags, S, T)
+        if abc:
+            pat.assemble_abc(out=S0)
+
+    ms = _time_steps(step, steps, warmup=2)
+    nv = gdim + 1
+    b_alg = 8 * pat.nnz * 2 + 4 * nv * C_total + 8 * gdim * mesh.num_vertices + 16 * C_total
+    if abc:
+        b_alg += 8 * S0.numel()
+    res = {"workload": "%s order-%d S+T%s, %s" % ("UnitCube(%d)" % n if gdim == 3 else "UnitSquare(%d)" % n, order,
+                                                 "+S_0 (compact boundary rows)" if abc else "",
+                                                 "1st-order ABC on all exterior faces, no PEC" if abc else "PEC"),
+           "cells": C_total, "nnz_per_matrix": pat.nnz, "ms_per_step": ms, "value": C_total / (ms * 1e-3),
+           "unit": "cells/s", "roofline_frac": b_alg / (ms * 1e-3) / 1e9 / peak, "achieved_GBps": b_alg / (ms * 1e-3) / 1e9,
+           "algorithmic_bytes": b_alg}
+    if abc:
+        res["abc_nnz"] = int(S0.numel())
+    del pat, S, T, S0, flags, eps, mu, space, mesh
+    _free_device()
+    return res
+
+
+def run_extras(peak):
+    """Measurements next to the headline line (N=1 only; each one frees its buffers).  Failures are reported, not fatal."""
+    out = {}
+    jobs = [("config5_one_gpu_streamed", lambda: extra_streamed_cube(203, peak)),
+            ("unitcube150_resident", lambda: extra_resident(150, 2, peak)),
+            ("config4_abc_order2", lambda: extra_resident(119, 2, peak, abc=True)),
+            ("config4_abc_order1", lambda: extra_resident(119, 1, peak, abc=True)),
+            ("unitcube119_order1", lambda: extra_resident(119, 1, peak)),
+            ("unitsquare4096_order2", lambda: extra_resident(4096, 2, peak, gdim=2)),
+            ("unitsquare4096_order1", lambda: extra_resident(4096, 1, peak, gdim=2))]
+    for name, fn in jobs:
+        t0 = time.perf_counter()
+        try:
+            out[name] = fn()
+        except Exception as e:  # noqa: BLE001
+            out[name] = {"error": repr(e)[:300]}
+            _free_device()
+        out[name]["wall_s"] = round(time.perf_counter() - t0, 2)
+    return out
 
 
 def host_memory_available():

@@ -170,6 +170,24 @@ SFEM_API int sfem_bicgstab(sfem_pattern_t pat, int n_mats, const double* const* 
                   const double* d_b, double* d_x, int preconditioner, double rtol, int maxiter, int* iterations,
                   double* relres, void* stream);
 
+/* Compact storage of the ABC matrix S_0 (/root/reference/sucemfem/BoundaryConditions/ABC.py:56-57): only the rows of
+ * DOF entities that lie ON an exterior facet are non-zero (a basis function has no tangential trace on a facet that
+ * does not contain its entity), so only those rows are stored, each with the columns of the same row of the S/M
+ * pattern: compact values == the boundary rows of the full-pattern S_0 of sfem_assemble(SFEM_FORM_ABC), bit for bit,
+ * and no nnz-sized array has to be cleared.  Dirichlet rows inside the set become unit rows; Dirichlet rows outside
+ * it exist only in the full form.
+ *   sfem_abc_info     dof rows and non-zeros of the compact storage (builds the row list on first use)
+ *   sfem_abc_export   d_rows[n_rows] global dof row numbers, d_rowptr[n_rows+1], d_cols[nnz] (or NULL)
+ *   sfem_assemble_abc values into d_values_compact[nnz]; d_facet_mask as in sfem_assemble
+ * Consumers: OR SFEM_MATS_LAST_IS_ABC_COMPACT into n_mats of sfem_matvec / sfem_bicgstab when the LAST value array is
+ * in this storage (A = S - k0^2 M + j k0 S_0 applied without a full-pattern S_0,
+ * /root/reference/sucemfem/ProblemConfigurations/EMDrivenProblem.py:67-72). */
+#define SFEM_MATS_LAST_IS_ABC_COMPACT 0x100
+SFEM_API int sfem_abc_info(sfem_pattern_t pat, void* stream, int64_t* n_rows, int64_t* nnz);
+SFEM_API int sfem_abc_export(sfem_pattern_t pat, int64_t* d_rows, int64_t* d_rowptr, int32_t* d_cols, void* stream);
+SFEM_API int sfem_assemble_abc(sfem_pattern_t pat, const uint8_t* d_facet_mask, const uint8_t* d_pec_row_flags,
+                               double* d_values_compact, void* stream);
+
 /* Sustained fp64 FMA rate of the current device in TFLOP/s (8 independent DFMA chains per thread on every SM): the
  * denominator of the fp64 roofline bench.py reports; no counterpart in the reference (measurement support). */
 SFEM_API int sfem_measure_fp64_peak(double* tflops, void* stream);

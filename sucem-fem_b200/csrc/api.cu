@@ -190,6 +190,34 @@ __global__ void k_ident(const int64_t* __restrict__ ent_rowptr, const int32_t* _
 }
 
 }  // namespace
+// dof-level CSR of the compact ABC storage: global dof row numbers, row pointer, (optionally) column ids
+__global__ void k_abc_export(const int64_t* __restrict__ ent_rowptr, const int32_t* __restrict__ ent_cols,
+                             const int64_t* __restrict__ list, const int64_t* __restrict__ out_rowptr, int64_t n_list,
+                             int q, int64_t ent_lo, int64_t* __restrict__ rows, int64_t* __restrict__ rowptr,
+                             int32_t* __restrict__ cols) {
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t i = blockIdx.x * (int64_t)(blockDim.x >> 5) + w;
+  if (i > n_list) return;
+  if (i == n_list) {
+    if (lane == 0) rowptr[q * i] = (int64_t)q * q * out_rowptr[i];
+    return;
+  }
+  const int64_t r = list[i], a = ent_rowptr[r], ao = out_rowptr[i];
+  const int len = (int)(ent_rowptr[r + 1] - a);
+  for (int k = 0; k < q; ++k) {
+    const int64_t rs = (int64_t)q * q * ao + (int64_t)k * q * len;
+    if (lane == 0) {
+      rows[q * i + k] = q * (ent_lo + r) + k;
+      rowptr[q * i + k] = rs;
+    }
+    if (cols)
+      for (int idx = lane; idx < q * len; idx += 32) {
+        const int s = idx / q, kp = idx - s * q;
+        cols[rs + idx] = q * ent_cols[a + s] + kp;
+      }
+  }
+}
+
 }  // namespace sfem
 
 using namespace sfem;
@@ -508,6 +536,37 @@ int sfem_assemble(sfem_pattern_t pat, int form, const double* d_coef, const uint
   const double* eps = form == SFEM_FORM_MASS ? d_coef : nullptr;
   const double* mu = form == SFEM_FORM_STIFFNESS ? d_coef : nullptr;
   return assemble_generic(pat, form, eps, mu, d_facet_mask, d_pec_row_flags, d_values, nullptr, (cudaStream_t)stream);
+}
+
+int sfem_abc_info(sfem_pattern_t pat, void* stream, int64_t* n_rows, int64_t* nnz) {
+  SFEM_CHECK(pat, "NULL pattern");
+  DeviceGuard dg(pat->space->mesh->device);
+  SFEM_TRY(build_abc_rows(pat, (cudaStream_t)stream));
+  const int q = pat->space->order;
+  if (n_rows) *n_rows = q * pat->n_abc_rows;
+  if (nnz) *nnz = (int64_t)q * q * pat->abc_nnz_ent;
+  return 0;
+}
+
+int sfem_abc_export(sfem_pattern_t pat, int64_t* d_rows, int64_t* d_rowptr, int32_t* d_cols, void* stream) {
+  SFEM_CHECK(pat && d_rows && d_rowptr, "NULL argument");
+  SFEM_CHECK(!d_cols || pat->space->ndof < (int64_t)2147483647, "column ids exceed int32");
+  DeviceGuard dg(pat->space->mesh->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  SFEM_TRY(build_abc_rows(pat, st));
+  const int64_t n = pat->n_abc_rows;
+  k_abc_export<<<(unsigned)((n + 1 + 7) / 8), 256, 0, st>>>(pat->ent_rowptr, pat->ent_cols, pat->abc_rows, pat->abc_rowptr, n,
+                                                          pat->space->order, pat->ent_lo, d_rows, d_rowptr, d_cols);
+  SFEM_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int sfem_assemble_abc(sfem_pattern_t pat, const uint8_t* d_facet_mask, const uint8_t* d_pec_row_flags,
+                      double* d_values_compact, void* stream) {
+  SFEM_CHECK(pat && d_values_compact, "NULL argument");
+  DeviceGuard dg(pat->space->mesh->device);
+  return assemble_generic(pat, SFEM_FORM_ABC, nullptr, nullptr, d_facet_mask, d_pec_row_flags, d_values_compact, nullptr,
+                          (cudaStream_t)stream, true);
 }
 
 int sfem_assemble_ST(sfem_pattern_t pat, const double* d_eps_r, const double* d_mu_r,

@@ -1200,7 +1200,8 @@ bool canonical_supported(const sfem_pattern_s* pat) {
 int canonical_launches(const sfem_pattern_s* pat) {
   if (pat->space->order == 1) return 1;
   const int64_t E = pat->space->E;
-  return (pat->ent_lo < E ? 1 : 0) + (pat->ent_hi > E ? 1 : 0);
+  // edge rows: k_pack_coef + k_canon_edges2 (or the lane-pair kernel alone); face rows: k_canon_faces
+  return (pat->ent_lo < E ? (pat->rec_e2 ? 2 : 1) : 0) + (pat->ent_hi > E ? 1 : 0);
 }
 
 // (mu_r, eps_r) of every cell side by side: one 16-byte gather per item instead of two 8-byte ones

@@ -194,6 +194,7 @@ struct PatView {
   bool canon;  // slot table in canonical column order
   const int64_t* row_list;  // optional: only these block-relative row entities are assembled (ABC: boundary rows)
   int64_t n_list;
+  const int64_t* out_rowptr;  // optional (with row_list): entity-level output offset of list entry i (compact S_0)
 };
 
 constexpr int kWarps = 8;
@@ -209,6 +210,7 @@ k_values_generic(PatView pv, const double* __restrict__ geo, const double* __res
   constexpr int Q = ORDER, NP = El::NP, NFAC = DIM + 1;
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
   int64_t r = blockIdx.x * (int64_t)kWarps + w;
+  const int64_t li = r;
   if (pv.row_list) {
     if (r >= pv.n_list) return;
     r = pv.row_list[r];
@@ -217,9 +219,10 @@ k_values_generic(PatView pv, const double* __restrict__ geo, const double* __res
   const int64_t g = pv.ent_lo + r;
   const int64_t a = pv.ent_rowptr[r];
   const int len = (int)(pv.ent_rowptr[r + 1] - a);
+  const int64_t a_out = pv.out_rowptr ? pv.out_rowptr[li] : a;
   const int64_t i0 = pv.inc_ptr[g], i1 = pv.inc_ptr[g + 1];
   for (int k = 0; k < Q; ++k) {
-    const int64_t rs = (int64_t)Q * Q * a + (int64_t)k * Q * len;
+    const int64_t rs = (int64_t)Q * Q * a_out + (int64_t)k * Q * len;
     const bool pecrow = pec && pec[Q * g + k];
     for (int idx = lane; idx < Q * len; idx += 32) {
       const int s = idx / Q, kp = idx - s * Q;
@@ -540,7 +543,16 @@ __global__ void k_ident_rows(const int64_t* __restrict__ ent_rowptr, const int32
   }
 }
 
-static int build_abc_rows(sfem_pattern_s* pat, cudaStream_t st) {
+__global__ void k_list_row_len(const int64_t* __restrict__ ent_rowptr, const int64_t* __restrict__ list, int64_t n,
+                               int64_t* __restrict__ len) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i > n) return;
+  len[i] = i < n ? ent_rowptr[list[i] + 1] - ent_rowptr[list[i]] : 0;
+}
+
+}  // namespace
+
+int build_abc_rows(sfem_pattern_s* pat, cudaStream_t st) {
   if (pat->n_abc_rows >= 0) return 0;
   const sfem_space_s* sp = pat->space;
   const int64_t n = pat->n_rows_ent;
@@ -565,28 +577,44 @@ static int build_abc_rows(sfem_pattern_s* pat, cudaStream_t st) {
   SFEM_CUDA(cudaMemcpyAsync(&h, d_count, 8, cudaMemcpyDeviceToHost, st));
   SFEM_CUDA(cudaStreamSynchronize(st));
   dev_free(tmp, st); dev_free(flags, st); dev_free(d_count, st);
+  // offsets of the listed rows in the compact storage: exclusive scan of their lengths
+  int64_t* len = nullptr;
+  SFEM_CUDA(dev_malloc(&len, (h + 1) * 8, st));
+  SFEM_CUDA(dev_malloc(&pat->abc_rowptr, (h + 1) * 8, st));
+  k_list_row_len<<<(unsigned)((h + 1 + 255) / 256), 256, 0, st>>>(pat->ent_rowptr, pat->abc_rows, h, len);
+  tb = 0;
+  SFEM_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tb, len, pat->abc_rowptr, (int)(h + 1), st));
+  SFEM_CUDA(dev_malloc(&tmp, tb + 16, st));
+  SFEM_CUDA(cub::DeviceScan::ExclusiveSum(tmp, tb, len, pat->abc_rowptr, (int)(h + 1), st));
+  SFEM_CUDA(cudaMemcpyAsync(&pat->abc_nnz_ent, pat->abc_rowptr + h, 8, cudaMemcpyDeviceToHost, st));
+  SFEM_CUDA(cudaStreamSynchronize(st));
+  dev_free(tmp, st); dev_free(len, st);
   pat->n_abc_rows = h;
   return 0;
 }
 
+namespace {
+
 template <int DIM, int ORDER>
 int launch_generic(const sfem_pattern_s* pat, int form, const double* coef_a, const double* coef_b,
                    const uint8_t* facet_mask, const uint8_t* pec, double* out_a, double* out_b,
-                   cudaStream_t st) {
+                   cudaStream_t st, bool abc_compact) {
   const sfem_space_s* sp = pat->space;
   const sfem_mesh_s* m = sp->mesh;
   PatView pv{sp->inc_ptr, sp->inc_cell, sp->inc_loc, pat->ent_rowptr, pat->ent_cols, pat->pos,
-             pat->ent_lo, pat->n_rows_ent, pat->inc_base, sp->n_ent_cell, pos_is_canonical(sp), nullptr, 0};
+             pat->ent_lo, pat->n_rows_ent, pat->inc_base, sp->n_ent_cell, pos_is_canonical(sp), nullptr, 0, nullptr};
   if (pat->n_rows_ent == 0) return 0;
   unsigned grid = (unsigned)((pat->n_rows_ent + kWarps - 1) / kWarps);
   if (form == SFEM_FORM_ABC) {
-    // S_0 lives on the S/M pattern but only rows next to the boundary are non-zero: clear everything at memset
-    // speed, assemble the boundary rows, then write the unit rows of Dirichlet dofs (which may be interior)
+    // Only the rows of entities ON the boundary are non-zero.  Full form: S_0 lives on the S/M pattern -- clear
+    // everything at memset speed, assemble the boundary rows, then write the unit rows of Dirichlet dofs (which may be
+    // interior).  Compact form: only those rows are stored (offsets abc_rowptr), nothing to clear.
     SFEM_TRY(build_abc_rows(const_cast<sfem_pattern_s*>(pat), st));
     const int64_t nnz = (int64_t)ORDER * ORDER * pat->nnz_ent;
-    SFEM_CUDA(cudaMemsetAsync(out_a, 0, nnz * sizeof(double), st));
+    if (!abc_compact) SFEM_CUDA(cudaMemsetAsync(out_a, 0, nnz * sizeof(double), st));
     pv.row_list = pat->abc_rows;
     pv.n_list = pat->n_abc_rows;
+    if (abc_compact) pv.out_rowptr = pat->abc_rowptr;
     grid = (unsigned)((pat->n_abc_rows + kWarps - 1) / kWarps);
   }
   const int32_t* cell_facets = DIM == 3 ? sp->cell_faces : sp->cell_edges;
@@ -608,8 +636,9 @@ int launch_generic(const sfem_pattern_s* pat, int form, const double* coef_a, co
     case SFEM_FORM_ABC:
       if (grid > 0)
         k_values_generic<DIM, ORDER, 2><<<grid, kWarps * 32, 0, st>>>(pv, geo, m->coords, m->cells, cell_facets,
-                                                                     sp->cell_extmask, facet_mask, nullptr, out_a, nullptr);
-      if (pec)
+                                                                     sp->cell_extmask, facet_mask,
+                                                                     abc_compact ? pec : nullptr, out_a, nullptr);
+      if (pec && !abc_compact)
         k_ident_rows<<<(unsigned)((pat->n_rows_ent + 7) / 8), 256, 0, st>>>(pat->ent_rowptr, pat->ent_cols, ORDER,
                                                                           pat->ent_lo, pat->n_rows_ent, pec, out_a);
       break;
@@ -628,12 +657,12 @@ int launch_generic(const sfem_pattern_s* pat, int form, const double* coef_a, co
 // S -> out_a, M -> out_b with coef_a = eps_r, coef_b = mu_r.
 int assemble_generic(const sfem_pattern_s* pat, int form, const double* coef_a, const double* coef_b,
                      const uint8_t* facet_mask, const uint8_t* pec, double* out_a, double* out_b,
-                     cudaStream_t st) {
+                     cudaStream_t st, bool abc_compact) {
   const int dim = pat->space->mesh->gdim, order = pat->space->order;
-  if (dim == 3 && order == 1) return launch_generic<3, 1>(pat, form, coef_a, coef_b, facet_mask, pec, out_a, out_b, st);
-  if (dim == 3 && order == 2) return launch_generic<3, 2>(pat, form, coef_a, coef_b, facet_mask, pec, out_a, out_b, st);
-  if (dim == 2 && order == 1) return launch_generic<2, 1>(pat, form, coef_a, coef_b, facet_mask, pec, out_a, out_b, st);
-  if (dim == 2 && order == 2) return launch_generic<2, 2>(pat, form, coef_a, coef_b, facet_mask, pec, out_a, out_b, st);
+  if (dim == 3 && order == 1) return launch_generic<3, 1>(pat, form, coef_a, coef_b, facet_mask, pec, out_a, out_b, st, abc_compact);
+  if (dim == 3 && order == 2) return launch_generic<3, 2>(pat, form, coef_a, coef_b, facet_mask, pec, out_a, out_b, st, abc_compact);
+  if (dim == 2 && order == 1) return launch_generic<2, 1>(pat, form, coef_a, coef_b, facet_mask, pec, out_a, out_b, st, abc_compact);
+  if (dim == 2 && order == 2) return launch_generic<2, 2>(pat, form, coef_a, coef_b, facet_mask, pec, out_a, out_b, st, abc_compact);
   set_error("unsupported (dim, order)");
   return 2;
 }
@@ -655,7 +684,7 @@ int assemble_rows_ST(const sfem_pattern_s* pat, const double* eps, const double*
   }
   if (pat->n_rows_ent == 0) return 0;
   PatView pv{sp->inc_ptr, sp->inc_cell, sp->inc_loc, pat->ent_rowptr, pat->ent_cols, pat->pos,
-             pat->ent_lo, pat->n_rows_ent, pat->inc_base, sp->n_ent_cell, pos_is_canonical(sp), nullptr, 0};
+             pat->ent_lo, pat->n_rows_ent, pat->inc_base, sp->n_ent_cell, pos_is_canonical(sp), nullptr, 0, nullptr};
   if (m->gdim == 3) {
     // tile = 32 rows of the longest length, capped so that several CTAs stay resident (longer spans write directly)
     constexpr int kWarpsT1 = kTet1Threads / 32;

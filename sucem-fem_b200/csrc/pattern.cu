@@ -487,6 +487,7 @@ void free_pattern_buffers(sfem_pattern_s* pat, cudaStream_t st) {
   dev_free(pat->rec_e2, st); pat->rec_e2 = nullptr;
   dev_free(pat->aux_e2, st); pat->aux_e2 = nullptr;
   dev_free(pat->abc_rows, st); pat->abc_rows = nullptr;
+  dev_free(pat->abc_rowptr, st); pat->abc_rowptr = nullptr;
 }
 
 int export_pattern(const sfem_pattern_s* pat, int64_t* d_rowptr, int32_t* d_cols, cudaStream_t st, int64_t nnz_base) {

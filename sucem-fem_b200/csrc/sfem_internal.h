@@ -151,6 +151,8 @@ struct sfem_pattern_s {
   int64_t n_batch_e2 = 0;
   int64_t* abc_rows = nullptr;    // block-relative row entities that lie on an exterior facet (lazily built)
   int64_t n_abc_rows = -1;
+  int64_t* abc_rowptr = nullptr;  // [n_abc_rows+1] entity-level offsets of those rows in the COMPACT S_0 storage
+  int64_t abc_nnz_ent = 0;
   int64_t inc_base = 0;           // = space->inc_ptr[ent_lo]
   int64_t n_inc_block = 0;
   int max_row_len = 0;            // longest entity row of the block
@@ -198,7 +200,9 @@ int build_pattern_block(sfem_pattern_s* pat, const int64_t* rowptr_all, int64_t 
 int export_pattern(const sfem_pattern_s* pat, int64_t* d_rowptr, int32_t* d_cols, cudaStream_t st, int64_t nnz_base = 0);
 int assemble_generic(const sfem_pattern_s* pat, int form, const double* coef_a, const double* coef_b,
                      const uint8_t* facet_mask, const uint8_t* pec, double* out_a, double* out_b,
-                     cudaStream_t st);
+                     cudaStream_t st, bool abc_compact = false);
+// boundary-row list + compact offsets of the ABC matrix (lazily built, synchronises `st` the first time)
+int build_abc_rows(sfem_pattern_s* pat, cudaStream_t st);
 int assemble_rows_ST(const sfem_pattern_s* pat, const double* eps, const double* mu, const uint8_t* pec, double* S,
                      double* T, cudaStream_t st);
 bool rows_supported(const sfem_pattern_s* pat);

@@ -32,7 +32,55 @@ struct MatvecArgs {
   double cre[kMaxMats], cim[kMaxMats];
   int n_mats;
   int64_t n_rows_ent;
+  // optional last term in compact boundary-row storage (S_0, sfem_assemble_abc): y += c * S0 x over the listed rows
+  const double* __restrict__ abc_vals;
+  const int64_t* __restrict__ abc_rows;
+  const int64_t* __restrict__ abc_rowptr;
+  int64_t n_abc;
+  double abc_cre, abc_cim;
 };
+
+// y[q*r + k] += c * sum_cols S0[q*r + k, col] x[col] for the row entities of the compact ABC storage: one warp per row
+// entity (the boundary rows are a vanishing share of the matrix: no tuning).
+template <int Q, bool CPLX>
+__global__ void k_matvec_abc(MatvecArgs p, const double* __restrict__ x, double* __restrict__ y) {
+  const int lane = threadIdx.x & 31;
+  const int64_t i = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  if (i >= p.n_abc) return;
+  const int64_t r = p.abc_rows[i], a = p.ent_rowptr[r], ao = p.abc_rowptr[i];
+  const int len = (int)(p.ent_rowptr[r + 1] - a);
+  for (int k = 0; k < Q; ++k) {
+    double2 acc = make_double2(0.0, 0.0);
+    for (int idx = lane; idx < Q * len; idx += 32) {
+      const int s = idx / Q, kp = idx - s * Q;
+      const double v = p.abc_vals[(int64_t)Q * Q * ao + (int64_t)k * Q * len + idx];
+      const int64_t c = (int64_t)Q * p.ent_cols[a + s] + kp;
+      if (CPLX) {
+        const double2 xv = reinterpret_cast<const double2*>(x)[c];
+        acc.x = fma(v, xv.x, acc.x);
+        acc.y = fma(v, xv.y, acc.y);
+      } else {
+        acc.x = fma(v, x[c], acc.x);
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      acc.x += __shfl_xor_sync(0xffffffffu, acc.x, o);
+      if (CPLX) acc.y += __shfl_xor_sync(0xffffffffu, acc.y, o);
+    }
+    if (lane == 0) {
+      if (CPLX) {
+        double2* yy = reinterpret_cast<double2*>(y) + Q * r + k;
+        double2 t = *yy;
+        t.x += p.abc_cre * acc.x - p.abc_cim * acc.y;
+        t.y += p.abc_cre * acc.y + p.abc_cim * acc.x;
+        *yy = t;
+      } else {
+        y[Q * r + k] += p.abc_cre * acc.x;
+      }
+    }
+  }
+}
 
 __device__ __forceinline__ double2 cfma(double2 acc, double2 a, double2 b) {  // acc + a*b
   acc.x = fma(a.x, b.x, acc.x);
@@ -156,9 +204,34 @@ __global__ void k_inv_diag(MatvecArgs p, int64_t ent_lo, double2* __restrict__ o
       dre = fma(p.cre[m], v, dre);
       dim = fma(p.cim[m], v, dim);
     }
-    const double n2 = dre * dre + dim * dim;
-    out[Q * r + k] = n2 > 0.0 ? make_double2(dre / n2, -dim / n2) : make_double2(1.0, 0.0);
+    out[Q * r + k] = make_double2(dre, dim);
   }
+}
+// + the diagonal of the compact ABC term
+template <int Q>
+__global__ void k_diag_abc(MatvecArgs p, int64_t ent_lo, double2* __restrict__ out) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= p.n_abc) return;
+  const int64_t r = p.abc_rows[i], a = p.ent_rowptr[r], ao = p.abc_rowptr[i];
+  const int len = (int)(p.ent_rowptr[r + 1] - a);
+  int lo = 0, hi = len - 1;
+  const int32_t g = (int32_t)(ent_lo + r);
+  while (lo < hi) {
+    int mid = (lo + hi) >> 1;
+    if (p.ent_cols[a + mid] < g) lo = mid + 1; else hi = mid;
+  }
+  for (int k = 0; k < Q; ++k) {
+    const double v = p.abc_vals[(int64_t)Q * Q * ao + (int64_t)k * Q * len + (int64_t)Q * lo + k];
+    out[Q * r + k].x += p.abc_cre * v;
+    out[Q * r + k].y += p.abc_cim * v;
+  }
+}
+__global__ void k_invert_diag(double2* __restrict__ d, int64_t n) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double2 v = d[i];
+  const double n2 = v.x * v.x + v.y * v.y;
+  d[i] = n2 > 0.0 ? make_double2(v.x / n2, -v.y / n2) : make_double2(1.0, 0.0);
 }
 
 // ---- complex vector kernels of the solver (deterministic two-stage reductions) ---------------------------------
@@ -269,8 +342,23 @@ __global__ void k_residual(const double2* __restrict__ b, const double2* __restr
 
 inline unsigned grid_for(int64_t n, int bs = 256) { return (unsigned)((n + bs - 1) / bs); }
 
-int fill_args(const sfem_pattern_s* pat, int n_mats, const double* const* d_values, const double* coef, MatvecArgs* a) {
-  SFEM_CHECK(n_mats >= 1 && n_mats <= kMaxMats, "n_mats must be between 1 and 4");
+int fill_args(sfem_pattern_s* pat, int n_mats_flags, const double* const* d_values, const double* coef, MatvecArgs* a,
+              cudaStream_t st) {
+  const bool last_compact = (n_mats_flags & SFEM_MATS_LAST_IS_ABC_COMPACT) != 0;
+  const int n_all = n_mats_flags & 0xff;
+  SFEM_CHECK(n_all >= 1 && n_all <= kMaxMats, "n_mats must be between 1 and 4");
+  const int n_mats = last_compact ? n_all - 1 : n_all;
+  a->abc_vals = nullptr; a->abc_rows = nullptr; a->abc_rowptr = nullptr; a->n_abc = 0; a->abc_cre = a->abc_cim = 0.0;
+  if (last_compact) {
+    SFEM_CHECK(d_values[n_all - 1], "NULL value array");
+    SFEM_TRY(build_abc_rows(pat, st));
+    a->abc_vals = d_values[n_all - 1];
+    a->abc_rows = pat->abc_rows;
+    a->abc_rowptr = pat->abc_rowptr;
+    a->n_abc = pat->n_abc_rows;
+    a->abc_cre = coef ? coef[2 * (n_all - 1)] : 1.0;
+    a->abc_cim = coef ? coef[2 * (n_all - 1) + 1] : 0.0;
+  }
   a->ent_rowptr = pat->ent_rowptr;
   a->ent_cols = pat->ent_cols;
   a->n_mats = n_mats;
@@ -296,15 +384,27 @@ void launch_matvec_nm(const MatvecArgs& a, unsigned grid, const double* x, doubl
 
 int launch_matvec(const sfem_pattern_s* pat, const MatvecArgs& a, bool cplx, const double* x, double* y, cudaStream_t st) {
   if (pat->n_rows_ent == 0) return 0;
+  const int q0 = pat->space->order;
+  if (a.n_mats == 0)  // only the compact term: y = 0 first
+    SFEM_CUDA(cudaMemsetAsync(y, 0, (size_t)q0 * pat->n_rows_ent * (cplx ? 16 : 8), st));
   int num_sms = 148;
   SFEM_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, pat->device));
   // persistent: as many CTAs as are resident (3 per SM by the kernel's launch bounds), at most one row per half-warp
   const unsigned grid = (unsigned)std::min<int64_t>((int64_t)num_sms * 3, grid_for(pat->n_rows_ent * 16));
   const int q = pat->space->order;
-  if (q == 2 && cplx) launch_matvec_nm<2, true>(a, grid, x, y, st);
-  else if (q == 2) launch_matvec_nm<2, false>(a, grid, x, y, st);
-  else if (cplx) launch_matvec_nm<1, true>(a, grid, x, y, st);
-  else launch_matvec_nm<1, false>(a, grid, x, y, st);
+  if (a.n_mats > 0) {
+    if (q == 2 && cplx) launch_matvec_nm<2, true>(a, grid, x, y, st);
+    else if (q == 2) launch_matvec_nm<2, false>(a, grid, x, y, st);
+    else if (cplx) launch_matvec_nm<1, true>(a, grid, x, y, st);
+    else launch_matvec_nm<1, false>(a, grid, x, y, st);
+  }
+  if (a.n_abc > 0) {
+    const unsigned g2 = grid_for(a.n_abc * 32);
+    if (q == 2 && cplx) k_matvec_abc<2, true><<<g2, 256, 0, st>>>(a, x, y);
+    else if (q == 2) k_matvec_abc<2, false><<<g2, 256, 0, st>>>(a, x, y);
+    else if (cplx) k_matvec_abc<1, true><<<g2, 256, 0, st>>>(a, x, y);
+    else k_matvec_abc<1, false><<<g2, 256, 0, st>>>(a, x, y);
+  }
   SFEM_CUDA(cudaGetLastError());
   return 0;
 }
@@ -324,9 +424,11 @@ int sfem_matvec(sfem_pattern_t pat, int n_mats, const double* const* d_values, c
   SFEM_CHECK(pat && d_values && d_x && d_y, "NULL argument");
   DeviceGuard dg(pat->device);
   MatvecArgs a;
-  SFEM_TRY(fill_args(pat, n_mats, d_values, coef_re_im, &a));
-  if (!complex_vectors)
-    for (int m = 0; m < n_mats; ++m) SFEM_CHECK(a.cim[m] == 0.0, "real vectors need real coefficients");
+  SFEM_TRY(fill_args(pat, n_mats, d_values, coef_re_im, &a, (cudaStream_t)stream));
+  if (!complex_vectors) {
+    for (int m = 0; m < a.n_mats; ++m) SFEM_CHECK(a.cim[m] == 0.0, "real vectors need real coefficients");
+    SFEM_CHECK(a.abc_cim == 0.0, "real vectors need real coefficients");
+  }
   return launch_matvec(pat, a, complex_vectors != 0, d_x, d_y, (cudaStream_t)stream);
 }
 
@@ -339,7 +441,7 @@ int sfem_bicgstab(sfem_pattern_t pat, int n_mats, const double* const* d_values,
   DeviceGuard dg(pat->device);
   cudaStream_t st = (cudaStream_t)stream;
   MatvecArgs a;
-  SFEM_TRY(fill_args(pat, n_mats, d_values, coef_re_im, &a));
+  SFEM_TRY(fill_args(pat, n_mats, d_values, coef_re_im, &a, st));
   const int64_t n = pat->space->ndof;
   const int q = pat->space->order;
   double2* work = nullptr;  // r, rhat, p, v, s, t, phat, shat, minv + reduction scratch
@@ -374,6 +476,11 @@ int sfem_bicgstab(sfem_pattern_t pat, int n_mats, const double* const* d_values,
     if (preconditioner == 1) {
       if (q == 2) k_inv_diag<2><<<grid_for(pat->n_rows_ent), 256, 0, st>>>(a, pat->ent_lo, minv);
       else k_inv_diag<1><<<grid_for(pat->n_rows_ent), 256, 0, st>>>(a, pat->ent_lo, minv);
+      if (a.n_abc > 0) {
+        if (q == 2) k_diag_abc<2><<<grid_for(a.n_abc), 256, 0, st>>>(a, pat->ent_lo, minv);
+        else k_diag_abc<1><<<grid_for(a.n_abc), 256, 0, st>>>(a, pat->ent_lo, minv);
+      }
+      k_invert_diag<<<grid_for(n), 256, 0, st>>>(minv, n);
       mi = minv;
     }
     cplx_t bb, rr;

@@ -11,6 +11,7 @@ LIB_PATH = os.environ.get('SUCEM_B200_LIB') or os.path.join(os.path.dirname(_HER
 
 FORM_MASS, FORM_STIFFNESS, FORM_ABC = 0, 1, 2
 KERNEL_AUTO, KERNEL_GENERIC, KERNEL_CANONICAL, KERNEL_ROWS = 0, 1, 2, 3
+MATS_LAST_IS_ABC_COMPACT = 0x100
 
 
 class NativeError(RuntimeError):
@@ -62,6 +63,9 @@ def _load():
         'sfem_space_count_nnz': (i32, [vp, vp, P(i64)]),
         'sfem_space_assemble_to_host': (i32, [vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, vp]),
         'sfem_measure_fp64_peak': (i32, [P(dbl), vp]),
+        'sfem_abc_info': (i32, [vp, vp, P(i64), P(i64)]),
+        'sfem_abc_export': (i32, [vp, vp, vp, vp, vp]),
+        'sfem_assemble_abc': (i32, [vp, vp, vp, vp, vp]),
         'sfem_host_alloc': (i32, [C.c_size_t, P(vp)]),
         'sfem_host_free': (i32, [vp]),
     }

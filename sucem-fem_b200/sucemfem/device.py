@@ -221,9 +221,39 @@ class DevicePattern(object):
                                            kernel, _stream_ptr()))
         return S, T
 
-    def matvec(self, values, x, coefs=None, out=None):
+    # ---- compact ABC matrix S_0: only the rows of boundary entities are stored (sfem_abc_*) ----
+    def abc_info(self):
+        """(dof rows, non-zeros) of the compact S_0 storage."""
+        nr, nz = C.c_int64(), C.c_int64()
+        with torch.cuda.device(self.space.mesh.device):
+            N.check(N.lib.sfem_abc_info(self.handle, _stream_ptr(), C.byref(nr), C.byref(nz)))
+        return nr.value, nz.value
+
+    def new_abc_values(self):
+        return torch.empty(self.abc_info()[1], dtype=torch.float64, device=self.space.mesh.device)
+
+    def assemble_abc(self, facet_mask=None, pec_flags=None, out=None):
+        """S_0 in compact boundary-row storage: equal, bit for bit, to the boundary rows of assemble(FORM_ABC)."""
+        out = self.new_abc_values() if out is None else out
+        with torch.cuda.device(self.space.mesh.device):
+            N.check(N.lib.sfem_assemble_abc(self.handle, _ptr(facet_mask), _ptr(pec_flags), _ptr(out), _stream_ptr()))
+        return out
+
+    def abc_csr(self, with_cols=True):
+        """(rows int64 [n] global dof numbers, rowptr int64 [n+1], cols int32 [nnz] or None) of the compact storage."""
+        dev = self.space.mesh.device
+        nr, nz = self.abc_info()
+        rows = torch.empty(nr, dtype=torch.int64, device=dev)
+        rowptr = torch.empty(nr + 1, dtype=torch.int64, device=dev)
+        cols = torch.empty(nz, dtype=torch.int32, device=dev) if with_cols else None
+        with torch.cuda.device(dev):
+            N.check(N.lib.sfem_abc_export(self.handle, _ptr(rows), _ptr(rowptr), _ptr(cols), _stream_ptr()))
+        return rows, rowptr, cols
+
+    def matvec(self, values, x, coefs=None, out=None, last_is_abc_compact=False):
         """y = sum_m coefs[m] * (A_m x) for value arrays that share this pattern (sfem_matvec).  x: device tensor
-        [ndof], float64 or complex128; coefs: python complex / float per matrix (default 1)."""
+        [ndof], float64 or complex128; coefs: python complex / float per matrix (default 1).  last_is_abc_compact: the
+        last array is a compact S_0 (assemble_abc)."""
         values = list(values)
         cplx = x.dtype == torch.complex128
         assert x.dtype in (torch.float64, torch.complex128) and x.is_contiguous()
@@ -237,10 +267,12 @@ class DevicePattern(object):
                 flat += [complex(c).real, complex(c).imag]
             co = (C.c_double * len(flat))(*flat)
         with torch.cuda.device(self.space.mesh.device):
-            N.check(N.lib.sfem_matvec(self.handle, len(values), vp, co, int(cplx), _ptr(x), _ptr(out), _stream_ptr()))
+            nm = len(values) | (N.MATS_LAST_IS_ABC_COMPACT if last_is_abc_compact else 0)
+            N.check(N.lib.sfem_matvec(self.handle, nm, vp, co, int(cplx), _ptr(x), _ptr(out), _stream_ptr()))
         return out
 
-    def bicgstab(self, values, coefs, b, x0=None, preconditioner='diagonal', rtol=1e-5, maxiter=None):
+    def bicgstab(self, values, coefs, b, x0=None, preconditioner='diagonal', rtol=1e-5, maxiter=None,
+                 last_is_abc_compact=False):
         """Solve (sum_m coefs[m] A_m) x = b with BiCGStab on the device (sfem_bicgstab).  Returns (x, info, iterations,
         relres) with scipy's info convention (0 converged, > 0 = maxiter reached, < 0 breakdown)."""
         values = list(values)
@@ -256,7 +288,8 @@ class DevicePattern(object):
         maxiter = min(10 * self.space.ndof if maxiter is None else int(maxiter), 2 ** 31 - 1)   # scipy's default; c_int
         it, rr = C.c_int(0), C.c_double(0.0)
         with torch.cuda.device(dev):
-            rc = N.lib.sfem_bicgstab(self.handle, len(values), vp, co, _ptr(b), _ptr(x), pre, float(rtol), maxiter,
+            nm = len(values) | (N.MATS_LAST_IS_ABC_COMPACT if last_is_abc_compact else 0)
+            rc = N.lib.sfem_bicgstab(self.handle, nm, vp, co, _ptr(b), _ptr(x), pre, float(rtol), maxiter,
                                      C.byref(it), C.byref(rr), _stream_ptr())
         if rc == 6:
             return x, it.value, it.value, rr.value

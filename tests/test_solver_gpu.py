@@ -48,6 +48,72 @@ def test_matvec_matches_scipy(mesh, order):
     assert np.abs(yb - ref[blk.row_begin:blk.row_begin + blk.n_rows]).max() <= 1e-13 * np.abs(ref).max()
 
 
+@pytest.mark.parametrize('mesh,order', [('cube', 2), ('cube', 1), ('square', 2), ('square', 1)])
+def test_compact_abc_matrix(mesh, order):
+    """S_0 in compact boundary-row storage (sfem_assemble_abc): the stored rows are exactly the non-zero rows of the
+    full-pattern S_0 (bit for bit, Dirichlet unit rows included), its CSR export rebuilds the same matrix, and the
+    matvec / BiCGStab that take it as the last term agree with the full-pattern ones."""
+    import scipy.sparse as sps
+    import torch
+    from sucemfem import device as dev, _native as N
+    co, ce = meshes.unit_cube(3, 2, 4) if mesh == 'cube' else meshes.unit_square(5, 4)
+    rng = np.random.default_rng(5)
+    co = co + 0.03 * rng.standard_normal(co.shape)
+    sp = dev.DeviceSpace(dev.DeviceMesh(co, ce), order)
+    b = sp.partition(2)
+    for lo, hi in [(0, -1), (b[1], b[2])]:
+        pat = dev.DevicePattern(sp, lo, hi)
+        rowptr, cols = pat.csr()
+        full = pat.assemble(N.FORM_ABC)
+        comp = pat.assemble_abc()
+        rows, crp, ccols = pat.abc_csr()
+        nr, nz = pat.abc_info()
+        assert (len(rows), len(comp), int(crp[-1])) == (nr, nz, nz)
+        # the listed rows, concatenated, are the compact values and columns; every other row of the full form is zero
+        rl = rows - pat.row_begin
+        ln = rowptr[rl + 1] - rowptr[rl]
+        idx = torch.repeat_interleave(rowptr[rl], ln) + (torch.arange(int(ln.sum()), device='cuda')
+                                                        - torch.repeat_interleave(torch.cumsum(ln, 0) - ln, ln))
+        assert torch.equal(full[idx], comp) and torch.equal(cols[idx], ccols)
+        assert torch.equal(crp[1:] - crp[:-1], ln)
+        mask = torch.ones_like(full, dtype=torch.bool)
+        mask[idx] = False
+        assert float(full[mask].abs().max()) == 0.0 if mask.any() else True
+    # consumers (pattern of all rows)
+    pat = sp.pattern()
+    S, M = pat.assemble(N.FORM_STIFFNESS), pat.assemble(N.FORM_MASS)
+    full, comp = pat.assemble(N.FORM_ABC), pat.assemble_abc()
+    coefs = [1.0, -2.5, 0.7j]
+    x = torch.from_numpy(rng.standard_normal(sp.ndof) + 1j * rng.standard_normal(sp.ndof)).cuda()
+    y_full = pat.matvec([S, M, full], x, coefs)
+    y_comp = pat.matvec([S, M, comp], x, coefs, last_is_abc_compact=True)
+    assert float((y_full - y_comp).abs().max()) <= 1e-13 * float(y_full.abs().max())
+    y_only = pat.matvec([comp], x, [0.7j], last_is_abc_compact=True)
+    y_ref = pat.matvec([full], x, [0.7j])
+    assert float((y_only - y_ref).abs().max()) <= 1e-13 * float(y_ref.abs().max())
+    xr = torch.from_numpy(rng.standard_normal(sp.ndof)).cuda()
+    assert float((pat.matvec([M, comp], xr, [1.0, 2.0], last_is_abc_compact=True)
+                  - pat.matvec([M, full], xr, [1.0, 2.0])).abs().max()) <= 1e-12
+    k0 = 1.3
+    cs = [1.0, -k0 ** 2, 1j * k0]
+    rhs = torch.from_numpy(rng.standard_normal(sp.ndof) + 0j).cuda()
+    xa, ia, _, _ = pat.bicgstab([S, M, full], cs, rhs, rtol=1e-10)
+    xb, ib, _, _ = pat.bicgstab([S, M, comp], cs, rhs, rtol=1e-10, last_is_abc_compact=True)
+    assert ia == 0 and ib == 0
+    assert float((xa - xb).abs().max()) <= 1e-7 * float(xa.abs().max())
+    # Dirichlet rows inside the stored set become unit rows, as in the full form
+    markers = torch.zeros(sp.n_facets, dtype=torch.int32, device='cuda')
+    sp.mark_exterior_facets(markers, 999)
+    flags = sp.pec_row_flags(markers, 999)
+    rows, crp, _ = pat.abc_csr(with_cols=False)
+    fullp, compp = pat.assemble(N.FORM_ABC, pec_flags=flags), pat.assemble_abc(pec_flags=flags)
+    rowptr, _ = pat.csr()
+    ln = rowptr[rows + 1] - rowptr[rows]
+    idx = torch.repeat_interleave(rowptr[rows], ln) + (torch.arange(int(ln.sum()), device='cuda')
+                                                      - torch.repeat_interleave(torch.cumsum(ln, 0) - ln, ln))
+    assert torch.equal(fullp[idx], compp)
+
+
 def _problem(device_resident):
     from sucemfem import dolfin_compat as dolfin
     from sucemfem.BoundaryConditions import ABCBoundaryCondition, BoundaryConditions
