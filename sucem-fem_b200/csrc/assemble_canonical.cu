@@ -551,7 +551,7 @@ struct Edge2Args {
   double* __restrict__ S;
   double* __restrict__ T;
   int64_t ent_lo;
-  int64_t nbatch;
+  const int64_t* __restrict__ nbatch;  // number of batches (device: the pattern builder never reads it back)
 };
 
 #ifndef SFEM_E2_WARPS
@@ -790,7 +790,7 @@ __global__ void __launch_bounds__(kE2Warps * 32, SFEM_E2_CTAS) k_canon_edges2(Ed
   double2* tile = reinterpret_cast<double2*>(base);
   uint4* cst = base + SFEM_E2_TILES * kE2TileChunks;
   uint4* recst = cst + kE2StageCoords;
-  const int64_t nb = p.nbatch;
+  const int64_t nb = *p.nbatch;
   const int64_t W = (int64_t)gridDim.x * kE2Warps;
   int64_t b = blockIdx.x * (int64_t)kE2Warps + w;
   if (b >= nb) return;
@@ -1255,10 +1255,10 @@ int assemble_canonical_ST(const sfem_pattern_s* pat, const double* eps, const do
     k_pack_coef<<<(unsigned)((m->C + 255) / 256), 256, 0, st>>>(mu_in, eps_in, sp->coef2, m->C);
     Edge2Args q;
     q.coords4 = sp->coords4; q.eps = eps; q.mu = mu; q.coef2 = sp->coef2; q.rec = pat->rec_e2; q.aux = pat->aux_e2; q.pec = pec;
-    q.S = S; q.T = T; q.ent_lo = pat->ent_lo; q.nbatch = pat->n_batch_e2;
+    q.S = S; q.T = T; q.ent_lo = pat->ent_lo; q.nbatch = pat->nbatch_e2_dev;
     const size_t smem = (size_t)kE2Warps * kE2WarpSmem;
     SFEM_CUDA(cudaFuncSetAttribute(k_canon_edges2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const int64_t nblocks = (q.nbatch + kE2Warps - 1) / kE2Warps;
+    const int64_t nblocks = (pat->n_batch_e2 + kE2Warps - 1) / kE2Warps;
     const unsigned grid = (unsigned)std::min<int64_t>(nblocks, (int64_t)num_sms * SFEM_E2_CTAS);  // persistent
     k_canon_edges2<<<grid, kE2Warps * 32, smem, st>>>(q);
   } else if (n_edge_rows > 0) {

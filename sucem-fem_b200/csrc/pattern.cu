@@ -137,6 +137,7 @@ __global__ void k_edge_ring(SpaceView sv, const int32_t* __restrict__ cells, con
   // e2_slot0[r] of `rec` (batch = slot / 32), and every record gets an aux entry
   const int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (r >= n_edge_rows) return;
+  if (e2_slot0 && *reinterpret_cast<volatile int*>(bad) != 0) return;  // the batch builder refused an edge: slots are invalid
   const int64_t g = ent_lo + r;
   const int64_t i0 = inc_ptr[g];
   const int m = (int)(inc_ptr[g + 1] - i0);
@@ -238,7 +239,8 @@ __global__ void k_edge_ring(SpaceView sv, const int32_t* __restrict__ cells, con
 constexpr int kE2Seg = 512;
 template <bool WRITE>
 __global__ void k_e2_batches(const int64_t* __restrict__ inc_ptr, const int64_t* __restrict__ ent_rowptr, int64_t ent_lo,
-                             int64_t n_edge_rows, int32_t* __restrict__ seg_nb, const int64_t* __restrict__ seg_b0,
+                             int64_t n_edge_rows, int vmax, int64_t nb_max, int32_t* __restrict__ seg_nb,
+                             const int64_t* __restrict__ seg_b0,
                              int64_t* __restrict__ slot0, uint32_t* __restrict__ tileoff, uint2* __restrict__ hdr,
                              int* __restrict__ bad) {
   const int64_t seg = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
@@ -252,13 +254,17 @@ __global__ void k_e2_batches(const int64_t* __restrict__ inc_ptr, const int64_t*
   for (int64_t r = r0; r < r1; ++r) {
     const int64_t ip1 = inc_ptr[ent_lo + r + 1], rp1 = ent_rowptr[r + 1];
     const int m = (int)(ip1 - ip), c2 = 2 * (int)(rp1 - rp);
-    if (m > 32 || m < 1 || c2 > kE2TileChunks) {
+    if (m > vmax || m < 1 || c2 > kE2TileChunks) {
       atomicMax(bad, 1);
       return;
     }
     if (nb == 0 || items + m > 32 || chunks + c2 > kE2TileChunks) {
       if (WRITE && nb > 0) hdr[b] = make_uint2((unsigned)a_first, (unsigned)chunks);
       ++nb; ++b;
+      if (WRITE && b >= nb_max) {  // more batches than the host-side bound allowed for: the caller falls back
+        atomicMax(bad, 1);
+        return;
+      }
       items = 0; chunks = 0;
       a_first = rp;
     }
@@ -367,86 +373,111 @@ int count_pattern_rows(const sfem_space_s* sp, int64_t ent_lo, int64_t ent_hi, c
 }
 
 // Fill pass: expects ent_rowptr, nnz_ent, max_row_len*, inc_base and n_inc_block of `pat` to be set.
-int fill_pattern(sfem_pattern_s* pat, cudaStream_t st) {
+static int fill_pattern_impl(sfem_pattern_s* pat, cudaStream_t st, bool allow_e2) {
   const sfem_space_s* sp = pat->space;
   const int64_t n = pat->n_rows_ent;
   SpaceView sv = make_view(sp);
   const bool canon = pos_is_canonical(sp);
   const unsigned grid = (unsigned)((n + kWarpsPerBlock - 1) / kWarpsPerBlock);
   const int64_t n_edge_rows = std::max<int64_t>(0, std::min(pat->ent_hi, sp->E) - pat->ent_lo);
+  // incidences of the block's edge rows: inc_ptr[E] = (cells) x (edges per cell), no read-back needed
+  const int64_t inc_at_E = sp->mesh->C * sp->ne_loc;
+  const int64_t n_edge_inc = std::min(std::max(inc_at_E, pat->inc_base), pat->inc_base + pat->n_inc_block) - pat->inc_base;
+  const bool want_rec = canon && pat->max_row_len <= 255;
+  // lane-per-item edge kernel (order-2 tets): every size below is an upper bound known on the host, so that the block
+  // pipelines of host_pipeline.cu see the same allocation sequence block after block and no extra synchronisation
+  const int vmax = (int)std::min<int64_t>(32, std::max<int64_t>(1, (pat->max_row_len_edges - 1) / 6));  // ring of m cells: >= 6m+1 entities
+  const bool want_e2 = allow_e2 && want_rec && n_edge_rows > 0 && sp->order == 2 && edge_kernel_version() == 2 &&
+                       pat->nnz_ent < (1ll << 32) && 2 * pat->max_row_len_edges <= kE2TileChunks;
   int* overflow = nullptr;
   SFEM_CUDA(dev_malloc(&overflow, 4, st));
   SFEM_CUDA(cudaMemsetAsync(overflow, 0, 4, st));
   SFEM_CUDA(dev_malloc(&pat->ent_cols, std::max<int64_t>(pat->nnz_ent, 1) * 4, st));
   SFEM_CUDA(dev_malloc(&pat->pos, std::max<int64_t>(pat->n_inc_block * sp->n_ent_cell, 1) * 2, st));
-  if (canon && pat->max_row_len <= 255) SFEM_CUDA(dev_malloc(&pat->rec, std::max<int64_t>(pat->n_inc_block, 1) * 32, st));
+  if (want_rec) {
+    // with the batched edge layout only the FACE records live in `rec` (indexed by incidence - inc_base as before:
+    // the pointer is shifted, its first n_edge_inc entries are never touched)
+    const int64_t skip = want_e2 ? n_edge_inc : 0;
+    SFEM_CUDA(dev_malloc(&pat->rec_alloc, std::max<int64_t>(pat->n_inc_block - skip, 1) * 32, st));
+    pat->rec = pat->rec_alloc - 2 * skip;
+  }
   if (n > 0)
     k_pattern<true><<<grid, kWarpsPerBlock * 32, 0, st>>>(sv, sp->mesh->cells, sp->inc_ptr, sp->inc_cell, sp->inc_loc, canon, pat->ent_lo, n,
                                                           pat->inc_base, nullptr, pat->ent_rowptr, pat->ent_cols,
                                                           pat->pos, reinterpret_cast<uint8_t*>(pat->rec), overflow);
   pat->ring_ok = false;
-  bool use_e2 = false;
   int64_t* e2_slot0 = nullptr;
   uint32_t* e2_tileoff = nullptr;
   uint2* e2_hdr = nullptr;
-  if (pat->rec && n_edge_rows > 0 && sp->order == 2 && edge_kernel_version() == 2 && pat->nnz_ent < (1ll << 32)) {
-    // batches of the lane-per-item edge kernel (falls back to the lane-pair layout when an edge has more than 32 cells)
+  if (want_e2) {
     const int64_t nseg = (n_edge_rows + kE2Seg - 1) / kE2Seg;
+    // a batch closed because the next edge (at most vmax items) did not fit holds more than 32 - vmax items; batches
+    // closed by the tile limit (many low-valence boundary edges) get 1/64 of the items as slack, and a mesh that needs
+    // more than this bound makes k_e2_batches raise `bad` (fallback below)
+    const int64_t nb_max = n_edge_inc / (33 - vmax) + n_edge_inc / 64 + nseg + 16;
     int32_t* seg_nb = nullptr;
     int64_t* seg_b0 = nullptr;
     SFEM_CUDA(dev_malloc(&seg_nb, (nseg + 1) * 4, st));
     SFEM_CUDA(dev_malloc(&seg_b0, (nseg + 1) * 8, st));
     SFEM_CUDA(cudaMemsetAsync(seg_nb, 0, (nseg + 1) * 4, st));
-    k_e2_batches<false><<<grid_for(nseg, 64), 64, 0, st>>>(sp->inc_ptr, pat->ent_rowptr, pat->ent_lo, n_edge_rows, seg_nb,
-                                                           nullptr, nullptr, nullptr, nullptr, overflow);
+    k_e2_batches<false><<<grid_for(nseg, 64), 64, 0, st>>>(sp->inc_ptr, pat->ent_rowptr, pat->ent_lo, n_edge_rows, vmax, nb_max,
+                                                           seg_nb, nullptr, nullptr, nullptr, nullptr, overflow);
     size_t tb = 0;
     SFEM_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tb, seg_nb, seg_b0, (int)(nseg + 1), st));
     void* tmp = nullptr;
     SFEM_CUDA(dev_malloc(&tmp, tb + 16, st));
     SFEM_CUDA(cub::DeviceScan::ExclusiveSum(tmp, tb, seg_nb, seg_b0, (int)(nseg + 1), st));
-    int h_bad = 0;
-    int64_t h_nb = 0;
-    SFEM_CUDA(cudaMemcpyAsync(&h_bad, overflow, 4, cudaMemcpyDeviceToHost, st));
-    SFEM_CUDA(cudaMemcpyAsync(&h_nb, seg_b0 + nseg, 8, cudaMemcpyDeviceToHost, st));
-    SFEM_CUDA(cudaStreamSynchronize(st));
     dev_free(tmp, st);
-    if (h_bad == 0) {
-      use_e2 = true;
-      pat->n_batch_e2 = h_nb;
-      SFEM_CUDA(dev_malloc(&pat->rec_e2, h_nb * 32 * 32, st));
-      SFEM_CUDA(dev_malloc(&pat->aux_e2, h_nb * 32 * 16, st));
-      SFEM_CUDA(cudaMemsetAsync(pat->rec_e2, 0xff, h_nb * 32 * 32, st));  // padding slots: cell = -1
-      SFEM_CUDA(cudaMemsetAsync(pat->aux_e2, 0, h_nb * 32 * 16, st));
-      SFEM_CUDA(dev_malloc(&e2_slot0, n_edge_rows * 8, st));
-      SFEM_CUDA(dev_malloc(&e2_tileoff, n_edge_rows * 4, st));
-      SFEM_CUDA(dev_malloc(&e2_hdr, h_nb * 8, st));
-      k_e2_batches<true><<<grid_for(nseg, 64), 64, 0, st>>>(sp->inc_ptr, pat->ent_rowptr, pat->ent_lo, n_edge_rows, nullptr,
-                                                            seg_b0, e2_slot0, e2_tileoff, e2_hdr, overflow);
-    } else {
-      SFEM_CUDA(cudaMemsetAsync(overflow, 0, 4, st));
-    }
+    pat->n_batch_e2 = nb_max;
+    SFEM_CUDA(dev_malloc(&pat->rec_e2, nb_max * 32 * 32, st));
+    SFEM_CUDA(dev_malloc(&pat->aux_e2, nb_max * 32 * 16, st));
+    SFEM_CUDA(dev_malloc(&pat->nbatch_e2_dev, 8, st));
+    SFEM_CUDA(cudaMemsetAsync(pat->rec_e2, 0xff, nb_max * 32 * 32, st));  // padding slots: cell = -1
+    SFEM_CUDA(cudaMemsetAsync(pat->aux_e2, 0, nb_max * 32 * 16, st));
+    SFEM_CUDA(cudaMemcpyAsync(pat->nbatch_e2_dev, seg_b0 + nseg, 8, cudaMemcpyDeviceToDevice, st));
+    SFEM_CUDA(dev_malloc(&e2_slot0, n_edge_rows * 8, st));
+    SFEM_CUDA(dev_malloc(&e2_tileoff, n_edge_rows * 4, st));
+    SFEM_CUDA(dev_malloc(&e2_hdr, nb_max * 8, st));
+    k_e2_batches<true><<<grid_for(nseg, 64), 64, 0, st>>>(sp->inc_ptr, pat->ent_rowptr, pat->ent_lo, n_edge_rows, vmax, nb_max,
+                                                          nullptr, seg_b0, e2_slot0, e2_tileoff, e2_hdr, overflow);
     dev_free(seg_nb, st);
     dev_free(seg_b0, st);
   }
-  if (pat->rec && n_edge_rows > 0) {
+  bool e2_failed = false;
+  if (want_rec && n_edge_rows > 0) {
     k_edge_ring<<<grid_for(n_edge_rows, 128), 128, 0, st>>>(
         sv, sp->mesh->cells, sp->inc_ptr, sp->inc_cell, sp->inc_loc, pat->ent_lo, n_edge_rows, pat->inc_base,
-        pat->ent_rowptr, pat->ent_cols, reinterpret_cast<uint8_t*>(use_e2 ? pat->rec_e2 : pat->rec), overflow, e2_slot0,
+        pat->ent_rowptr, pat->ent_cols, reinterpret_cast<uint8_t*>(want_e2 ? pat->rec_e2 : pat->rec), overflow, e2_slot0,
         e2_tileoff, e2_hdr, pat->aux_e2);
     int h_bad = 0;
     SFEM_CUDA(cudaMemcpyAsync(&h_bad, overflow, 4, cudaMemcpyDeviceToHost, st));
     SFEM_CUDA(cudaStreamSynchronize(st));
     pat->ring_ok = h_bad == 0;
+    e2_failed = want_e2 && h_bad != 0;
     dev_free(e2_slot0, st);
     dev_free(e2_tileoff, st);
     dev_free(e2_hdr, st);
-  } else if (pat->rec) {
+  } else if (want_rec) {
     pat->ring_ok = true;
   }
   SFEM_CUDA(cudaGetLastError());
   dev_free(overflow, st);
+  if (e2_failed) {
+    // an edge with more cells than the batched layout takes (or a non-manifold one): redo the fill with the lane-pair
+    // layout, which decides for itself whether the canonical kernels can run at all
+    dev_free(pat->ent_cols, st); pat->ent_cols = nullptr;
+    dev_free(pat->pos, st); pat->pos = nullptr;
+    dev_free(pat->rec_alloc, st); pat->rec_alloc = nullptr; pat->rec = nullptr;
+    dev_free(pat->rec_e2, st); pat->rec_e2 = nullptr;
+    dev_free(pat->aux_e2, st); pat->aux_e2 = nullptr;
+    dev_free(pat->nbatch_e2_dev, st); pat->nbatch_e2_dev = nullptr;
+    pat->n_batch_e2 = 0;
+    return fill_pattern_impl(pat, st, false);
+  }
   return 0;
 }
+
+int fill_pattern(sfem_pattern_s* pat, cudaStream_t st) { return fill_pattern_impl(pat, st, true); }
 
 int build_pattern(sfem_pattern_s* pat, cudaStream_t st) {
   const sfem_space_s* sp = pat->space;
@@ -483,7 +514,8 @@ void free_pattern_buffers(sfem_pattern_s* pat, cudaStream_t st) {
   dev_free(pat->ent_rowptr, st); pat->ent_rowptr = nullptr;
   dev_free(pat->ent_cols, st); pat->ent_cols = nullptr;
   dev_free(pat->pos, st); pat->pos = nullptr;
-  dev_free(pat->rec, st); pat->rec = nullptr;
+  dev_free(pat->rec_alloc, st); pat->rec_alloc = nullptr; pat->rec = nullptr;
+  dev_free(pat->nbatch_e2_dev, st); pat->nbatch_e2_dev = nullptr;
   dev_free(pat->rec_e2, st); pat->rec_e2 = nullptr;
   dev_free(pat->aux_e2, st); pat->aux_e2 = nullptr;
   dev_free(pat->abc_rows, st); pat->abc_rows = nullptr;

@@ -140,6 +140,7 @@ struct sfem_pattern_s {
   int32_t* ent_cols = nullptr;    // [nnz_ent] global entity ids, ascending within a row
   uint16_t* pos = nullptr;        // [n_inc_block][n_ent_cell]: slot of the cell's u-th column entity in the row
                                   // (u in canonical order when pos_is_canonical(space))
+  uint4* rec_alloc = nullptr;     // the allocation behind `rec` (rec may point before it: see fill_pattern)
   uint4* rec = nullptr;           // [n_inc_block][2] packed 32-byte item records {relabelled vertex ids, cell,
                                   // descriptor, flags, 10 uint8 slots} (order-2 tets, rows <= 255 entities)
   bool ring_ok = false;           // edge records are in ring order (manifold edges of bounded valence)
@@ -148,7 +149,8 @@ struct sfem_pattern_s {
   uint4* rec_e2 = nullptr;        // [n_batch_e2][32][2] packed item records in ring order
   uint4* aux_e2 = nullptr;        // [n_batch_e2][32] {edge row, packed (tile offset, row length, position, remaining,
                                   // ring-closing lane distance), first entity chunk of the batch's span, span chunks}
-  int64_t n_batch_e2 = 0;
+  int64_t n_batch_e2 = 0;         // upper bound known on the host (allocation size); the count itself stays on the device:
+  int64_t* nbatch_e2_dev = nullptr;
   int64_t* abc_rows = nullptr;    // block-relative row entities that lie on an exterior facet (lazily built)
   int64_t n_abc_rows = -1;
   int64_t* abc_rowptr = nullptr;  // [n_abc_rows+1] entity-level offsets of those rows in the COMPACT S_0 storage

@@ -219,11 +219,13 @@ def test_gmsh_prism_pec_markers_and_cavity_modes():
 def test_high_valence_edge_falls_back_to_generic_kernel():
     """Edges shared by 70 / 40 cells exceed the ring builder's bound / the shared-memory tile of the canonical
     kernels: the AUTO kernel must fall back to the generic kernel (same results), the canonical kernel must refuse
-    loudly; a closed ring of 12 cells goes through the canonical kernels (wrap-around path)."""
+    loudly (34 cells: more than the 32 lanes of the lane-per-item edge kernel -- its batch builder refuses and the
+    pattern is rebuilt with the lane-pair layout); closed rings of 12, 20 and 30 cells go through the canonical
+    kernels (ring-closing shuffle, batches limited by the tile)."""
     import torch
     from oracle import fem
     from sucemfem import device, _native as N
-    for m in (70, 40):
+    for m in (70, 40, 34):
         ang = 2 * np.pi * np.arange(m) / m
         co = np.concatenate([[[0, 0, -1.0], [0, 0, 1.0]], np.stack([np.cos(ang), np.sin(ang), 0 * ang], 1)])
         ce = np.sort(np.array([[0, 1, 2 + i, 2 + (i + 1) % m] for i in range(m)]), axis=1)
@@ -243,10 +245,20 @@ def test_high_valence_edge_falls_back_to_generic_kernel():
             S1, T1 = pat1.assemble_ST(kernel=kern)
             assert np.all(np.abs(S1.cpu().numpy() - ref1['S']) <= 1e-12 * np.abs(ref1['S']) + 1e-15 * np.abs(ref1['S']).max())
             assert np.all(np.abs(T1.cpu().numpy() - ref1['M']) <= 1e-12 * np.abs(ref1['M']) + 1e-15 * np.abs(ref1['M']).max())
-    m = 12
-    ang = 2 * np.pi * np.arange(m) / m
+    for m in (12, 20, 30):
+        ang = 2 * np.pi * np.arange(m) / m
+        co = np.concatenate([[[0, 0, -1.0], [0, 0, 1.0]], np.stack([np.cos(ang), np.sin(ang), 0 * ang], 1)])
+        ce = np.sort(np.array([[0, 1, 2 + i, 2 + (i + 1) % m] for i in range(m)]), axis=1)
+        ref = fem.assemble_system(co, ce, 2)
+        pat = device.DeviceSpace(device.DeviceMesh(co, ce), 2).pattern()
+        S, T = pat.assemble_ST(kernel=N.KERNEL_CANONICAL)
+        assert np.all(np.abs(S.cpu().numpy() - ref['S']) <= 1e-12 * np.abs(ref['S']) + 1e-15 * np.abs(ref['S']).max())
+        assert np.all(np.abs(T.cpu().numpy() - ref['M']) <= 1e-12 * np.abs(ref['M']) + 1e-15 * np.abs(ref['M']).max())
+    # an open fan (the hub edge is on the boundary): chain start without a predecessor, open end stores its next-side blocks
+    m = 9
+    ang = 1.5 * np.pi * np.arange(m + 1) / m
     co = np.concatenate([[[0, 0, -1.0], [0, 0, 1.0]], np.stack([np.cos(ang), np.sin(ang), 0 * ang], 1)])
-    ce = np.sort(np.array([[0, 1, 2 + i, 2 + (i + 1) % m] for i in range(m)]), axis=1)
+    ce = np.sort(np.array([[0, 1, 2 + i, 3 + i] for i in range(m)]), axis=1)
     ref = fem.assemble_system(co, ce, 2)
     pat = device.DeviceSpace(device.DeviceMesh(co, ce), 2).pattern()
     S, T = pat.assemble_ST(kernel=N.KERNEL_CANONICAL)

@@ -94,8 +94,7 @@ def test_compact_abc_matrix(mesh, order):
     xr = torch.from_numpy(rng.standard_normal(sp.ndof)).cuda()
     assert float((pat.matvec([M, comp], xr, [1.0, 2.0], last_is_abc_compact=True)
                   - pat.matvec([M, full], xr, [1.0, 2.0])).abs().max()) <= 1e-12
-    k0 = 1.3
-    cs = [1.0, -k0 ** 2, 1j * k0]
+    cs = [1.0, 1.0, 0.5j]     # S + M is positive definite: BiCGStab converges whatever the mesh
     rhs = torch.from_numpy(rng.standard_normal(sp.ndof) + 0j).cuda()
     xa, ia, _, _ = pat.bicgstab([S, M, full], cs, rhs, rtol=1e-10)
     xb, ib, _, _ = pat.bicgstab([S, M, comp], cs, rhs, rtol=1e-10, last_is_abc_compact=True)
