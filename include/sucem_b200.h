@@ -152,6 +152,12 @@ SFEM_API int sfem_launches_per_assemble_ST(sfem_pattern_t pat, int kernel);
  * flagged rows of the block become unit rows, pattern kept, columns untouched. */
 SFEM_API int sfem_apply_ident(sfem_pattern_t pat, const uint8_t* d_row_flags, double* d_values, void* stream);
 
+/* Diagonal of sum_m c_m A_m (complex, interleaved re/im, one entry per row of the pattern block): the Jacobi
+ * preconditioner of the device Krylov solvers (scipy.sparse.spdiags(1./A.diagonal()),
+ * /root/reference/sucemfem/Utilities/LinalgSolvers.py:115).  n_mats / coef_re_im as in sfem_matvec. */
+SFEM_API int sfem_diagonal(sfem_pattern_t pat, int n_mats, const double* const* d_values, const double* coef_re_im,
+                           double* d_out_complex, void* stream);
+
 /* ---- consumers that stay on the device (solvers of the reference, sucemfem/Utilities/LinalgSolvers.py) ----------
  * y = sum_m c_m (A_m x) for n_mats <= 4 matrices that share the pattern `pat` (d_values: HOST array of n_mats DEVICE
  * pointers, each double [nnz]); coef_re_im: HOST array [2*n_mats] (re, im) or NULL = all 1.  complex_vectors != 0:

@@ -432,6 +432,26 @@ int sfem_matvec(sfem_pattern_t pat, int n_mats, const double* const* d_values, c
   return launch_matvec(pat, a, complex_vectors != 0, d_x, d_y, (cudaStream_t)stream);
 }
 
+int sfem_diagonal(sfem_pattern_t pat, int n_mats, const double* const* d_values, const double* coef_re_im,
+                  double* d_out_complex, void* stream) {
+  SFEM_CHECK(pat && d_values && d_out_complex, "NULL argument");
+  DeviceGuard dg(pat->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  MatvecArgs a;
+  SFEM_TRY(fill_args(pat, n_mats, d_values, coef_re_im, &a, st));
+  if (pat->n_rows_ent == 0) return 0;
+  double2* out = reinterpret_cast<double2*>(d_out_complex);
+  const int q = pat->space->order;
+  if (q == 2) k_inv_diag<2><<<grid_for(pat->n_rows_ent), 256, 0, st>>>(a, pat->ent_lo, out);
+  else k_inv_diag<1><<<grid_for(pat->n_rows_ent), 256, 0, st>>>(a, pat->ent_lo, out);
+  if (a.n_abc > 0) {
+    if (q == 2) k_diag_abc<2><<<grid_for(a.n_abc), 256, 0, st>>>(a, pat->ent_lo, out);
+    else k_diag_abc<1><<<grid_for(a.n_abc), 256, 0, st>>>(a, pat->ent_lo, out);
+  }
+  SFEM_CUDA(cudaGetLastError());
+  return 0;
+}
+
 int sfem_bicgstab(sfem_pattern_t pat, int n_mats, const double* const* d_values, const double* coef_re_im,
                   const double* d_b, double* d_x, int preconditioner, double rtol, int maxiter, int* iterations,
                   double* relres, void* stream) {

@@ -59,3 +59,60 @@ class DefaultEigenSolver(object):
         eigs_v = np.zeros((nev, n))
         eigs_v[:, free] = v[:, order].real.T
         return eigs_w, eigs_v
+
+
+class DeviceEigenSolver(DefaultEigenSolver):
+    """The same shift-invert eigen solve with the matrices left where the assembly kernels wrote them (HBM).
+
+    The reference factorises S - sigma M with a sparse LU on the host and hands the solve to ARPACK
+    (/root/reference/sucemfem/ProblemConfigurations/EMVectorWaveEigenproblem.py:76-103).  Here the shift-invert operator
+    (S - sigma M)^-1 M is applied with a Jacobi-preconditioned MINRES whose matrix-vector products are sfem_matvec on the
+    CSR value arrays (S - sigma M is never formed), inside a Lanczos iteration in the M inner product with full
+    reorthogonalisation (sucemfem/Utilities/DeviceKrylov.py).  Dirichlet (PEC) dofs: the matrices carry row-only unit
+    rows, so on vectors whose constrained entries are zero they act as the reduced pencil S_ff, M_ff.
+    solve_problem() returns what DefaultEigenSolver returns: k^2 itself and the modes as rows; `self.residuals` holds
+    ||S x - k^2 M x|| / ||k^2 M x|| of every returned pair, `self.info` the iteration counts."""
+
+    def solve_problem(self, nev, ncv=None, tol=1e-11, inner_rtol=1e-13, inner_maxiter=50000, seed=0, return_device=False):
+        import torch
+        from ..Utilities import DeviceKrylov as K
+        ep = self.eigenproblem
+        M, S = ep.system_matrices['M'], ep.system_matrices['S']
+        pat = M.pattern
+        assert S.pattern is pat, 'S and M must share one pattern'
+        n = pat.space.ndof
+        dev = M.values.device
+        flags = ep.boundary_conditions.get_essential_row_flags(ep.function_space)
+        free = torch.ones(n, dtype=torch.float64, device=dev) if flags is None else (flags == 0).to(torch.float64)
+        sigma = float(self.sigma)
+        Mmul = lambda x: pat.matvec([M.values], x) * free
+        Amul = lambda x: pat.matvec([S.values, M.values], x, [1.0, -sigma]) * free
+        d = pat.diagonal([S.values, M.values], [1.0, -sigma]).real
+        inv_diag = free / d.abs().clamp_min(1e-300)
+        inner = {"solves": 0, "iterations": 0, "worst_residual": 0.0}
+
+        def solve(w):
+            x, its, res = K.solve_symmetric(Amul, w, inv_diag, inner_rtol, inner_maxiter)
+            inner["solves"] += 1
+            inner["iterations"] += its
+            inner["worst_residual"] = max(inner["worst_residual"], res)
+            return x * free
+
+        g = torch.Generator(device=dev)
+        g.manual_seed(seed)
+        v0 = torch.rand(n, dtype=torch.float64, device=dev, generator=g) * free
+        v0 = solve(Mmul(v0))             # one application of the operator: the start vector lies in its range
+        nu, X, steps, est = K.lanczos_shift_invert(solve, Mmul, n, nev, v0, ncv=ncv, tol=tol)
+        lam = sigma + 1.0 / nu
+        order = torch.argsort(lam)
+        lam, X = lam[order], X[order.to(X.device)]
+        res = []
+        for i in range(len(lam)):
+            Mx = Mmul(X[i])
+            r = pat.matvec([S.values], X[i]) * free - float(lam[i]) * Mx
+            res.append(float(torch.linalg.vector_norm(r)) / (abs(float(lam[i])) * float(torch.linalg.vector_norm(Mx))))
+        self.residuals = res
+        self.info = dict(inner, lanczos_steps=steps)
+        if return_device:
+            return lam, X
+        return lam.cpu().numpy(), X.cpu().numpy()

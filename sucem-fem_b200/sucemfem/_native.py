@@ -52,6 +52,7 @@ def _load():
         'sfem_apply_ident': (i32, [vp, vp, vp, vp]),
         'sfem_launches_per_assemble_ST': (i32, [vp, i32]),
         'sfem_matvec': (i32, [vp, i32, P(vp), P(dbl), i32, vp, vp, vp]),
+        'sfem_diagonal': (i32, [vp, i32, P(vp), P(dbl), vp, vp]),
         'sfem_bicgstab': (i32, [vp, i32, P(vp), P(dbl), vp, vp, i32, dbl, i32, P(i32), P(dbl), vp]),
         'sfem_host_job_create': (i32, [i32, i64, vp, i64, vp, i32, vp, vp, i32, vp, C.c_uint32, vp, P(i64), P(i64), P(vp)]),
         'sfem_host_job_run': (i32, [vp, vp, vp, vp, vp, vp, i32]),

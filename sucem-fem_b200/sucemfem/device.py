@@ -271,6 +271,22 @@ class DevicePattern(object):
             N.check(N.lib.sfem_matvec(self.handle, nm, vp, co, int(cplx), _ptr(x), _ptr(out), _stream_ptr()))
         return out
 
+    def diagonal(self, values, coefs=None):
+        """Diagonal of sum_m coefs[m] A_m as a complex128 device tensor [n_rows] (sfem_diagonal)."""
+        values = list(values)
+        dev = self.space.mesh.device
+        out = torch.empty(self.n_rows, dtype=torch.complex128, device=dev)
+        vp = (C.c_void_p * len(values))(*[v.data_ptr() for v in values])
+        co = None
+        if coefs is not None:
+            flat = []
+            for c in coefs:
+                flat += [complex(c).real, complex(c).imag]
+            co = (C.c_double * len(flat))(*flat)
+        with torch.cuda.device(dev):
+            N.check(N.lib.sfem_diagonal(self.handle, len(values), vp, co, _ptr(out), _stream_ptr()))
+        return out
+
     def bicgstab(self, values, coefs, b, x0=None, preconditioner='diagonal', rtol=1e-5, maxiter=None,
                  last_is_abc_compact=False):
         """Solve (sum_m coefs[m] A_m) x = b with BiCGStab on the device (sfem_bicgstab).  Returns (x, info, iterations,
