@@ -112,6 +112,23 @@ SFEM_API int sfem_pec_row_flags(sfem_space_t space, const uint32_t* d_markers, u
 SFEM_API int sfem_expand_material(int64_t n_cells, const uint32_t* d_regions, int n_regions, const uint32_t* region_ids,
                          const double* values, double* d_out, uint32_t* bad_region, void* stream);
 
+/* Partitioned mesh (multi-GPU, BASELINE north_star: "the mesh is partitioned ... ghost elements duplicated"): `space`
+ * was created from ONE RANK's cells -- its own contiguous range of the global cell list plus every other cell that
+ * shares a vertex with them (halo), in global cell order, with locally renumbered vertices.  First-appearance numbering
+ * of such a sub-mesh gives the entities that first appear in the rank's OWN cells one contiguous local index range, in
+ * the global order; their global indices are that range shifted (offsets from an all-gather of the per-rank counts).
+ * This call attaches the global numbering: d_edge_gid[E_local] / d_face_gid[F_local] = global edge / face index of
+ * every local entity (owned: the shift; others: looked up in the owners' tables -- sucemfem/partition.py), plus the
+ * first owned local / global index of each class.  From then on patterns of this space report GLOBAL column ids, sorted
+ * by them, and GLOBAL row numbers (sfem_pattern_info, sfem_pattern_export, sfem_abc_export); entity ranges passed to
+ * sfem_pattern_create stay LOCAL (the owned ranges), as do the PEC flag and marker arrays.  Rows of owned entities are
+ * bit-identical to the same rows assembled from the whole mesh.  Tetrahedra only; a row block may not mix edge rows
+ * and face rows.  No counterpart in the reference (serial). */
+SFEM_API int sfem_space_set_global_ids(sfem_space_t space, const int32_t* d_edge_gid, const int32_t* d_face_gid,
+                                       int64_t n_edges_global, int64_t n_faces_global, int64_t own_edge_lo_local,
+                                       int64_t own_edge_lo_global, int64_t own_face_lo_local,
+                                       int64_t own_face_lo_global, void* stream);
+
 /* ---- sparsity pattern: replaces DOLFIN's SparsityPatternBuilder + tensor init inside dolfin.assemble
  * (sucemfem/SystemMatrices.py:54).  Rows are owned by DOF-entity: the pattern covers the rows of the
  * entities [ent_lo, ent_hi) of the combined entity numbering (edges, then faces / cell interiors), i.e.

@@ -171,7 +171,7 @@ __global__ void k_find_bounds_class(const int64_t* __restrict__ inc_ptr, int64_t
 
 // row-only ident on assembled values: one warp per row entity
 __global__ void k_ident(const int64_t* __restrict__ ent_rowptr, const int32_t* __restrict__ ent_cols, int q,
-                        int64_t ent_lo, int64_t n_rows, const uint8_t* __restrict__ flags,
+                        int64_t ent_lo, int64_t gshift, int64_t n_rows, const uint8_t* __restrict__ flags,
                         double* __restrict__ vals) {
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t r = blockIdx.x * (int64_t)(blockDim.x >> 5) + w;
@@ -184,16 +184,21 @@ __global__ void k_ident(const int64_t* __restrict__ ent_rowptr, const int32_t* _
     const int64_t rs = (int64_t)q * q * a + (int64_t)k * q * len;
     for (int idx = lane; idx < q * len; idx += 32) {
       int s = idx / q, kp = idx - s * q;
-      vals[rs + idx] = (ent_cols[a + s] == g && kp == k) ? 1.0 : 0.0;
+      vals[rs + idx] = (ent_cols[a + s] == g + gshift && kp == k) ? 1.0 : 0.0;
     }
   }
 }
 
 }  // namespace
+__global__ void k_offset_i32(const int32_t* __restrict__ in, int32_t* __restrict__ out, int64_t n, int32_t off) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < n) out[i] = in[i] + off;
+}
+
 // dof-level CSR of the compact ABC storage: global dof row numbers, row pointer, (optionally) column ids
 __global__ void k_abc_export(const int64_t* __restrict__ ent_rowptr, const int32_t* __restrict__ ent_cols,
                              const int64_t* __restrict__ list, const int64_t* __restrict__ out_rowptr, int64_t n_list,
-                             int q, int64_t ent_lo, int64_t* __restrict__ rows, int64_t* __restrict__ rowptr,
+                             int q, int64_t ent_lo_global, int64_t* __restrict__ rows, int64_t* __restrict__ rowptr,
                              int32_t* __restrict__ cols) {
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t i = blockIdx.x * (int64_t)(blockDim.x >> 5) + w;
@@ -207,7 +212,7 @@ __global__ void k_abc_export(const int64_t* __restrict__ ent_rowptr, const int32
   for (int k = 0; k < q; ++k) {
     const int64_t rs = (int64_t)q * q * ao + (int64_t)k * q * len;
     if (lane == 0) {
-      rows[q * i + k] = q * (ent_lo + r) + k;
+      rows[q * i + k] = q * (ent_lo_global + r) + k;
       rowptr[q * i + k] = rs;
     }
     if (cols)
@@ -330,6 +335,8 @@ int sfem_space_destroy(sfem_space_t sp) {
   dev_free(sp->coords4, st);
   dev_free(sp->ones, st);
   dev_free(sp->coef2, st);
+  dev_free(sp->gid_e, st);
+  dev_free(sp->gid_f, st);
   dev_free(sp->rowptr_all, st);
   if (sp->drain) {
     cudaStreamSynchronize(sp->drain);
@@ -425,10 +432,37 @@ int sfem_expand_material(int64_t n_cells, const uint32_t* d_regions, int n_regio
   return 0;
 }
 
+int sfem_space_set_global_ids(sfem_space_t sp, const int32_t* d_edge_gid, const int32_t* d_face_gid,
+                              int64_t n_edges_global, int64_t n_faces_global, int64_t own_edge_lo_local,
+                              int64_t own_edge_lo_global, int64_t own_face_lo_local, int64_t own_face_lo_global,
+                              void* stream) {
+  SFEM_CHECK(sp && d_edge_gid, "NULL argument");
+  SFEM_CHECK(sp->mesh->gdim == 3, "partitioned meshes: tetrahedra only");
+  SFEM_CHECK(sp->order == 1 || d_face_gid, "order 2 needs the face map");
+  SFEM_CHECK(!sp->rowptr_all, "set the global ids before any pattern is counted");
+  DeviceGuard dg(sp->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (!sp->gid_e) SFEM_CUDA(dev_malloc(&sp->gid_e, std::max<int64_t>(sp->E, 1) * 4, st));
+  SFEM_CUDA(cudaMemcpyAsync(sp->gid_e, d_edge_gid, sp->E * 4, cudaMemcpyDeviceToDevice, st));
+  if (sp->order == 2) {
+    if (!sp->gid_f) SFEM_CUDA(dev_malloc(&sp->gid_f, std::max<int64_t>(sp->F, 1) * 4, st));
+    k_offset_i32<<<grid_for(sp->F), 256, 0, st>>>(d_face_gid, sp->gid_f, sp->F, (int32_t)n_edges_global);
+  }
+  sp->gshift_e = own_edge_lo_global - own_edge_lo_local;
+  sp->gshift_f = (n_edges_global + own_face_lo_global) - (sp->E + own_face_lo_local);
+  sp->n_ent_global = n_edges_global + (sp->order == 2 ? n_faces_global : 0);
+  sp->ndof_global = sp->order * sp->n_ent_global;
+  SFEM_CHECK(sp->n_ent_global < (int64_t)2147483647, "global entity ids exceed int32");
+  SFEM_CUDA(cudaGetLastError());
+  return 0;
+}
+
 int sfem_pattern_create(sfem_space_t sp, int64_t ent_lo, int64_t ent_hi, void* stream, sfem_pattern_t* out) {
   SFEM_CHECK(sp && out, "NULL argument");
   if (ent_hi < 0) ent_hi = sp->n_ent;
   SFEM_CHECK(0 <= ent_lo && ent_lo <= ent_hi && ent_hi <= sp->n_ent, "entity range out of bounds");
+  SFEM_CHECK(!sp->gid_e || ent_hi <= sp->E || ent_lo >= sp->E,
+             "partitioned mesh: a row block holds edge rows or face rows, not both");
   DeviceGuard dg(sp->mesh->device);
   auto* pat = new sfem_pattern_s();
   pat->space = sp;
@@ -436,6 +470,7 @@ int sfem_pattern_create(sfem_space_t sp, int64_t ent_lo, int64_t ent_hi, void* s
   pat->stream = (cudaStream_t)stream;
   pat->ent_lo = ent_lo;
   pat->ent_hi = ent_hi;
+  if (sp->gid_e) pat->gshift = ent_lo >= sp->E && ent_hi > ent_lo ? sp->gshift_f : sp->gshift_e;
   pat->n_rows_ent = ent_hi - ent_lo;
   int rc = build_pattern(pat, (cudaStream_t)stream);
   if (rc != 0) {
@@ -458,7 +493,7 @@ int sfem_pattern_destroy(sfem_pattern_t pat) {
 int sfem_pattern_info(sfem_pattern_t pat, int64_t* row_begin, int64_t* n_rows, int64_t* nnz) {
   SFEM_CHECK(pat, "NULL pattern");
   const int q = pat->space->order;
-  if (row_begin) *row_begin = q * pat->ent_lo;
+  if (row_begin) *row_begin = q * (pat->ent_lo + pat->gshift);
   if (n_rows) *n_rows = q * pat->n_rows_ent;
   if (nnz) *nnz = (int64_t)q * q * pat->nnz_ent;
   return 0;
@@ -466,7 +501,7 @@ int sfem_pattern_info(sfem_pattern_t pat, int64_t* row_begin, int64_t* n_rows, i
 
 int sfem_pattern_export(sfem_pattern_t pat, int64_t* d_rowptr, int32_t* d_cols, void* stream) {
   SFEM_CHECK(pat && d_rowptr, "NULL argument");
-  SFEM_CHECK(pat->space->ndof < (int64_t)2147483647, "column ids exceed int32");
+  SFEM_CHECK(std::max(pat->space->ndof, pat->space->ndof_global) < (int64_t)2147483647, "column ids exceed int32");
   DeviceGuard dg(pat->space->mesh->device);
   return export_pattern(pat, d_rowptr, d_cols, (cudaStream_t)stream);
 }
@@ -522,7 +557,7 @@ int sfem_apply_ident(sfem_pattern_t pat, const uint8_t* d_row_flags, double* d_v
   DeviceGuard dg(pat->space->mesh->device);
   if (pat->n_rows_ent == 0) return 0;
   k_ident<<<(unsigned)((pat->n_rows_ent + 7) / 8), 256, 0, (cudaStream_t)stream>>>(
-      pat->ent_rowptr, pat->ent_cols, pat->space->order, pat->ent_lo, pat->n_rows_ent, d_row_flags, d_values);
+      pat->ent_rowptr, pat->ent_cols, pat->space->order, pat->ent_lo, pat->gshift, pat->n_rows_ent, d_row_flags, d_values);
   SFEM_CUDA(cudaGetLastError());
   return 0;
 }
@@ -556,7 +591,7 @@ int sfem_abc_export(sfem_pattern_t pat, int64_t* d_rows, int64_t* d_rowptr, int3
   SFEM_TRY(build_abc_rows(pat, st));
   const int64_t n = pat->n_abc_rows;
   k_abc_export<<<(unsigned)((n + 1 + 7) / 8), 256, 0, st>>>(pat->ent_rowptr, pat->ent_cols, pat->abc_rows, pat->abc_rowptr, n,
-                                                          pat->space->order, pat->ent_lo, d_rows, d_rowptr, d_cols);
+                                                          pat->space->order, pat->ent_lo + pat->gshift, d_rows, d_rowptr, d_cols);
   SFEM_CUDA(cudaGetLastError());
   return 0;
 }

@@ -190,6 +190,7 @@ struct PatView {
   const int32_t* ent_cols;
   const uint16_t* pos;
   int64_t ent_lo, n_rows, inc_base;
+  int64_t gshift;  // global id of row entity = ent_lo + r + gshift
   int nec;
   bool canon;  // slot table in canonical column order
   const int64_t* row_list;  // optional: only these block-relative row entities are assembled (ABC: boundary rows)
@@ -228,7 +229,7 @@ k_values_generic(PatView pv, const double* __restrict__ geo, const double* __res
       const int s = idx / Q, kp = idx - s * Q;
       double accA = 0.0, accB = 0.0;
       if (pecrow) {
-        accA = accB = (pv.ent_cols[a + s] == g && kp == k) ? 1.0 : 0.0;
+        accA = accB = (pv.ent_cols[a + s] == g + pv.gshift && kp == k) ? 1.0 : 0.0;
       } else {
         for (int64_t i = i0; i < i1; ++i) {
           const uint16_t* ps = pv.pos + (i - pv.inc_base) * pv.nec;
@@ -525,7 +526,7 @@ __global__ void k_abc_row_flags(const int64_t* __restrict__ inc_ptr, const int32
 }
 
 __global__ void k_ident_rows(const int64_t* __restrict__ ent_rowptr, const int32_t* __restrict__ ent_cols, int q,
-                             int64_t ent_lo, int64_t n_rows, const uint8_t* __restrict__ flags,
+                             int64_t ent_lo, int64_t gshift, int64_t n_rows, const uint8_t* __restrict__ flags,
                              double* __restrict__ vals) {
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t r = blockIdx.x * (int64_t)(blockDim.x >> 5) + w;
@@ -538,7 +539,7 @@ __global__ void k_ident_rows(const int64_t* __restrict__ ent_rowptr, const int32
     const int64_t rs = (int64_t)q * q * a + (int64_t)k * q * len;
     for (int idx = lane; idx < q * len; idx += 32) {
       int s = idx / q, kp = idx - s * q;
-      vals[rs + idx] = (ent_cols[a + s] == g && kp == k) ? 1.0 : 0.0;
+      vals[rs + idx] = (ent_cols[a + s] == g + gshift && kp == k) ? 1.0 : 0.0;
     }
   }
 }
@@ -602,7 +603,7 @@ int launch_generic(const sfem_pattern_s* pat, int form, const double* coef_a, co
   const sfem_space_s* sp = pat->space;
   const sfem_mesh_s* m = sp->mesh;
   PatView pv{sp->inc_ptr, sp->inc_cell, sp->inc_loc, pat->ent_rowptr, pat->ent_cols, pat->pos,
-             pat->ent_lo, pat->n_rows_ent, pat->inc_base, sp->n_ent_cell, pos_is_canonical(sp), nullptr, 0, nullptr};
+             pat->ent_lo, pat->n_rows_ent, pat->inc_base, pat->gshift, sp->n_ent_cell, pos_is_canonical(sp), nullptr, 0, nullptr};
   if (pat->n_rows_ent == 0) return 0;
   unsigned grid = (unsigned)((pat->n_rows_ent + kWarps - 1) / kWarps);
   if (form == SFEM_FORM_ABC) {
@@ -640,7 +641,7 @@ int launch_generic(const sfem_pattern_s* pat, int form, const double* coef_a, co
                                                                      abc_compact ? pec : nullptr, out_a, nullptr);
       if (pec && !abc_compact)
         k_ident_rows<<<(unsigned)((pat->n_rows_ent + 7) / 8), 256, 0, st>>>(pat->ent_rowptr, pat->ent_cols, ORDER,
-                                                                          pat->ent_lo, pat->n_rows_ent, pec, out_a);
+                                                                          pat->ent_lo, pat->gshift, pat->n_rows_ent, pec, out_a);
       break;
     default:  // 3: fused S (out_a) and M (out_b)
       k_values_generic<DIM, ORDER, 3><<<grid, kWarps * 32, 0, st>>>(pv, geo, m->coords, m->cells, cell_facets,
@@ -684,7 +685,7 @@ int assemble_rows_ST(const sfem_pattern_s* pat, const double* eps, const double*
   }
   if (pat->n_rows_ent == 0) return 0;
   PatView pv{sp->inc_ptr, sp->inc_cell, sp->inc_loc, pat->ent_rowptr, pat->ent_cols, pat->pos,
-             pat->ent_lo, pat->n_rows_ent, pat->inc_base, sp->n_ent_cell, pos_is_canonical(sp), nullptr, 0, nullptr};
+             pat->ent_lo, pat->n_rows_ent, pat->inc_base, pat->gshift, sp->n_ent_cell, pos_is_canonical(sp), nullptr, 0, nullptr};
   if (m->gdim == 3) {
     // tile = 32 rows of the longest length, capped so that several CTAs stay resident (longer spans write directly)
     constexpr int kWarpsT1 = kTet1Threads / 32;

@@ -127,6 +127,13 @@ struct sfem_space_s {
   int64_t nnz_ent_all = 0;
   int max_len_edges_all = 0, max_len_other_all = 0;
   cudaStream_t drain = nullptr;       // device->host drain stream of sfem_space_assemble_to_host (lazily created)
+  // Partitioned mesh (sfem_space_set_global_ids): this space was numbered on ONE RANK's cells (own + halo); column
+  // entities are reported through these maps (local edge / face -> global combined entity id), rows of the owned
+  // ranges are shifted by gshift_e / gshift_f (global id - local combined id).  nullptr / 0: the space is the mesh.
+  int32_t* gid_e = nullptr;           // [E]
+  int32_t* gid_f = nullptr;           // [F] (already offset by the global edge count)
+  int64_t gshift_e = 0, gshift_f = 0;
+  int64_t n_ent_global = 0, ndof_global = 0;
 };
 
 struct sfem_pattern_s {
@@ -155,6 +162,7 @@ struct sfem_pattern_s {
   int64_t n_abc_rows = -1;
   int64_t* abc_rowptr = nullptr;  // [n_abc_rows+1] entity-level offsets of those rows in the COMPACT S_0 storage
   int64_t abc_nnz_ent = 0;
+  int64_t gshift = 0;             // global combined entity id of a row entity = ent_lo + r + gshift (partitioned mesh)
   int64_t inc_base = 0;           // = space->inc_ptr[ent_lo]
   int64_t n_inc_block = 0;
   int max_row_len = 0;            // longest entity row of the block
@@ -167,11 +175,20 @@ namespace sfem {
 struct SpaceView {
   const int32_t* cell_edges;
   const int32_t* cell_faces;
+  const int32_t* gid_e;  // partitioned mesh: local -> global combined entity ids (else nullptr)
+  const int32_t* gid_f;
   int ne_loc, n_ent_cell;
   int64_t E;
+  // the id under which dof entity u of cell c appears as a COLUMN (global numbering)
   __device__ __forceinline__ int32_t ent(int64_t c, int u) const {
-    if (u < ne_loc) return cell_edges[c * ne_loc + u];
-    if (cell_faces) return (int32_t)(E + cell_faces[c * 4 + (u - ne_loc)]);
+    if (u < ne_loc) {
+      const int32_t e = cell_edges[c * ne_loc + u];
+      return gid_e ? gid_e[e] : e;
+    }
+    if (cell_faces) {
+      const int32_t f = cell_faces[c * 4 + (u - ne_loc)];
+      return gid_f ? gid_f[f] : (int32_t)(E + f);
+    }
     return (int32_t)(E + c);
   }
 };
@@ -179,6 +196,8 @@ inline SpaceView make_view(const sfem_space_s* s) {
   SpaceView v;
   v.cell_edges = s->cell_edges;
   v.cell_faces = (s->mesh->gdim == 3 && s->order == 2) ? s->cell_faces : nullptr;
+  v.gid_e = s->gid_e;
+  v.gid_f = s->gid_f;
   v.ne_loc = s->ne_loc;
   v.n_ent_cell = s->n_ent_cell;
   v.E = s->E;

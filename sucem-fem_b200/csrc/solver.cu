@@ -442,11 +442,11 @@ int sfem_diagonal(sfem_pattern_t pat, int n_mats, const double* const* d_values,
   if (pat->n_rows_ent == 0) return 0;
   double2* out = reinterpret_cast<double2*>(d_out_complex);
   const int q = pat->space->order;
-  if (q == 2) k_inv_diag<2><<<grid_for(pat->n_rows_ent), 256, 0, st>>>(a, pat->ent_lo, out);
-  else k_inv_diag<1><<<grid_for(pat->n_rows_ent), 256, 0, st>>>(a, pat->ent_lo, out);
+  if (q == 2) k_inv_diag<2><<<grid_for(pat->n_rows_ent), 256, 0, st>>>(a, pat->ent_lo + pat->gshift, out);
+  else k_inv_diag<1><<<grid_for(pat->n_rows_ent), 256, 0, st>>>(a, pat->ent_lo + pat->gshift, out);
   if (a.n_abc > 0) {
-    if (q == 2) k_diag_abc<2><<<grid_for(a.n_abc), 256, 0, st>>>(a, pat->ent_lo, out);
-    else k_diag_abc<1><<<grid_for(a.n_abc), 256, 0, st>>>(a, pat->ent_lo, out);
+    if (q == 2) k_diag_abc<2><<<grid_for(a.n_abc), 256, 0, st>>>(a, pat->ent_lo + pat->gshift, out);
+    else k_diag_abc<1><<<grid_for(a.n_abc), 256, 0, st>>>(a, pat->ent_lo + pat->gshift, out);
   }
   SFEM_CUDA(cudaGetLastError());
   return 0;
@@ -494,11 +494,11 @@ int sfem_bicgstab(sfem_pattern_t pat, int n_mats, const double* const* d_values,
   const double2* mi = nullptr;
   do {
     if (preconditioner == 1) {
-      if (q == 2) k_inv_diag<2><<<grid_for(pat->n_rows_ent), 256, 0, st>>>(a, pat->ent_lo, minv);
-      else k_inv_diag<1><<<grid_for(pat->n_rows_ent), 256, 0, st>>>(a, pat->ent_lo, minv);
+      if (q == 2) k_inv_diag<2><<<grid_for(pat->n_rows_ent), 256, 0, st>>>(a, pat->ent_lo + pat->gshift, minv);
+      else k_inv_diag<1><<<grid_for(pat->n_rows_ent), 256, 0, st>>>(a, pat->ent_lo + pat->gshift, minv);
       if (a.n_abc > 0) {
-        if (q == 2) k_diag_abc<2><<<grid_for(a.n_abc), 256, 0, st>>>(a, pat->ent_lo, minv);
-        else k_diag_abc<1><<<grid_for(a.n_abc), 256, 0, st>>>(a, pat->ent_lo, minv);
+        if (q == 2) k_diag_abc<2><<<grid_for(a.n_abc), 256, 0, st>>>(a, pat->ent_lo + pat->gshift, minv);
+        else k_diag_abc<1><<<grid_for(a.n_abc), 256, 0, st>>>(a, pat->ent_lo + pat->gshift, minv);
       }
       k_invert_diag<<<grid_for(n), 256, 0, st>>>(minv, n);
       mi = minv;

@@ -41,6 +41,7 @@ def _load():
         'sfem_mark_exterior_facets': (i32, [vp, vp, C.c_uint32, vp]),
         'sfem_pec_row_flags': (i32, [vp, vp, C.c_uint32, vp, vp]),
         'sfem_expand_material': (i32, [i64, vp, i32, P(C.c_uint32), P(dbl), vp, P(C.c_uint32), vp]),
+        'sfem_space_set_global_ids': (i32, [vp, vp, vp, i64, i64, i64, i64, i64, i64, vp]),
         'sfem_pattern_create': (i32, [vp, i64, i64, vp, P(vp)]),
         'sfem_pattern_destroy': (i32, [vp]),
         'sfem_pattern_info': (i32, [vp, P(i64), P(i64), P(i64)]),

@@ -1,0 +1,77 @@
+"""Partitioned mesh on the device (sucemfem/partition.py + sfem_space_set_global_ids; SURVEY 8.2 row e): every logical
+rank builds its space from its own cells + halo only, the phases of the global numbering run between them, and the two
+row blocks each rank assembles -- pattern (global column ids), S, T, PEC unit rows, compact S_0 -- concatenate BIT FOR
+BIT to what one space over the whole mesh gives.  (All logical ranks share one GPU here; tests/test_partition.py runs the
+numbering phases through torch.distributed with gloo, and bench.py --gpus N through NCCL.)"""
+import numpy as np
+import pytest
+
+from oracle import meshes
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize('order', [2, 1])
+@pytest.mark.parametrize('world', [2, 3])
+def test_rank_blocks_concatenate_to_the_global_assembly(order, world):
+    import torch
+    from sucemfem import device as dev, partition as P, _native as N
+    co, ce = meshes.unit_cube(6, 5, 7)
+    rng = np.random.default_rng(11)
+    co = co + 0.02 * rng.standard_normal(co.shape)
+    eps, mu = rng.uniform(1, 16, len(ce)), rng.uniform(1, 2, len(ce))
+    # the whole mesh on one space
+    sp = dev.DeviceSpace(dev.DeviceMesh(co, ce), order)
+    markers = torch.zeros(sp.n_facets, dtype=torch.int32, device='cuda')
+    sp.mark_exterior_facets(markers, 999)
+    flags = sp.pec_row_flags(markers, 999)
+    pat = sp.pattern()
+    d_eps, d_mu = torch.from_numpy(eps).cuda(), torch.from_numpy(mu).cuda()
+    S, T = pat.assemble_ST(d_eps, d_mu, flags)
+    rowptr, cols = pat.csr()
+    E = sp.n_edges
+    # logical ranks
+    ranks = [P.RankSpace(co, ce, order, p, world, distributed=False) for p in range(world)]
+    P.number_logical_ranks([r.numbering for r in ranks])
+    blocks = {0: [], 1: []}
+    for r in ranks:
+        r._attach()
+        assert r.ndof_global == sp.ndof
+        lm = torch.zeros(r.space.n_facets, dtype=torch.int32, device='cuda')
+        r.space.mark_exterior_facets(lm, 999)
+        lflags = r.space.pec_row_flags(lm, 999)
+        le = torch.from_numpy(r.local_cell_values(eps)).cuda()
+        lmu = torch.from_numpy(r.local_cell_values(mu)).cuda()
+        for k, bp in enumerate(r.patterns()):
+            s, t = bp.assemble_ST(le, lmu, lflags)
+            rp, cl = bp.csr()
+            blocks[k].append((bp.row_begin, bp.n_rows, rp, cl, s, t))
+    # edge blocks tile the edge rows, face blocks the face rows, in rank order
+    pos = 0
+    for k in ((0, 1) if order == 2 else (0,)):
+        for row_begin, n_rows, rp, cl, s, t in blocks[k]:
+            assert row_begin == pos
+            a, b = int(rowptr[pos]), int(rowptr[pos + n_rows])
+            assert torch.equal(rp + a, rowptr[pos:pos + n_rows + 1])
+            assert torch.equal(cl, cols[a:b])
+            assert torch.equal(s, S[a:b]) and torch.equal(t, T[a:b])
+            pos += n_rows
+        if k == 0:
+            assert pos == order * E
+    assert pos == sp.ndof
+
+
+def test_halo_is_thin_and_generic_kernel_agrees():
+    import torch
+    from sucemfem import device as dev, partition as P, _native as N
+    co, ce = meshes.unit_cube(10)
+    ranks = [P.RankSpace(co, ce, 2, p, 4, distributed=False) for p in range(4)]
+    P.number_logical_ranks([r.numbering for r in ranks])
+    for r in ranks:
+        r._attach()
+        assert len(r.rc.cell_ids) <= 0.5 * len(ce) + 1       # own quarter + at most one cube layer either side
+        for bp in r.patterns():
+            a = bp.assemble_ST(kernel=N.KERNEL_CANONICAL)
+            b = bp.assemble_ST(kernel=N.KERNEL_GENERIC)
+            for x, y in zip(a, b):
+                assert float((x - y).abs().max()) <= 1e-12 * float(y.abs().max())
