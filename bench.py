@@ -66,8 +66,9 @@ def workload_config(n, world, kernel="auto"):
     c = cube_counts(n)
     return {"workload": "UnitCube(%d) N1curl order-2 S+T, PEC on all exterior faces, per-cell eps_r~U[1,16) "
                         "mu_r~U[1,2)" % n, "tets": c["tets"], "ndof": c["ndof"], "nnz_per_matrix": c["nnz"],
-            "partition": "rows by DOF-entity ownership (one edge range + one face range per rank, each "
-                         "balanced by incidence count), %d rank(s), ghost cells duplicated" % world,
+            "partition": "%d rank(s): contiguous cell ranges of equal size + halo cells (duplicated), each rank numbers its "
+                         "own sub-mesh; rows by first-appearance ownership of the DOF entities (one edge range + one face "
+                         "range per rank); no data-path collective" % world,
             "l2": "outputs per step (%.1f GB over all ranks) exceed L2; no flush needed" % (16e-9 * c["nnz"]),
             "kernel": kernel}
 
@@ -240,23 +241,44 @@ def main():
 
     # ---- one-time set-up (not timed as part of a step): mesh, numbering, this rank's row block ----------
     t_setup = time.perf_counter()
-    mesh = device.DeviceMesh.unit(n, n, n)
-    space = device.DeviceSpace(mesh, args.order)
+    g = torch.Generator(device='cuda')
+    g.manual_seed(1234)
+    rs = None
     if world == 1:
+        mesh = device.DeviceMesh.unit(n, n, n)
+        space = device.DeviceSpace(mesh, args.order)
         pats = [device.DevicePattern(space, 0, -1)]
-    else:   # one range of edge rows + one range of face rows per rank: every rank runs the same mix of work
-        eb, ob = space.partition_by_class(world)
-        pats = [device.DevicePattern(space, eb[rank], eb[rank + 1]), device.DevicePattern(space, ob[rank], ob[rank + 1])]
+        C_total, V_total, ndof_total = mesh.num_cells, mesh.num_vertices, space.ndof
+        eps = 1.0 + 15.0 * torch.rand(C_total, dtype=torch.float64, device='cuda', generator=g)
+        mu = 1.0 + torch.rand(C_total, dtype=torch.float64, device='cuda', generator=g)
+        eps_all, mu_all = eps, mu
+        block_local_row0 = [0]
+    else:
+        # partitioned mesh: this rank numbers ONLY its own cells + halo; two counts and the interface tables are exchanged
+        # over NCCL (sucemfem/partition.py).  The synthetic generator writes the whole cell list to the device once; the
+        # rank's selection is one pass over it, then it is dropped.
+        from sucemfem import partition
+        gen = device.DeviceMesh.unit(n, n, n)
+        C_total, V_total = gen.num_cells, gen.num_vertices
+        eps_all = 1.0 + 15.0 * torch.rand(C_total, dtype=torch.float64, device='cuda', generator=g)
+        mu_all = 1.0 + torch.rand(C_total, dtype=torch.float64, device='cuda', generator=g)
+        rs = partition.RankSpace(gen.coords, gen.cells, args.order, rank, world)
+        del gen
+        mesh, space = rs.mesh, rs.space
+        pats = rs.patterns()
+        eps, mu = rs.local_cell_values(eps_all).contiguous(), rs.local_cell_values(mu_all).contiguous()
+        ndof_total = rs.ndof_global
+        rn = rs.numbering
+        block_local_row0 = [args.order * rn.e_lo, args.order * (space.n_edges + rn.f_lo)]
     markers = torch.zeros(space.n_facets, dtype=torch.int32, device='cuda')
     space.mark_exterior_facets(markers, 999)
     flags = space.pec_row_flags(markers, 999)
     torch.cuda.synchronize()
     setup_ms = (time.perf_counter() - t_setup) * 1e3
-    C_total = mesh.num_cells
-    g = torch.Generator(device='cuda')
-    g.manual_seed(1234)
-    eps = 1.0 + 15.0 * torch.rand(C_total, dtype=torch.float64, device='cuda', generator=g)
-    mu = 1.0 + torch.rand(C_total, dtype=torch.float64, device='cuda', generator=g)
+    resident_bytes = torch.cuda.memory_allocated()
+    cached = (C.c_int64(), C.c_int64())
+    N.check(N.lib.sfem_cached_memory_info(C.byref(cached[0]), C.byref(cached[1])))
+    resident_bytes += cached[1].value
     vals = [(pat.new_values(), pat.new_values()) for pat in pats]
     kernel = args.kernel
     n_rows, nnz = sum(pat.n_rows for pat in pats), sum(pat.nnz for pat in pats)
@@ -299,8 +321,8 @@ def main():
 
     # ---- roofline: this rank's step (its launches back to back on the launching stream, CUDA events) ------
     peak, peak_src = peak_hbm()
-    share = n_rows / float(space.ndof)
-    b_alg = algorithmic_bytes(C_total * share, mesh.num_vertices * share, nnz)
+    share = n_rows / float(ndof_total)
+    b_alg = algorithmic_bytes(C_total * share, V_total * share, nnz)
     achieved = b_alg / (ms_local / K * 1e-3) / 1e9
     traffic, traffic_note = None, "no ncu capture of this build and workload is committed"
     try:  # DRAM bytes per step from the committed ncu capture (profiles/), only if it is this workload AND this build
@@ -332,22 +354,25 @@ def main():
     cfg = workload_config(n, world, {0: "auto", 1: "generic", 2: "canonical"}[kernel])
     if args.order == 2 and not args.n:
         cc = cube_counts(n)
-        assert (C_total, space.ndof) == (cc["tets"], cc["ndof"]), 'closed-form workload sizes differ from the device'
+        assert (C_total, ndof_total) == (cc["tets"], cc["ndof"]), 'closed-form workload sizes differ from the device'
         assert world > 1 or nnz == cc["nnz"], 'closed-form nnz differs from the device pattern'
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic", "config": cfg,
             "nnz_per_matrix_this_rank": nnz,
-            "setup_ms": setup_ms, "roofline": roofline, "gpu_launches": None,
+            "setup_ms": setup_ms, "setup_resident_bytes_this_rank": int(resident_bytes),
+            "cells_held_this_rank": int(mesh.num_cells), "roofline": roofline, "gpu_launches": None,
             "per_rank_ms_per_step": [round(x, 3) for x in per_rank_ms]}
 
     # ---- correctness of what was just timed: sampled rows of S and T of every block of this rank vs the CPU oracle ----
     if args.check and args.order == 2:
-        line.update(check_timed_matrices(n, space, pats, vals, flags, eps, mu, rank, world))
+        line.update(check_timed_matrices(n, (rs.numbering.E_global, rs.numbering.F_global) if rs else
+                                         (space.n_edges, space.n_faces), pats, vals, flags, eps_all, mu_all, rank, world,
+                                         block_local_row0))
 
     # ---- e2e through the public API with HOST buffers (rank-local; N=1 only measures the full pipeline) ---
     line["gpu_launches"] = sum(launches_per_step(kernel, pat) for pat in pats) * K
-    del pats, vals, flags, markers, eps, mu, space, mesh     # the resident benchmark's buffers are not needed any more
+    del pats, vals, flags, markers, eps, mu, eps_all, mu_all, space, mesh, rs     # the resident benchmark's buffers are not needed any more
     _free_device()
     if not args.no_e2e:
         try:
@@ -393,7 +418,7 @@ def main():
         dist.destroy_process_group()
 
 
-def check_timed_matrices(n, space, pats, vals, flags, eps, mu, rank, world):
+def check_timed_matrices(n, n_edges_faces, pats, vals, flags, eps, mu, rank, world, block_local_row0):
     """--check (default): the S and T arrays the timed loop left behind are compared, for a sample of rows of every row
     block of this rank (head, tail, the rows around every multiple of 2^28 in the value index -- the 2^31 / 2^32
     offsets -- and random ones), with the reference algorithm run on the host for exactly those rows (oracle/rowcheck.py;
@@ -407,12 +432,14 @@ def check_timed_matrices(n, space, pats, vals, flags, eps, mu, rank, world):
     try:
         from oracle import rowcheck
         orc = rowcheck.CubeOracle(n)
-        assert (orc.E, orc.F) == (space.n_edges, space.n_faces), 'entity counts differ'
+        assert (orc.E, orc.F) == tuple(n_edges_faces), 'entity counts differ'
         h_eps, h_mu = eps.cpu().numpy(), mu.cpu().numpy()
         for k, (pat, (S, T)) in enumerate(zip(pats, vals)):
             rowptr, cols = pat.csr()
+            # flags are indexed by the rank's LOCAL dof numbers (partitioned mesh): global row - shift
             r = rowcheck.check_block(orc, rowptr, cols, S, T, pat.row_begin, pat.n_rows, pat.nnz, flags, h_eps, h_mu,
-                                     20000 // len(pats), 'rank %d block %d' % (rank, k), seed=rank)
+                                     20000 // len(pats), 'rank %d block %d' % (rank, k), seed=rank,
+                                     flags_row_shift=pat.row_begin - block_local_row0[k])
             info["rows"] += r["rows"]
             info["entries"] += r["entries"]
             info["max_err_over_tol"] = max(info["max_err_over_tol"], r["max_err_over_tol"])

@@ -127,7 +127,8 @@ def gather_rows_torch(rowptr, rows_rel, arrays):
     return [x[idx].cpu().numpy() for x in arrays], ln.cpu().numpy()
 
 
-def check_block(orc, rowptr, cols, S, T, row_begin, n_rows, nnz, flags, eps, mu, n_random, label, seed=0):
+def check_block(orc, rowptr, cols, S, T, row_begin, n_rows, nnz, flags, eps, mu, n_random, label, seed=0,
+                flags_row_shift=0):
     """Compare a sample of the rows of one assembled row block (device tensors: block-relative rowptr, cols, S, T; flags =
     the device's uint8 PEC row flags or None) with the oracle.  eps, mu: host arrays.  Returns the summary dict."""
     import torch
@@ -138,7 +139,7 @@ def check_block(orc, rowptr, cols, S, T, row_begin, n_rows, nnz, flags, eps, mu,
     pec = None
     if flags is not None:
         pec = orc.pec_flags_of(rows)
-        got = flags[torch.from_numpy(rows).to(flags.device)].cpu().numpy()
+        got = flags[torch.from_numpy(rows - flags_row_shift).to(flags.device)].cpu().numpy()
         assert np.array_equal(pec, got), '%s: PEC row flags differ from the geometric rule' % label
     want = orc.rows(rows, eps, mu, pec)
     assert np.array_equal(np.diff(want[0]), ln), '%s: row lengths differ' % label

@@ -439,7 +439,6 @@ int sfem_space_set_global_ids(sfem_space_t sp, const int32_t* d_edge_gid, const 
   SFEM_CHECK(sp && d_edge_gid, "NULL argument");
   SFEM_CHECK(sp->mesh->gdim == 3, "partitioned meshes: tetrahedra only");
   SFEM_CHECK(sp->order == 1 || d_face_gid, "order 2 needs the face map");
-  SFEM_CHECK(!sp->rowptr_all, "set the global ids before any pattern is counted");
   DeviceGuard dg(sp->device);
   cudaStream_t st = (cudaStream_t)stream;
   if (!sp->gid_e) SFEM_CUDA(dev_malloc(&sp->gid_e, std::max<int64_t>(sp->E, 1) * 4, st));

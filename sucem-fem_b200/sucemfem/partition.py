@@ -36,28 +36,31 @@ def cell_ranges(n_cells, world):
 
 
 class RankCells(object):
-    """One rank's share of the mesh (host arrays)."""
+    """One rank's share of the mesh: own cells [lo, hi) of the global cell list + halo.  `cells` may be a numpy array or
+    a torch tensor on any device (the selection runs where the cell list lives: one pass over it)."""
 
     def __init__(self, cells, lo, hi):
-        cells = np.asarray(cells)
+        cells = cells if isinstance(cells, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(cells))
+        cells = cells.long()
+        dev = cells.device
         n_vertices = int(cells.max()) + 1
-        own_v = np.zeros(n_vertices, bool)
-        own_v[cells[lo:hi].ravel()] = True
-        touch = own_v[cells].any(axis=1)
+        own_v = torch.zeros(n_vertices, dtype=torch.bool, device=dev)
+        own_v[cells[lo:hi].reshape(-1)] = True
+        touch = own_v[cells].any(dim=1)
         touch[lo:hi] = True
-        self.cell_ids = np.nonzero(touch)[0]                         # global cell indices, ascending
-        self.own_lo = int(np.searchsorted(self.cell_ids, lo))        # local index range of the own cells
+        self.cell_ids = torch.nonzero(touch).flatten()                 # global cell indices, ascending
+        self.own_lo = int(torch.searchsorted(self.cell_ids, torch.tensor([lo], device=dev)))   # local range of the own cells
         self.own_hi = self.own_lo + (hi - lo)
         loc = cells[self.cell_ids]
-        self.vertex_ids = np.unique(loc)                             # global vertex ids, ascending
-        self.cells_local = np.searchsorted(self.vertex_ids, loc).astype(np.int32)
-        halo_v = np.zeros(n_vertices, bool)
-        halo = np.ones(len(self.cell_ids), bool)
+        self.vertex_ids = torch.unique(loc)                            # global vertex ids, ascending
+        self.cells_local = torch.searchsorted(self.vertex_ids, loc.reshape(-1)).reshape(loc.shape).to(torch.int32)
+        halo = torch.ones(len(self.cell_ids), dtype=torch.bool, device=dev)
         halo[self.own_lo:self.own_hi] = False
-        halo_v[loc[halo].ravel()] = True
+        halo_v = torch.zeros(n_vertices, dtype=torch.bool, device=dev)
+        halo_v[loc[halo].reshape(-1)] = True
         shared = own_v & halo_v
         # own cells that other ranks hold as halo: exactly those with a shared vertex
-        self.boundary_cells = self.own_lo + np.nonzero(shared[cells[lo:hi]].any(axis=1))[0]
+        self.boundary_cells = self.own_lo + torch.nonzero(shared[cells[lo:hi]].any(dim=1)).flatten()
         self.global_range = (lo, hi)
 
 
@@ -88,8 +91,8 @@ class RankNumbering(object):
         if self.cf is not None:
             ff = _first_cell(self.cf, self.F)
             self.f_lo, self.f_hi = int((ff < rc.own_lo).sum()), int((ff < rc.own_hi).sum())
-        self.cells_g = torch.from_numpy(rc.vertex_ids[rc.cells_local]).to(dev).long()   # [C, 4] global vertex ids
-        self.bcells = torch.from_numpy(rc.boundary_cells).to(dev).long()
+        self.cells_g = rc.vertex_ids.to(dev)[rc.cells_local.to(dev).long()]   # [C, 4] global vertex ids
+        self.bcells = rc.boundary_cells.to(dev).long()
 
     def counts(self):
         return [self.e_hi - self.e_lo, self.f_hi - self.f_lo]
@@ -207,7 +210,8 @@ class RankSpace(object):
         lo, hi = cell_ranges(len(cells), world)[rank]
         self.rc = rc = RankCells(cells, lo, hi)
         self.rank, self.world = rank, world
-        self.mesh = device.DeviceMesh(np.ascontiguousarray(np.asarray(coords)[rc.vertex_ids]), rc.cells_local)
+        coords = coords if isinstance(coords, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(coords))
+        self.mesh = device.DeviceMesh(coords.to(rc.vertex_ids.device)[rc.vertex_ids].cuda(), rc.cells_local.cuda())
         self.space = device.DeviceSpace(self.mesh, order)
         ce, cf = self.space.cell_entities()
         self.numbering = rn = RankNumbering(rc, ce, cf if order == 2 else None, order)
@@ -239,4 +243,7 @@ class RankSpace(object):
 
     def local_cell_values(self, per_cell_global):
         """Slice of a per-cell array of the WHOLE mesh (eps_r, mu_r, regions) for this rank's cells (own + halo)."""
-        return per_cell_global[self.rc.cell_ids]
+        ids = self.rc.cell_ids
+        if isinstance(per_cell_global, torch.Tensor):
+            return per_cell_global[ids.to(per_cell_global.device)]
+        return per_cell_global[ids.cpu().numpy()]

@@ -36,13 +36,13 @@ def _mesh(name):
 def _rank_numbering(P, ce, p, world, order):
     lo, hi = P.cell_ranges(len(ce), world)[p]
     rc = P.RankCells(ce, lo, hi)
-    loc = fem.number_entities(rc.cells_local)        # numbering of the rank's sub-mesh only
+    loc = fem.number_entities(rc.cells_local.numpy())        # numbering of the rank's sub-mesh only
     return P.RankNumbering(rc, torch.from_numpy(loc['cell_edges'].astype(np.int32)),
                            torch.from_numpy(loc['cell_faces'].astype(np.int32)), order)
 
 
 def _check_rank(rn, num, order):
-    ids = rn.rc.cell_ids
+    ids = rn.rc.cell_ids.numpy()
     assert np.array_equal(rn.e_gid.numpy()[rn.ce.numpy()], num['cell_edges'][ids])
     if order == 2:
         assert np.array_equal(rn.f_gid.numpy()[rn.cf.numpy()], num['cell_faces'][ids])
@@ -70,7 +70,7 @@ def test_logical_ranks_reproduce_global_numbering(name, world, order):
     for p, rn in enumerate(ranks):
         owned = np.arange(rn.e_off, rn.e_off + rn.e_hi - rn.e_lo)
         holders = np.nonzero(np.isin(num['cell_edges'], owned).any(axis=1))[0]
-        assert np.isin(holders, rn.rc.cell_ids).all()
+        assert np.isin(holders, rn.rc.cell_ids.numpy()).all()
     # the halo is thin on a slab partition of a structured cube
     if name == 'cube' and world == 2:
         assert all(len(r.rc.cell_ids) < 0.85 * len(ce) for r in ranks)
