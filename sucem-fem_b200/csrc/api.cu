@@ -569,7 +569,9 @@ int sfem_assemble(sfem_pattern_t pat, int form, const double* d_coef, const uint
   DeviceGuard dg(pat->space->mesh->device);
   const double* eps = form == SFEM_FORM_MASS ? d_coef : nullptr;
   const double* mu = form == SFEM_FORM_STIFFNESS ? d_coef : nullptr;
-  return assemble_generic(pat, form, eps, mu, d_facet_mask, d_pec_row_flags, d_values, nullptr, (cudaStream_t)stream);
+  // S_0: the boundary-row kernel unless the generic kernel is asked for (cross-check)
+  return assemble_generic(pat, form, eps, mu, d_facet_mask, d_pec_row_flags, d_values, nullptr, (cudaStream_t)stream, false,
+                          kernel != SFEM_KERNEL_GENERIC);
 }
 
 int sfem_abc_info(sfem_pattern_t pat, void* stream, int64_t* n_rows, int64_t* nnz) {

@@ -281,6 +281,78 @@ k_values_generic(PatView pv, const double* __restrict__ geo, const double* __res
   }
 }
 
+// ---- K4: the ABC matrix S_0, rows of the entities ON the boundary ---------------------------------------------------
+// One warp per listed row entity.  Only the dofs in the closure of an exterior facet have a tangential trace on it, so a
+// row of S_0 is non-zero only at the closure entities of the (usually two) exterior facets that contain the row entity:
+// the warp clears the entity's rows (unit rows for Dirichlet dofs), then visits the incident cells in ascending order and
+// their exterior facets in ascending local order -- the generic kernel's summation order, so both give the same bits --
+// and for each facet that contains the row entity computes the facet geometry ONCE and lets one lane per (closure
+// entity, k, k') add its 6-term contraction to the slot.  The generic kernel (kept as SFEM_KERNEL_GENERIC cross-check)
+// recomputes the geometry for every (column, cell, facet) of the full row.
+template <int DIM, int ORDER>
+__global__ void __launch_bounds__(kWarps * 32)
+k_abc_rows(PatView pv, const double* __restrict__ coords, const int32_t* __restrict__ cells,
+           const int32_t* __restrict__ cell_facets, const uint8_t* __restrict__ cell_extmask,
+           const uint8_t* __restrict__ facet_mask, const uint8_t* __restrict__ pec, double* __restrict__ out) {
+  using El = Elem<DIM, ORDER>;
+  constexpr int Q = ORDER, NP = El::NP, NFAC = DIM + 1;
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t li = blockIdx.x * (int64_t)kWarps + w;
+  if (li >= pv.n_list) return;
+  const int64_t r = pv.row_list[li];
+  const int64_t g = pv.ent_lo + r;
+  const int64_t a = pv.ent_rowptr[r];
+  const int len = (int)(pv.ent_rowptr[r + 1] - a);
+  const int64_t a_out = pv.out_rowptr ? pv.out_rowptr[li] : a;
+  const int64_t rs0 = (int64_t)Q * Q * a_out;
+  bool pecrow[Q];
+#pragma unroll
+  for (int k = 0; k < Q; ++k) pecrow[k] = pec && pec[Q * g + k];
+  for (int k = 0; k < Q; ++k)
+    for (int idx = lane; idx < Q * len; idx += 32) {
+      const int s = idx / Q, kp = idx - s * Q;
+      out[rs0 + (int64_t)k * Q * len + idx] = (pecrow[k] && pv.ent_cols[a + s] == g + pv.gshift && kp == k) ? 1.0 : 0.0;
+    }
+  __syncwarp();
+  for (int64_t i = pv.inc_ptr[g]; i < pv.inc_ptr[g + 1]; ++i) {
+    const int64_t c = pv.inc_cell[i];
+    const unsigned m = cell_extmask[c];
+    if (!m) continue;
+    const int loc = pv.inc_loc[i];
+    unsigned on;  // local facets that contain the row entity (k_abc_row_flags)
+    if (DIM == 3) on = loc < 6 ? ((0xCA6953u >> (4 * loc)) & 15u) : (1u << (loc - 6));
+    else on = loc < 3 ? (1u << loc) : 0u;
+    const uint16_t* ps = pv.pos + (i - pv.inc_base) * pv.nec;
+    for (int lf = 0; lf < NFAC; ++lf) {
+      if (!(((m & on) >> lf) & 1u)) continue;
+      if (facet_mask && !facet_mask[cell_facets[c * NFAC + lf]]) continue;
+      double K[6];
+      facet_geometry<DIM>(coords, cells + c * (DIM + 1), lf, K);
+      // closure of the facet: tets -- its three edges (+ the face entity at order 2); triangles -- the edge itself
+      constexpr int NCL = DIM == 3 ? (ORDER == 2 ? 4 : 3) : 1;
+      if (lane < NCL * Q * Q) {
+        const int ci = lane / (Q * Q), k = (lane / Q) % Q, kp = lane % Q;
+        const int u = DIM == 3 ? (ci < 3 ? tet_face_edge(lf, ci) : 6 + lf) : lf;
+        // slot of local entity u of this cell in the row (the slot table of tets is in canonical column order)
+        int s = -1;
+        for (int uu = 0; uu < pv.nec; ++uu) {
+          const int ut = pv.canon ? (int)((kCanonDesc[loc] >> (8 + 4 * uu)) & 15ull) : uu;
+          if (ut == u) s = ps[uu];
+        }
+        if (s >= 0 && !pecrow[k]) {
+          const double* B = El::facet(lf, loc * Q + k, u * Q + kp);
+          double* o = out + rs0 + (int64_t)k * Q * len + (int64_t)Q * s + kp;
+          double acc = *o;
+#pragma unroll
+          for (int p = 0; p < NP; ++p) acc += K[p] * B[p];
+          *o = acc;
+        }
+      }
+      __syncwarp();  // the next facet may add to the same slot (the row entity's own block)
+    }
+  }
+}
+
 // ---- triangles, S and T in one sweep: one THREAD per row entity -------------------------------------------------
 // Two triangles that share an edge share nothing else that carries a dof, so the q rows of an entity are
 // [the entity itself] + [the other entities of each incident cell]: every CSR chunk has exactly one contributing cell
@@ -599,7 +671,7 @@ namespace {
 template <int DIM, int ORDER>
 int launch_generic(const sfem_pattern_s* pat, int form, const double* coef_a, const double* coef_b,
                    const uint8_t* facet_mask, const uint8_t* pec, double* out_a, double* out_b,
-                   cudaStream_t st, bool abc_compact) {
+                   cudaStream_t st, bool abc_compact, bool abc_rows_kernel) {
   const sfem_space_s* sp = pat->space;
   const sfem_mesh_s* m = sp->mesh;
   PatView pv{sp->inc_ptr, sp->inc_cell, sp->inc_loc, pat->ent_rowptr, pat->ent_cols, pat->pos,
@@ -635,7 +707,10 @@ int launch_generic(const sfem_pattern_s* pat, int form, const double* coef_a, co
                                                                    sp->cell_extmask, facet_mask, pec, out_a, nullptr);
       break;
     case SFEM_FORM_ABC:
-      if (grid > 0)
+      if (grid > 0 && abc_rows_kernel)
+        k_abc_rows<DIM, ORDER><<<grid, kWarps * 32, 0, st>>>(pv, m->coords, m->cells, cell_facets, sp->cell_extmask,
+                                                            facet_mask, abc_compact ? pec : nullptr, out_a);
+      else if (grid > 0)
         k_values_generic<DIM, ORDER, 2><<<grid, kWarps * 32, 0, st>>>(pv, geo, m->coords, m->cells, cell_facets,
                                                                      sp->cell_extmask, facet_mask,
                                                                      abc_compact ? pec : nullptr, out_a, nullptr);
@@ -658,12 +733,12 @@ int launch_generic(const sfem_pattern_s* pat, int form, const double* coef_a, co
 // S -> out_a, M -> out_b with coef_a = eps_r, coef_b = mu_r.
 int assemble_generic(const sfem_pattern_s* pat, int form, const double* coef_a, const double* coef_b,
                      const uint8_t* facet_mask, const uint8_t* pec, double* out_a, double* out_b,
-                     cudaStream_t st, bool abc_compact) {
+                     cudaStream_t st, bool abc_compact, bool abc_rows_kernel) {
   const int dim = pat->space->mesh->gdim, order = pat->space->order;
-  if (dim == 3 && order == 1) return launch_generic<3, 1>(pat, form, coef_a, coef_b, facet_mask, pec, out_a, out_b, st, abc_compact);
-  if (dim == 3 && order == 2) return launch_generic<3, 2>(pat, form, coef_a, coef_b, facet_mask, pec, out_a, out_b, st, abc_compact);
-  if (dim == 2 && order == 1) return launch_generic<2, 1>(pat, form, coef_a, coef_b, facet_mask, pec, out_a, out_b, st, abc_compact);
-  if (dim == 2 && order == 2) return launch_generic<2, 2>(pat, form, coef_a, coef_b, facet_mask, pec, out_a, out_b, st, abc_compact);
+  if (dim == 3 && order == 1) return launch_generic<3, 1>(pat, form, coef_a, coef_b, facet_mask, pec, out_a, out_b, st, abc_compact, abc_rows_kernel);
+  if (dim == 3 && order == 2) return launch_generic<3, 2>(pat, form, coef_a, coef_b, facet_mask, pec, out_a, out_b, st, abc_compact, abc_rows_kernel);
+  if (dim == 2 && order == 1) return launch_generic<2, 1>(pat, form, coef_a, coef_b, facet_mask, pec, out_a, out_b, st, abc_compact, abc_rows_kernel);
+  if (dim == 2 && order == 2) return launch_generic<2, 2>(pat, form, coef_a, coef_b, facet_mask, pec, out_a, out_b, st, abc_compact, abc_rows_kernel);
   set_error("unsupported (dim, order)");
   return 2;
 }

@@ -221,7 +221,7 @@ int build_pattern_block(sfem_pattern_s* pat, const int64_t* rowptr_all, int64_t 
 int export_pattern(const sfem_pattern_s* pat, int64_t* d_rowptr, int32_t* d_cols, cudaStream_t st, int64_t nnz_base = 0);
 int assemble_generic(const sfem_pattern_s* pat, int form, const double* coef_a, const double* coef_b,
                      const uint8_t* facet_mask, const uint8_t* pec, double* out_a, double* out_b,
-                     cudaStream_t st, bool abc_compact = false);
+                     cudaStream_t st, bool abc_compact = false, bool abc_rows_kernel = true);
 // boundary-row list + compact offsets of the ABC matrix (lazily built, synchronises `st` the first time)
 int build_abc_rows(sfem_pattern_s* pat, cudaStream_t st);
 int assemble_rows_ST(const sfem_pattern_s* pat, const double* eps, const double* mu, const uint8_t* pec, double* S,

@@ -326,7 +326,8 @@ def assemble(form, tensor=None, pec_row_flags=None, kernel=N.KERNEL_AUTO):
     pat = space.pattern()
     coef = None if form.coefficient is None else form.coefficient.device_values()
     code = {'mass': N.FORM_MASS, 'stiffness': N.FORM_STIFFNESS, 'abc': N.FORM_ABC}[form.kind]
-    vals = pat.assemble(code, coef=coef, pec_flags=pec_row_flags,
-                        kernel=N.KERNEL_GENERIC if kernel == N.KERNEL_AUTO else kernel)
+    if kernel == N.KERNEL_AUTO and form.kind != 'abc':   # single forms: the generic kernel; S_0: the boundary-row kernel
+        kernel = N.KERNEL_GENERIC
+    vals = pat.assemble(code, coef=coef, pec_flags=pec_row_flags, kernel=kernel)
     mat.init(pat, vals)
     return mat

@@ -79,8 +79,15 @@ def test_compact_abc_matrix(mesh, order):
         mask = torch.ones_like(full, dtype=torch.bool)
         mask[idx] = False
         assert float(full[mask].abs().max()) == 0.0 if mask.any() else True
-    # consumers (pattern of all rows)
+    # the boundary-row kernel (AUTO) and the generic kernel give the same bits, with a facet mask and Dirichlet rows too
     pat = sp.pattern()
+    fm = torch.from_numpy((rng.random(sp.n_facets) < 0.6).astype(np.uint8)).cuda()
+    mk = torch.zeros(sp.n_facets, dtype=torch.int32, device='cuda')
+    sp.mark_exterior_facets(mk, 999)
+    pf = sp.pec_row_flags(mk, 999)
+    for kw in (dict(), dict(facet_mask=fm), dict(pec_flags=pf), dict(facet_mask=fm, pec_flags=pf)):
+        assert torch.equal(pat.assemble(N.FORM_ABC, **kw), pat.assemble(N.FORM_ABC, kernel=N.KERNEL_GENERIC, **kw))
+    # consumers (pattern of all rows)
     S, M = pat.assemble(N.FORM_STIFFNESS), pat.assemble(N.FORM_MASS)
     full, comp = pat.assemble(N.FORM_ABC), pat.assemble_abc()
     coefs = [1.0, -2.5, 0.7j]
