@@ -79,14 +79,17 @@ def test_compact_abc_matrix(mesh, order):
         mask = torch.ones_like(full, dtype=torch.bool)
         mask[idx] = False
         assert float(full[mask].abs().max()) == 0.0 if mask.any() else True
-    # the boundary-row kernel (AUTO) and the generic kernel give the same bits, with a facet mask and Dirichlet rows too
+    # the boundary-row kernel (AUTO) against the generic kernel, with a facet mask and Dirichlet rows too.  Not bit for
+    # bit: the generic kernel also adds the exterior facets that do NOT contain the row entity, whose contraction
+    # vanishes only up to round-off (1e-17), where the boundary-row kernel stores exact zeros
     pat = sp.pattern()
     fm = torch.from_numpy((rng.random(sp.n_facets) < 0.6).astype(np.uint8)).cuda()
     mk = torch.zeros(sp.n_facets, dtype=torch.int32, device='cuda')
     sp.mark_exterior_facets(mk, 999)
     pf = sp.pec_row_flags(mk, 999)
     for kw in (dict(), dict(facet_mask=fm), dict(pec_flags=pf), dict(facet_mask=fm, pec_flags=pf)):
-        assert torch.equal(pat.assemble(N.FORM_ABC, **kw), pat.assemble(N.FORM_ABC, kernel=N.KERNEL_GENERIC, **kw))
+        va, vb = pat.assemble(N.FORM_ABC, **kw), pat.assemble(N.FORM_ABC, kernel=N.KERNEL_GENERIC, **kw)
+        assert bool(((va - vb).abs() <= 1e-12 * vb.abs() + 1e-15 * vb.abs().max()).all())
     # consumers (pattern of all rows)
     S, M = pat.assemble(N.FORM_STIFFNESS), pat.assemble(N.FORM_MASS)
     full, comp = pat.assemble(N.FORM_ABC), pat.assemble_abc()
