@@ -214,6 +214,7 @@ def main():
     ap.add_argument('--check', dest='check', action='store_true', default=True,
                     help='after the timed region compare sampled rows of the timed matrices with the CPU oracle (default)')
     ap.add_argument('--no-check', dest='check', action='store_false')
+    ap.add_argument('--no-gather', action='store_true', help='N > 1: skip the NCCL gather of the distributed CSR (config 3)')
     ap.add_argument('--no-extras', action='store_true',
                     help='skip the extra single-GPU measurements (config 5 streamed through one GPU, UnitCube(150), ...)')
     args = ap.parse_args()
@@ -394,6 +395,12 @@ def main():
             elif "error" not in e2e:
                 e2e = {"error": "another rank could not run the host-buffer pipeline"}
         line["e2e"] = e2e
+    # ---- the path's ONE collective (N > 1): replicate the distributed CSR of BASELINE config 3 for a solver, over NCCL -----
+    if world > 1 and not args.no_gather:
+        try:
+            line["gather_csr"] = gather_leg(rank, world)
+        except Exception as e:  # noqa: BLE001
+            line["gather_csr"] = {"error": repr(e)[:300]}
     # ---- CPU baseline (rank 0, N=1): bounded sample, 1 thread = what sucemfem + DOLFIN 1.0 run ------------
     if rank == 0 and world == 1 and not args.no_cpu:
         nz1, nzall = slab_layers(n, 80e3), slab_layers(n, 700e3)
@@ -602,6 +609,60 @@ def run_extras(peak):
             _free_device()
         out[name]["wall_s"] = round(time.perf_counter() - t0, 2)
     return out
+
+
+def gather_leg(rank, world, n=70, reps=3):
+    """SURVEY 8.2 row e, second half: the only collective of the path.  UnitCube(70) order 2 (BASELINE config 3, 13.2 M dofs,
+    571 M non-zeros per matrix), partitioned mesh; every rank assembles its two row blocks and the blocks (rowptr, cols, S, T)
+    are all-gathered into the full CSR on EVERY rank (sucemfem.parallel.gather_csr_two_class: one small all_gather of sizes,
+    then each array once, straight into its slice).  Device-timed, max over ranks; not part of the assembly step."""
+    import torch
+    import torch.distributed as dist
+    from sucemfem import device, parallel, partition
+    gen = device.DeviceMesh.unit(n, n, n)
+    g = torch.Generator(device='cuda')
+    g.manual_seed(1234)
+    eps_all = 1.0 + 15.0 * torch.rand(gen.num_cells, dtype=torch.float64, device='cuda', generator=g)
+    mu_all = 1.0 + torch.rand(gen.num_cells, dtype=torch.float64, device='cuda', generator=g)
+    rs = partition.RankSpace(gen.coords, gen.cells, 2, rank, world)
+    del gen
+    markers = torch.zeros(rs.space.n_facets, dtype=torch.int32, device='cuda')
+    rs.space.mark_exterior_facets(markers, 999)
+    flags = rs.space.pec_row_flags(markers, 999)
+    eps, mu = rs.local_cell_values(eps_all).contiguous(), rs.local_cell_values(mu_all).contiguous()
+    blocks = []
+    for pat in rs.patterns():
+        rp, cl = pat.csr()
+        S, T = pat.assemble_ST(eps, mu, flags)
+        blocks.append((rp, cl, [S, T]))
+    own = sum(b[1].numel() for b in blocks)
+    times = []
+    for it in range(reps + 1):
+        torch.cuda.synchronize()
+        dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        rowptr, cols, (Sf, Tf) = parallel.gather_csr_two_class(blocks[0], blocks[1])
+        e1.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1)], device='cuda')
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        if it > 0:
+            times.append(float(t.item()))
+    nnz, ndof = int(cols.numel()), int(rowptr.numel()) - 1
+    cc = cube_counts(n)
+    # structure checks on every rank (the bit-exact comparison with a single-rank assembly is tests/ + tools/gather_nccl.py)
+    ok = (nnz == cc["nnz"] and ndof == cc["ndof"] and int(rowptr[-1]) == nnz and bool((rowptr[1:] >= rowptr[:-1]).all())
+          and bool(torch.isfinite(Sf).all()) and bool(torch.isfinite(Tf).all()))
+    okt = torch.tensor([1.0 if ok else 0.0], device='cuda')
+    dist.all_reduce(okt, op=dist.ReduceOp.MIN)
+    ms = sorted(times)[len(times) // 2]
+    recv = (nnz - own) * 20 + (ndof + 1) * 8
+    del rowptr, cols, Sf, Tf, blocks, rs
+    _free_device()
+    return {"workload": "UnitCube(%d) order 2 (config 3): rowptr, cols, S, T replicated on every rank" % n, "n_gpus": world,
+            "nnz_per_matrix": nnz, "bytes_out_per_rank": nnz * 20 + (ndof + 1) * 8, "bytes_received_rank0": recv, "ms": ms,
+            "all_ms": [round(x, 2) for x in times], "GBps_received_per_gpu": recv / ms / 1e6, "structure_ok": bool(okt.item() == 1.0)}
 
 
 def host_memory_available():
