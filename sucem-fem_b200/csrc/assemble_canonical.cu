@@ -1201,7 +1201,8 @@ int canonical_launches(const sfem_pattern_s* pat) {
   if (pat->space->order == 1) return 1;
   const int64_t E = pat->space->E;
   // edge rows: k_pack_coef + k_canon_edges2 (or the lane-pair kernel alone); face rows: k_canon_faces
-  return (pat->ent_lo < E ? (pat->rec_e2 ? 2 : 1) : 0) + (pat->ent_hi > E ? 1 : 0);
+  // + cell geometry and row gather of the generic kernel for the rows of the per-entity fallback
+  return (pat->ent_lo < E ? (pat->rec_e2 ? 2 : 1) : 0) + (pat->ent_hi > E ? 1 : 0) + (pat->n_gen_rows > 0 ? 2 : 0);
 }
 
 // (mu_r, eps_r) of every cell side by side: one 16-byte gather per item instead of two 8-byte ones
@@ -1283,6 +1284,10 @@ int assemble_canonical_ST(const sfem_pattern_s* pat, const double* eps, const do
     k_canon_faces<<<grid, kThreadsFaces, smem, st>>>(p);
   }
   SFEM_CUDA(cudaGetLastError());
+  // per-entity fallback: the few edge rows the batched layout does not take (an edge with more cells than a warp has lanes,
+  // a row longer than the tile) are assembled by the generic kernel into the same arrays
+  if (pat->n_gen_rows > 0)
+    SFEM_TRY(assemble_generic(pat, 3, eps_in, mu_in, nullptr, pec, S, T, st, false, true, pat->gen_rows, pat->n_gen_rows));
   return 0;
 }
 

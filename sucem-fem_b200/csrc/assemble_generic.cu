@@ -671,7 +671,7 @@ namespace {
 template <int DIM, int ORDER>
 int launch_generic(const sfem_pattern_s* pat, int form, const double* coef_a, const double* coef_b,
                    const uint8_t* facet_mask, const uint8_t* pec, double* out_a, double* out_b,
-                   cudaStream_t st, bool abc_compact, bool abc_rows_kernel) {
+                   cudaStream_t st, bool abc_compact, bool abc_rows_kernel, const int64_t* row_list, int64_t n_list) {
   const sfem_space_s* sp = pat->space;
   const sfem_mesh_s* m = sp->mesh;
   PatView pv{sp->inc_ptr, sp->inc_cell, sp->inc_loc, pat->ent_rowptr, pat->ent_cols, pat->pos,
@@ -689,6 +689,12 @@ int launch_generic(const sfem_pattern_s* pat, int form, const double* coef_a, co
     pv.n_list = pat->n_abc_rows;
     if (abc_compact) pv.out_rowptr = pat->abc_rowptr;
     grid = (unsigned)((pat->n_abc_rows + kWarps - 1) / kWarps);
+  }
+  if (form != SFEM_FORM_ABC && row_list) {  // only these rows (per-entity fallback of the canonical path)
+    if (n_list == 0) return 0;
+    pv.row_list = row_list;
+    pv.n_list = n_list;
+    grid = (unsigned)((n_list + kWarps - 1) / kWarps);
   }
   const int32_t* cell_facets = DIM == 3 ? sp->cell_faces : sp->cell_edges;
   double* geo = nullptr;
@@ -733,12 +739,12 @@ int launch_generic(const sfem_pattern_s* pat, int form, const double* coef_a, co
 // S -> out_a, M -> out_b with coef_a = eps_r, coef_b = mu_r.
 int assemble_generic(const sfem_pattern_s* pat, int form, const double* coef_a, const double* coef_b,
                      const uint8_t* facet_mask, const uint8_t* pec, double* out_a, double* out_b,
-                     cudaStream_t st, bool abc_compact, bool abc_rows_kernel) {
+                     cudaStream_t st, bool abc_compact, bool abc_rows_kernel, const int64_t* row_list, int64_t n_list) {
   const int dim = pat->space->mesh->gdim, order = pat->space->order;
-  if (dim == 3 && order == 1) return launch_generic<3, 1>(pat, form, coef_a, coef_b, facet_mask, pec, out_a, out_b, st, abc_compact, abc_rows_kernel);
-  if (dim == 3 && order == 2) return launch_generic<3, 2>(pat, form, coef_a, coef_b, facet_mask, pec, out_a, out_b, st, abc_compact, abc_rows_kernel);
-  if (dim == 2 && order == 1) return launch_generic<2, 1>(pat, form, coef_a, coef_b, facet_mask, pec, out_a, out_b, st, abc_compact, abc_rows_kernel);
-  if (dim == 2 && order == 2) return launch_generic<2, 2>(pat, form, coef_a, coef_b, facet_mask, pec, out_a, out_b, st, abc_compact, abc_rows_kernel);
+  if (dim == 3 && order == 1) return launch_generic<3, 1>(pat, form, coef_a, coef_b, facet_mask, pec, out_a, out_b, st, abc_compact, abc_rows_kernel, row_list, n_list);
+  if (dim == 3 && order == 2) return launch_generic<3, 2>(pat, form, coef_a, coef_b, facet_mask, pec, out_a, out_b, st, abc_compact, abc_rows_kernel, row_list, n_list);
+  if (dim == 2 && order == 1) return launch_generic<2, 1>(pat, form, coef_a, coef_b, facet_mask, pec, out_a, out_b, st, abc_compact, abc_rows_kernel, row_list, n_list);
+  if (dim == 2 && order == 2) return launch_generic<2, 2>(pat, form, coef_a, coef_b, facet_mask, pec, out_a, out_b, st, abc_compact, abc_rows_kernel, row_list, n_list);
   set_error("unsupported (dim, order)");
   return 2;
 }

@@ -137,7 +137,8 @@ __global__ void k_edge_ring(SpaceView sv, const int32_t* __restrict__ cells, con
   // e2_slot0[r] of `rec` (batch = slot / 32), and every record gets an aux entry
   const int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (r >= n_edge_rows) return;
-  if (e2_slot0 && *reinterpret_cast<volatile int*>(bad) != 0) return;  // the batch builder refused an edge: slots are invalid
+  if (e2_slot0 && *reinterpret_cast<volatile int*>(bad) != 0) return;  // the batch builder gave up: slots are invalid
+  if (e2_slot0 && e2_slot0[r] < 0) return;                              // this edge's row goes to the generic kernel
   const int64_t g = ent_lo + r;
   const int64_t i0 = inc_ptr[g];
   const int m = (int)(inc_ptr[g + 1] - i0);
@@ -242,7 +243,7 @@ __global__ void k_e2_batches(const int64_t* __restrict__ inc_ptr, const int64_t*
                              int64_t n_edge_rows, int vmax, int64_t nb_max, int32_t* __restrict__ seg_nb,
                              const int64_t* __restrict__ seg_b0,
                              int64_t* __restrict__ slot0, uint32_t* __restrict__ tileoff, uint2* __restrict__ hdr,
-                             int* __restrict__ bad) {
+                             int* __restrict__ bad, int64_t* __restrict__ gen_rows, int gen_cap) {
   const int64_t seg = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   const int64_t r0 = seg * kE2Seg;
   if (r0 >= n_edge_rows) return;
@@ -255,11 +256,20 @@ __global__ void k_e2_batches(const int64_t* __restrict__ inc_ptr, const int64_t*
     const int64_t ip1 = inc_ptr[ent_lo + r + 1], rp1 = ent_rowptr[r + 1];
     const int m = (int)(ip1 - ip), c2 = 2 * (int)(rp1 - rp);
     if (m > vmax || m < 1 || c2 > kE2TileChunks) {
-      atomicMax(bad, 1);
-      return;
+      // an edge the lane-per-item kernel does not take (more cells than lanes, or a row longer than the tile): it gets no
+      // batch slots; the batch before it is closed, the row goes to the generic kernel (per-entity fallback, bad[1] counts)
+      if (WRITE) {
+        if (items > 0) hdr[b] = make_uint2((unsigned)a_first, (unsigned)chunks);
+        slot0[r] = -1;
+        const int k = atomicAdd(bad + 1, 1);
+        if (k < gen_cap) gen_rows[k] = r; else atomicMax(bad, 1);
+      }
+      items = 0; chunks = 0;
+      ip = ip1; rp = rp1;
+      continue;
     }
-    if (nb == 0 || items + m > 32 || chunks + c2 > kE2TileChunks) {
-      if (WRITE && nb > 0) hdr[b] = make_uint2((unsigned)a_first, (unsigned)chunks);
+    if (items == 0 || items + m > 32 || chunks + c2 > kE2TileChunks) {
+      if (WRITE && items > 0) hdr[b] = make_uint2((unsigned)a_first, (unsigned)chunks);
       ++nb; ++b;
       if (WRITE && b >= nb_max) {  // more batches than the host-side bound allowed for: the caller falls back
         atomicMax(bad, 1);
@@ -276,8 +286,11 @@ __global__ void k_e2_batches(const int64_t* __restrict__ inc_ptr, const int64_t*
     chunks += c2;
     ip = ip1; rp = rp1;
   }
-  if (WRITE) hdr[b] = make_uint2((unsigned)a_first, (unsigned)chunks);
-  else seg_nb[seg] = (int32_t)nb;
+  if (WRITE) {
+    if (items > 0) hdr[b] = make_uint2((unsigned)a_first, (unsigned)chunks);
+  } else {
+    seg_nb[seg] = (int32_t)nb;
+  }
 }
 
 __global__ void k_len_to_i64(const int32_t* __restrict__ len, int64_t* __restrict__ out, int64_t n) {
@@ -383,15 +396,18 @@ static int fill_pattern_impl(sfem_pattern_s* pat, cudaStream_t st, bool allow_e2
   // incidences of the block's edge rows: inc_ptr[E] = (cells) x (edges per cell), no read-back needed
   const int64_t inc_at_E = sp->mesh->C * sp->ne_loc;
   const int64_t n_edge_inc = std::min(std::max(inc_at_E, pat->inc_base), pat->inc_base + pat->n_inc_block) - pat->inc_base;
-  const bool want_rec = canon && pat->max_row_len <= 255;
+  // slots are bytes: face rows hold at most 16 entities, edge rows longer than the tile (224 entities) are excluded from the
+  // batched layout one by one (k_e2_batches); the lane-pair layout needs every row to fit
+  const bool e2_possible = allow_e2 && canon && sp->order == 2 && edge_kernel_version() == 2 && pat->nnz_ent < (1ll << 32) &&
+                           pat->max_row_len_other <= 16;
+  const bool want_rec = canon && (pat->max_row_len <= 255 || e2_possible);
   // lane-per-item edge kernel (order-2 tets): every size below is an upper bound known on the host, so that the block
   // pipelines of host_pipeline.cu see the same allocation sequence block after block and no extra synchronisation
   const int vmax = (int)std::min<int64_t>(32, std::max<int64_t>(1, (pat->max_row_len_edges - 1) / 6));  // ring of m cells: >= 6m+1 entities
-  const bool want_e2 = allow_e2 && want_rec && n_edge_rows > 0 && sp->order == 2 && edge_kernel_version() == 2 &&
-                       pat->nnz_ent < (1ll << 32) && 2 * pat->max_row_len_edges <= kE2TileChunks;
-  int* overflow = nullptr;
-  SFEM_CUDA(dev_malloc(&overflow, 4, st));
-  SFEM_CUDA(cudaMemsetAsync(overflow, 0, 4, st));
+  const bool want_e2 = e2_possible && n_edge_rows > 0;
+  int* overflow = nullptr;  // [0] a builder gave up (whole-pattern fallback), [1] rows handed to the generic kernel
+  SFEM_CUDA(dev_malloc(&overflow, 8, st));
+  SFEM_CUDA(cudaMemsetAsync(overflow, 0, 8, st));
   SFEM_CUDA(dev_malloc(&pat->ent_cols, std::max<int64_t>(pat->nnz_ent, 1) * 4, st));
   SFEM_CUDA(dev_malloc(&pat->pos, std::max<int64_t>(pat->n_inc_block * sp->n_ent_cell, 1) * 2, st));
   if (want_rec) {
@@ -414,14 +430,16 @@ static int fill_pattern_impl(sfem_pattern_s* pat, cudaStream_t st, bool allow_e2
     // a batch closed because the next edge (at most vmax items) did not fit holds more than 32 - vmax items; batches
     // closed by the tile limit (many low-valence boundary edges) get 1/64 of the items as slack, and a mesh that needs
     // more than this bound makes k_e2_batches raise `bad` (fallback below)
-    const int64_t nb_max = n_edge_inc / (33 - vmax) + n_edge_inc / 64 + nseg + 16;
+    const int64_t nb_max = n_edge_inc / (33 - std::min(vmax, 16)) + n_edge_inc / 64 + nseg + 16;
+    const int gen_cap = (int)std::min<int64_t>(n_edge_rows, 1 << 20);
+    SFEM_CUDA(dev_malloc(&pat->gen_rows, (size_t)gen_cap * 8, st));
     int32_t* seg_nb = nullptr;
     int64_t* seg_b0 = nullptr;
     SFEM_CUDA(dev_malloc(&seg_nb, (nseg + 1) * 4, st));
     SFEM_CUDA(dev_malloc(&seg_b0, (nseg + 1) * 8, st));
     SFEM_CUDA(cudaMemsetAsync(seg_nb, 0, (nseg + 1) * 4, st));
-    k_e2_batches<false><<<grid_for(nseg, 64), 64, 0, st>>>(sp->inc_ptr, pat->ent_rowptr, pat->ent_lo, n_edge_rows, vmax, nb_max,
-                                                           seg_nb, nullptr, nullptr, nullptr, nullptr, overflow);
+    k_e2_batches<false><<<grid_for(nseg, 64), 64, 0, st>>>(sp->inc_ptr, pat->ent_rowptr, pat->ent_lo, n_edge_rows, 32, nb_max,
+                                                           seg_nb, nullptr, nullptr, nullptr, nullptr, overflow, nullptr, 0);
     size_t tb = 0;
     SFEM_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tb, seg_nb, seg_b0, (int)(nseg + 1), st));
     void* tmp = nullptr;
@@ -438,8 +456,9 @@ static int fill_pattern_impl(sfem_pattern_s* pat, cudaStream_t st, bool allow_e2
     SFEM_CUDA(dev_malloc(&e2_slot0, n_edge_rows * 8, st));
     SFEM_CUDA(dev_malloc(&e2_tileoff, n_edge_rows * 4, st));
     SFEM_CUDA(dev_malloc(&e2_hdr, nb_max * 8, st));
-    k_e2_batches<true><<<grid_for(nseg, 64), 64, 0, st>>>(sp->inc_ptr, pat->ent_rowptr, pat->ent_lo, n_edge_rows, vmax, nb_max,
-                                                          nullptr, seg_b0, e2_slot0, e2_tileoff, e2_hdr, overflow);
+    k_e2_batches<true><<<grid_for(nseg, 64), 64, 0, st>>>(sp->inc_ptr, pat->ent_rowptr, pat->ent_lo, n_edge_rows, 32, nb_max,
+                                                          nullptr, seg_b0, e2_slot0, e2_tileoff, e2_hdr, overflow,
+                                                          pat->gen_rows, gen_cap);
     dev_free(seg_nb, st);
     dev_free(seg_b0, st);
   }
@@ -449,10 +468,12 @@ static int fill_pattern_impl(sfem_pattern_s* pat, cudaStream_t st, bool allow_e2
         sv, sp->mesh->cells, sp->inc_ptr, sp->inc_cell, sp->inc_loc, pat->ent_lo, n_edge_rows, pat->inc_base,
         pat->ent_rowptr, pat->ent_cols, reinterpret_cast<uint8_t*>(want_e2 ? pat->rec_e2 : pat->rec), overflow, e2_slot0,
         e2_tileoff, e2_hdr, pat->aux_e2);
-    int h_bad = 0;
-    SFEM_CUDA(cudaMemcpyAsync(&h_bad, overflow, 4, cudaMemcpyDeviceToHost, st));
+    int h_flags[2] = {0, 0};
+    SFEM_CUDA(cudaMemcpyAsync(h_flags, overflow, 8, cudaMemcpyDeviceToHost, st));
     SFEM_CUDA(cudaStreamSynchronize(st));
+    const int h_bad = h_flags[0];
     pat->ring_ok = h_bad == 0;
+    pat->n_gen_rows = want_e2 && h_bad == 0 ? h_flags[1] : 0;
     e2_failed = want_e2 && h_bad != 0;
     dev_free(e2_slot0, st);
     dev_free(e2_tileoff, st);
@@ -471,7 +492,9 @@ static int fill_pattern_impl(sfem_pattern_s* pat, cudaStream_t st, bool allow_e2
     dev_free(pat->rec_e2, st); pat->rec_e2 = nullptr;
     dev_free(pat->aux_e2, st); pat->aux_e2 = nullptr;
     dev_free(pat->nbatch_e2_dev, st); pat->nbatch_e2_dev = nullptr;
+    dev_free(pat->gen_rows, st); pat->gen_rows = nullptr;
     pat->n_batch_e2 = 0;
+    pat->n_gen_rows = 0;
     return fill_pattern_impl(pat, st, false);
   }
   return 0;
@@ -516,6 +539,7 @@ void free_pattern_buffers(sfem_pattern_s* pat, cudaStream_t st) {
   dev_free(pat->pos, st); pat->pos = nullptr;
   dev_free(pat->rec_alloc, st); pat->rec_alloc = nullptr; pat->rec = nullptr;
   dev_free(pat->nbatch_e2_dev, st); pat->nbatch_e2_dev = nullptr;
+  dev_free(pat->gen_rows, st); pat->gen_rows = nullptr;
   dev_free(pat->rec_e2, st); pat->rec_e2 = nullptr;
   dev_free(pat->aux_e2, st); pat->aux_e2 = nullptr;
   dev_free(pat->abc_rows, st); pat->abc_rows = nullptr;

@@ -158,6 +158,8 @@ struct sfem_pattern_s {
                                   // ring-closing lane distance), first entity chunk of the batch's span, span chunks}
   int64_t n_batch_e2 = 0;         // upper bound known on the host (allocation size); the count itself stays on the device:
   int64_t* nbatch_e2_dev = nullptr;
+  int64_t* gen_rows = nullptr;    // block-relative edge rows the batched layout does not take (more than 32 cells, rows longer
+  int64_t n_gen_rows = 0;         // than the tile): the canonical path hands exactly these to the generic kernel
   int64_t* abc_rows = nullptr;    // block-relative row entities that lie on an exterior facet (lazily built)
   int64_t n_abc_rows = -1;
   int64_t* abc_rowptr = nullptr;  // [n_abc_rows+1] entity-level offsets of those rows in the COMPACT S_0 storage
@@ -221,7 +223,8 @@ int build_pattern_block(sfem_pattern_s* pat, const int64_t* rowptr_all, int64_t 
 int export_pattern(const sfem_pattern_s* pat, int64_t* d_rowptr, int32_t* d_cols, cudaStream_t st, int64_t nnz_base = 0);
 int assemble_generic(const sfem_pattern_s* pat, int form, const double* coef_a, const double* coef_b,
                      const uint8_t* facet_mask, const uint8_t* pec, double* out_a, double* out_b,
-                     cudaStream_t st, bool abc_compact = false, bool abc_rows_kernel = true);
+                     cudaStream_t st, bool abc_compact = false, bool abc_rows_kernel = true,
+                     const int64_t* row_list = nullptr, int64_t n_list = 0);
 // boundary-row list + compact offsets of the ABC matrix (lazily built, synchronises `st` the first time)
 int build_abc_rows(sfem_pattern_s* pat, cudaStream_t st);
 int assemble_rows_ST(const sfem_pattern_s* pat, const double* eps, const double* mu, const uint8_t* pec, double* S,

@@ -217,11 +217,11 @@ def test_gmsh_prism_pec_markers_and_cavity_modes():
 
 
 def test_high_valence_edge_falls_back_to_generic_kernel():
-    """Edges shared by 70 / 40 cells exceed the ring builder's bound / the shared-memory tile of the canonical
-    kernels: the AUTO kernel must fall back to the generic kernel (same results), the canonical kernel must refuse
-    loudly (34 cells: more than the 32 lanes of the lane-per-item edge kernel -- its batch builder refuses and the
-    pattern is rebuilt with the lane-pair layout); closed rings of 12, 20 and 30 cells go through the canonical
-    kernels (ring-closing shuffle, batches limited by the tile)."""
+    """Per-ENTITY fallback: an edge shared by 70 / 40 / 34 cells has more items than a warp has lanes (and a row longer than
+    the shared-memory tile); the batch builder leaves exactly that edge out and the canonical path hands its rows to the
+    generic kernel, every other row stays on the canonical kernels (5 launches: pack, edges, faces, cell geometry, generic
+    rows).  Closed rings of 12, 20 and 30 cells go through the canonical kernels alone (ring-closing shuffle, batches limited
+    by the tile)."""
     import torch
     from oracle import fem
     from sucemfem import device, _native as N
@@ -235,8 +235,11 @@ def test_high_valence_edge_falls_back_to_generic_kernel():
         S, T = pat.assemble_ST(kernel=N.KERNEL_AUTO)
         assert np.all(np.abs(S.cpu().numpy() - ref['S']) <= 1e-12 * np.abs(ref['S']) + 1e-15 * np.abs(ref['S']).max())
         assert np.all(np.abs(T.cpu().numpy() - ref['M']) <= 1e-12 * np.abs(ref['M']) + 1e-15 * np.abs(ref['M']).max())
-        with pytest.raises(N.NativeError, match='canonical'):
-            pat.assemble_ST(kernel=N.KERNEL_CANONICAL)
+        assert N.lib.sfem_launches_per_assemble_ST(pat.handle, N.KERNEL_AUTO) == 5
+        Sc, Tc = pat.assemble_ST(kernel=N.KERNEL_CANONICAL)
+        assert torch.equal(Sc, S) and torch.equal(Tc, T)
+        Sg, Tg = pat.assemble_ST(kernel=N.KERNEL_GENERIC)
+        assert not torch.equal(Sg, S)        # the other rows really come from the canonical kernels
         # order 1 on the same fan: AUTO / ROWS = the thread-per-edge kernel; the hub edge's row (1 + 3 m entries)
         # makes its warp's span exceed the shared-memory tile at m = 70, which takes the direct-write path
         ref1 = fem.assemble_system(co, ce, 1)
@@ -251,6 +254,7 @@ def test_high_valence_edge_falls_back_to_generic_kernel():
         ce = np.sort(np.array([[0, 1, 2 + i, 2 + (i + 1) % m] for i in range(m)]), axis=1)
         ref = fem.assemble_system(co, ce, 2)
         pat = device.DeviceSpace(device.DeviceMesh(co, ce), 2).pattern()
+        assert N.lib.sfem_launches_per_assemble_ST(pat.handle, N.KERNEL_AUTO) == 3
         S, T = pat.assemble_ST(kernel=N.KERNEL_CANONICAL)
         assert np.all(np.abs(S.cpu().numpy() - ref['S']) <= 1e-12 * np.abs(ref['S']) + 1e-15 * np.abs(ref['S']).max())
         assert np.all(np.abs(T.cpu().numpy() - ref['M']) <= 1e-12 * np.abs(ref['M']) + 1e-15 * np.abs(ref['M']).max())
