@@ -695,39 +695,54 @@ def e2e_run(n, steps, rank=0, world=1):
     numpy mesh + materials in, scipy-ready CSR (rowptr, cols, S, T) in page-locked host arrays out.  Everything
     between -- H2D, numbering, PEC flags, pattern, S+T values, CSR expansion, D2H -- is inside the timed region; the
     D2H of row block k overlaps the assembly of block k+1.  Three untimed iterations come first (the first one page-locks the
-    output arrays, a one-off a caller that repeats the call keeps).  world > 1: every rank creates the job from the whole
-    mesh and streams only the rows it owns (one edge range + one face range); no communication."""
+    output arrays, a one-off a caller that repeats the call keeps).  world > 1: the mesh is partitioned -- every rank's job is
+    created from its own cells + halo (host arrays), the global numbering is exchanged over NCCL inside the timed region, and
+    the rank streams only the rows it owns (partition.RankHostJob)."""
     import numpy as np
     import torch
     from sucemfem import device
     # page-locked host arrays of the whole job: 20 B per non-zero (1660 n^3 non-zeros per matrix at order 2) + inputs
-    need = 20.0 * 1660.0 * n ** 3 + 100.0 * 6 * n ** 3 * world
+    need = 20.0 * 1660.0 * n ** 3 + 100.0 * 6 * n ** 3 * 2
     avail = host_memory_available()
     if avail is not None and need > 0.7 * avail:
         raise MemoryError("host-buffer outputs of this workload need %.0f GB of page-locked memory, %.0f GB available"
                           % (need / 1e9, avail / 1e9))
     gen = device.DeviceMesh.unit(n, n, n)          # synthesise the HOST input arrays (outside the timed region)
-    co, ce = gen.coords.cpu().numpy(), gen.cells.cpu().numpy()
-    del gen
-    rng = np.random.default_rng(1234)
-    eps = rng.uniform(1, 16, len(ce))
-    mu = rng.uniform(1, 2, len(ce))
-    pin = lambda a: torch.from_numpy(a).pin_memory()
-    h_co, h_ce, h_eps, h_mu = pin(co), pin(ce), pin(eps), pin(mu)
+    pin = lambda a: (a if isinstance(a, torch.Tensor) else torch.from_numpy(a)).contiguous().pin_memory()
+    g = torch.Generator(device='cuda')
+    g.manual_seed(1234)
+    n_cells_total = gen.num_cells
+    eps_d = 1.0 + 15.0 * torch.rand(n_cells_total, dtype=torch.float64, device='cuda', generator=g)
+    mu_d = 1.0 + torch.rand(n_cells_total, dtype=torch.float64, device='cuda', generator=g)
+    rc = None
+    if world == 1:
+        h_co, h_ce, h_eps, h_mu = pin(gen.coords.cpu()), pin(gen.cells.cpu()), pin(eps_d.cpu()), pin(mu_d.cpu())
+    else:
+        # mesh distribution (outside the timed region, like reading a rank's part of a mesh file): this rank's cells + halo
+        # with locally renumbered vertices, as host arrays
+        from sucemfem import partition
+        lo, hi = partition.cell_ranges(n_cells_total, world)[rank]
+        rc = partition.RankCells(gen.cells, lo, hi)
+        h_co, h_ce = pin(gen.coords[rc.vertex_ids].cpu()), pin(rc.cells_local.cpu())
+        h_eps, h_mu = pin(eps_d[rc.cell_ids].cpu()), pin(mu_d[rc.cell_ids].cpu())
+    del gen, eps_d, mu_d
+    _free_device()
     out, out2 = {}, {}
     times, t_create = [], []
     n_warm = 3      # untimed: the first one page-locks the output arrays, the next two let the host settle
     for it in range(steps + n_warm):
         torch.cuda.synchronize()
+        if world > 1:
+            torch.distributed.barrier()
         t0 = time.perf_counter()
-        job = device.HostAssemblyJob(h_co, h_ce, 2, h_eps, h_mu, pec='exterior')
-        t1 = time.perf_counter()
         if world == 1:
+            job = device.HostAssemblyJob(h_co, h_ce, 2, h_eps, h_mu, pec='exterior')
+            t1 = time.perf_counter()
             out = job.run(want=('cols', 'S', 'T'), out=out)
         else:
-            eb, ob = job.partition_by_class(world)
-            out = job.run_rows(eb[rank], eb[rank + 1], want=('cols', 'S', 'T'), out=out, order=2)
-            out2 = job.run_rows(ob[rank], ob[rank + 1], want=('cols', 'S', 'T'), out=out2, order=2)
+            job = partition.RankHostJob(rc, h_co, h_ce, 2, h_eps, h_mu, pec='exterior')
+            t1 = time.perf_counter()
+            out, out2 = job.run(want=('cols', 'S', 'T'), out_edges=out, out_faces=out2)
         job.close()
         torch.cuda.synchronize()
         if it >= n_warm:
@@ -735,15 +750,17 @@ def e2e_run(n, steps, rank=0, world=1):
             t_create.append(t1 - t0)
     dt = sorted(times)[len(times) // 2]      # median step
     h2d = sum(x.numel() * x.element_size() for x in (h_co, h_ce, h_eps, h_mu))
-    d2h = sum(x.numel() * x.element_size() for x in list(out.values()) + list(out2.values()))
+    d2h = sum(x.numel() * x.element_size() for x in list(out.values()) + list((out2 or {}).values()))
     # the copy shares the host's PCIe / memory system with the box's other tenants: single steps vary by 2x, so the
     # reported step is the median of up to 9 (all of them are listed, the fastest one separately)
-    return {"value": len(ce) / dt, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+    return {"value": n_cells_total / dt, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
             "ms_per_step": dt * 1e3, "steps_ms": [round(t * 1e3, 1) for t in times], "best_ms": round(min(times) * 1e3, 1),
             "create_ms": [round(t * 1e3, 1) for t in t_create],
             "includes": "H2D mesh+materials, numbering, PEC flags, pattern, S+T values, CSR expansion, D2H of rowptr/cols/S/T "
                         "(streamed in row blocks: D2H of block k overlaps assembly of block k+1)"
-                        + ("; every rank builds the numbering of the whole mesh and streams its own rows" if world > 1 else "")}
+                        + ("; partitioned mesh: every rank gets its own cells + halo as host arrays, numbers them, exchanges the "
+                           "global numbering over NCCL and streams the rows it owns" if world > 1 else ""),
+            "d2h_GBps_this_rank": d2h / dt / 1e9}
 
 
 if __name__ == '__main__':

@@ -247,3 +247,42 @@ class RankSpace(object):
         if isinstance(per_cell_global, torch.Tensor):
             return per_cell_global[ids.to(per_cell_global.device)]
         return per_cell_global[ids.cpu().numpy()]
+
+
+class RankHostJob(object):
+    """The host-buffer call (device.HostAssemblyJob = sfem_host_job_*) for ONE RANK of a partitioned mesh: the rank's cells +
+    halo come in as HOST arrays (local vertex numbering, from RankCells), the global numbering is exchanged over the process
+    group, and the rows the rank owns go out to its page-locked host arrays with GLOBAL column ids.  What the ranks write,
+    concatenated (edge rows in rank order, then face rows), is the CSR of the whole mesh."""
+
+    def __init__(self, rc, coords_local, cells_local, order, eps_local=None, mu_local=None, pec='exterior', group=None):
+        import ctypes as C
+        from . import device, _native as N
+        self.job = device.HostAssemblyJob(coords_local, cells_local, order, eps_local, mu_local, pec=pec)
+        sp = C.c_void_p()
+        N.check(N.lib.sfem_host_job_space(self.job.handle, C.byref(sp)))
+        n_cells = int(cells_local.shape[0])
+        ce = torch.empty((n_cells, 6), dtype=torch.int32, device='cuda')
+        cf = torch.empty((n_cells, 4), dtype=torch.int32, device='cuda') if order == 2 else None
+        N.check(N.lib.sfem_space_cell_entities(sp, ce.data_ptr(), cf.data_ptr() if cf is not None else None, None))
+        nd, ne, nf, ndc = C.c_int64(), C.c_int64(), C.c_int64(), C.c_int()
+        N.check(N.lib.sfem_space_info(sp, C.byref(nd), C.byref(ne), C.byref(nf), C.byref(ndc)))
+        self.n_edges_local, self.order = ne.value, order
+        torch.cuda.synchronize()
+        self.numbering = rn = number_distributed(RankNumbering(rc, ce, cf, order), group)
+        eg = rn.e_gid.to(torch.int32).contiguous()
+        fg = rn.f_gid.to(torch.int32).contiguous() if cf is not None else None
+        N.check(N.lib.sfem_space_set_global_ids(sp, eg.data_ptr(), fg.data_ptr() if fg is not None else None, rn.E_global,
+                                                rn.F_global, rn.e_lo, rn.e_off, rn.f_lo, rn.f_off, None))
+        torch.cuda.synchronize()
+
+    def run(self, want=('cols', 'S', 'T'), out_edges=None, out_faces=None):
+        rn, E = self.numbering, self.n_edges_local
+        oe = self.job.run_rows(rn.e_lo, rn.e_hi, want=want, out=out_edges, order=self.order)
+        of = None
+        if self.order == 2:
+            of = self.job.run_rows(E + rn.f_lo, E + rn.f_hi, want=want, out=out_faces, order=self.order)
+        return oe, of
+
+    def close(self):
+        self.job.close()

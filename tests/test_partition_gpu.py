@@ -75,3 +75,32 @@ def test_halo_is_thin_and_generic_kernel_agrees():
             b = bp.assemble_ST(kernel=N.KERNEL_GENERIC)
             for x, y in zip(a, b):
                 assert float((x - y).abs().max()) <= 1e-12 * float(y.abs().max())
+
+
+def test_rank_host_job_single_rank_group():
+    """partition.RankHostJob through torch.distributed (NCCL, a group of one): the whole mesh as the only rank's share must
+    give what the plain host job gives, bit for bit (plumbing of the host-buffer path of the partitioned mesh)."""
+    import os
+    import torch
+    import torch.distributed as dist
+    from sucemfem import device as dev, partition as P
+    co, ce = meshes.unit_cube(5, 4, 3)
+    rng = np.random.default_rng(2)
+    eps, mu = rng.uniform(1, 16, len(ce)), rng.uniform(1, 2, len(ce))
+    ref = dev.assemble_host(co, ce, 2, eps, mu, pec='exterior')
+    os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+    os.environ.setdefault('MASTER_PORT', str(29700 + os.getpid() % 200))
+    dist.init_process_group('nccl', rank=0, world_size=1)
+    try:
+        rc = P.RankCells(ce, 0, len(ce))
+        assert len(rc.cell_ids) == len(ce) and rc.own_lo == 0
+        job = P.RankHostJob(rc, co, ce, 2, eps, mu, pec='exterior')
+        oe, of = job.run()
+        job.close()
+    finally:
+        dist.destroy_process_group()
+    ne = oe['S'].numel()
+    for k in ('cols', 'S', 'T'):
+        assert torch.equal(torch.cat([oe[k], of[k]]), ref[k]), k
+    assert torch.equal(oe['rowptr'], ref['rowptr'][:oe['rowptr'].numel()])
+    assert torch.equal(of['rowptr'] + ne, ref['rowptr'][oe['rowptr'].numel() - 1:])
