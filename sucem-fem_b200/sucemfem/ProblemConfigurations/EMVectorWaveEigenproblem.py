@@ -67,13 +67,15 @@ class DeviceEigenSolver(DefaultEigenSolver):
     The reference factorises S - sigma M with a sparse LU on the host and hands the solve to ARPACK
     (/root/reference/sucemfem/ProblemConfigurations/EMVectorWaveEigenproblem.py:76-103).  Here the shift-invert operator
     (S - sigma M)^-1 M is applied with a Jacobi-preconditioned MINRES whose matrix-vector products are sfem_matvec on the
-    CSR value arrays (S - sigma M is never formed), inside a Lanczos iteration in the M inner product with full
+    CSR value arrays (S - sigma M is never formed; one iteration of the recurrence is a CUDA graph, the residual estimate
+    is read back every 25 iterations), inside a Lanczos iteration in the M inner product with full
     reorthogonalisation (sucemfem/Utilities/DeviceKrylov.py).  Dirichlet (PEC) dofs: the matrices carry row-only unit
     rows, so on vectors whose constrained entries are zero they act as the reduced pencil S_ff, M_ff.
     solve_problem() returns what DefaultEigenSolver returns: k^2 itself and the modes as rows; `self.residuals` holds
     ||S x - k^2 M x|| / ||k^2 M x|| of every returned pair, `self.info` the iteration counts."""
 
-    def solve_problem(self, nev, ncv=None, tol=1e-11, inner_rtol=1e-13, inner_maxiter=50000, seed=0, return_device=False):
+    def solve_problem(self, nev, ncv=None, tol=1e-11, inner_rtol=1e-13, inner_maxiter=50000, seed=0, return_device=False,
+                      use_cuda_graph=True):
         import torch
         from ..Utilities import DeviceKrylov as K
         ep = self.eigenproblem
@@ -90,9 +92,11 @@ class DeviceEigenSolver(DefaultEigenSolver):
         d = pat.diagonal([S.values, M.values], [1.0, -sigma]).real
         inv_diag = free / d.abs().clamp_min(1e-300)
         inner = {"solves": 0, "iterations": 0, "worst_residual": 0.0}
+        # the MINRES recurrence is launch-bound: one iteration is captured in a CUDA graph and replayed
+        graph = K.GraphMinres(Amul, inv_diag, n, dev) if use_cuda_graph else None
 
         def solve(w):
-            x, its, res = K.solve_symmetric(Amul, w, inv_diag, inner_rtol, inner_maxiter)
+            x, its, res = K.solve_symmetric(Amul, w, inv_diag, inner_rtol, inner_maxiter, graph=graph)
             inner["solves"] += 1
             inner["iterations"] += its
             inner["worst_residual"] = max(inner["worst_residual"], res)

@@ -61,18 +61,97 @@ def minres(A, b, inv_diag=None, rtol=1e-12, maxiter=20000, x0=None):
     return x, itn, phibar / beta1
 
 
-def solve_symmetric(A, b, inv_diag=None, rtol=1e-12, maxiter=20000, refinements=3):
-    """MINRES with iterative refinement on the TRUE residual: returns (x, total iterations, ||b - A x|| / ||b||)."""
+class GraphMinres(object):
+    """The same recurrence with every scalar kept on the device and ONE iteration captured in a CUDA graph: the loop is
+    launch-bound (a matrix-vector product and a dozen vector kernels per iteration, two scalar read-backs in the eager
+    version), so replaying the graph and reading the residual estimate back only every `check_every` iterations removes
+    the host from the loop.  A: callable on device tensors that only launches kernels on the current stream (sfem_matvec
+    + torch ops); n: vector length.  One instance per (A, inv_diag): buffers and the graph are reused across solves."""
+
+    def __init__(self, A, inv_diag, n, device, check_every=25):
+        self.A, self.inv_diag, self.n, self.check_every = A, inv_diag, n, check_every
+        z = lambda: torch.zeros(n, dtype=torch.float64, device=device)
+        self.x, self.y, self.r1, self.r2, self.v, self.w, self.w1, self.w2 = z(), z(), z(), z(), z(), z(), z(), z()
+        # scalars: beta, oldb, dbar, epsln, phibar, cs, sn
+        self.sc = torch.zeros(7, dtype=torch.float64, device=device)
+        self.graph = None
+
+    def _step(self):
+        beta, oldb, dbar, epsln, phibar, cs, sn = (self.sc[i] for i in range(7))
+        self.v.copy_(self.y / beta)
+        t = self.A(self.v)
+        t = t - (beta / oldb) * self.r1                    # r1 = 0 in the first iteration
+        alfa = torch.dot(self.v, t)
+        t = t - (alfa / beta) * self.r2
+        self.r1.copy_(self.r2)
+        self.r2.copy_(t)
+        self.y.copy_(self.r2 * self.inv_diag)
+        nb = torch.sqrt(torch.dot(self.r2, self.y).clamp_min(0.0))
+        oldeps = epsln.clone()
+        delta = cs * dbar + sn * alfa
+        gbar = sn * dbar - cs * alfa
+        n_eps = sn * nb
+        n_dbar = -cs * nb
+        gamma = torch.sqrt(gbar * gbar + nb * nb).clamp_min(1e-300)
+        n_cs, n_sn = gbar / gamma, nb / gamma
+        phi = n_cs * phibar
+        n_phibar = n_sn * phibar
+        self.w1.copy_(self.w2)
+        self.w2.copy_(self.w)
+        self.w.copy_((self.v - oldeps * self.w1 - delta * self.w2) / gamma)
+        self.x.add_(phi * self.w)
+        self.sc.copy_(torch.stack([nb, beta.clone(), n_dbar, n_eps, n_phibar, n_cs, n_sn]))
+
+    def solve(self, b, rtol=1e-12, maxiter=20000):
+        for t in (self.x, self.r1, self.w, self.w1, self.w2):
+            t.zero_()
+        self.r2.copy_(b)
+        self.y.copy_(b * self.inv_diag)
+        beta1 = float(torch.sqrt(torch.dot(self.r2, self.y)))
+        if beta1 == 0.0:
+            return self.x.clone(), 0, 0.0
+        self.sc.copy_(torch.tensor([beta1, 1.0, 0.0, 0.0, beta1, -1.0, 0.0], dtype=torch.float64))
+        if self.graph is None:
+            state = [t.clone() for t in (self.x, self.y, self.r1, self.r2, self.v, self.w, self.w1, self.w2, self.sc)]
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):               # warm-up outside the capture
+                self._step()
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph):
+                self._step()
+            for t, s0 in zip((self.x, self.y, self.r1, self.r2, self.v, self.w, self.w1, self.w2, self.sc), state):
+                t.copy_(s0)
+        itn = 0
+        while itn < maxiter:
+            for _ in range(self.check_every):
+                self.graph.replay()
+            itn += self.check_every
+            phibar, beta = float(self.sc[4]), float(self.sc[0])
+            if not math.isfinite(phibar):
+                raise ArithmeticError('MINRES: breakdown')
+            if phibar <= rtol * beta1 or beta == 0.0:
+                break
+        return self.x.clone(), itn, float(self.sc[4]) / beta1
+
+
+def solve_symmetric(A, b, inv_diag=None, rtol=1e-12, maxiter=20000, refinements=3, graph=None):
+    """MINRES with iterative refinement on the TRUE residual: returns (x, total iterations, ||b - A x|| / ||b||).
+    graph: a GraphMinres for (A, inv_diag) -- the CUDA-graph version of the same recurrence (device tensors only)."""
     bn = float(torch.linalg.vector_norm(b))
     if bn == 0.0:
         return torch.zeros_like(b), 0, 0.0
-    x, its, _ = minres(A, b, inv_diag, rtol, maxiter)
+    run = (lambda rhs, tol: graph.solve(rhs, tol, maxiter)) if graph is not None else \
+          (lambda rhs, tol: minres(A, rhs, inv_diag, tol, maxiter))
+    x, its, _ = run(b, rtol)
     res = float(torch.linalg.vector_norm(b - A(x))) / bn
     for _ in range(refinements):
         if res <= rtol:
             break
         r = b - A(x)
-        dx, it2, _ = minres(A, r, inv_diag, max(rtol / max(res, 1e-300), 1e-6) * 0.1, maxiter)
+        dx, it2, _ = run(r, max(rtol / max(res, 1e-300), 1e-6) * 0.1)
         x = x + dx
         its += it2
         res = float(torch.linalg.vector_norm(b - A(x))) / bn
