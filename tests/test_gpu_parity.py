@@ -354,6 +354,36 @@ def test_every_value_slot_is_written(dev, order):
                 assert torch.equal(S, S0) and torch.equal(T, T0)
 
 
+def test_lane_pair_edge_kernel_agrees_with_lane_per_item(dev, monkeypatch):
+    """The round-1 edge kernel (a lane PAIR per edge, loop over the ring) is the fallback layout when the batch builder
+    gives up; SFEM_EDGE_KERNEL=1 selects it at pattern creation.  Same rows, another summation order for the row edge's own
+    block: equal to 1e-12, both against the oracle, PEC included."""
+    import torch
+    from sucemfem import _native as N
+    co, ce = meshes.unit_cube(5, 4, 6)
+    rng = np.random.default_rng(4)
+    co = co + 0.02 * rng.standard_normal(co.shape)
+    eps, mu = rng.uniform(1, 16, len(ce)), rng.uniform(1, 2, len(ce))
+    num = fem.number_entities(ce)
+    ref = fem.assemble_system(co, ce, 2, eps_r=eps, mu_r=mu, pec_facet_mask=fem.exterior_facet_mask(ce, num))
+    base = fem.assemble_system(co, ce, 2, eps_r=eps, mu_r=mu)
+    sp = dev.DeviceSpace(dev.DeviceMesh(co, ce), 2)
+    markers = torch.zeros(sp.n_facets, dtype=torch.int32, device='cuda')
+    sp.mark_exterior_facets(markers, 999)
+    flags = sp.pec_row_flags(markers, 999)
+    d_eps, d_mu = torch.from_numpy(eps).cuda(), torch.from_numpy(mu).cuda()
+    out = {}
+    for version in ('2', '1'):
+        monkeypatch.setenv('SFEM_EDGE_KERNEL', version)
+        pat = dev.DevicePattern(sp, 0, -1)
+        assert N.lib.sfem_launches_per_assemble_ST(pat.handle, N.KERNEL_CANONICAL) == (3 if version == '2' else 2)
+        out[version] = pat.assemble_ST(d_eps, d_mu, flags, kernel=N.KERNEL_CANONICAL)
+        for got, want, scale in zip(out[version], (ref['S'], ref['M']), (base['S'], base['M'])):
+            assert close(got.cpu().numpy(), want, scale)
+    for a, b in zip(out['1'], out['2']):
+        assert bool(((a - b).abs() <= 1e-12 * b.abs() + 1e-15 * b.abs().max()).all())
+
+
 def test_canonical_midsize_vs_c_oracle(dev):
     """UnitCube(12) order 2 (10 368 tets, 3.0 M non-zeros) against the C restatement of the reference algorithm."""
     import torch
