@@ -66,6 +66,9 @@ SFEM_API const char* sfem_version(void);
  * cached when handles are destroyed (repeated set-ups reuse them).  This returns the cached memory to the driver
  * (synchronises the device).  Buffers of a handle are freed in the order of the stream the handle was created on. */
 SFEM_API int sfem_release_cached_memory(void);
+/* Grows the pool by `bytes` in ONE piece ahead of a large set-up (one driver mapping instead of the thousands the set-up's
+ * own allocations would trigger one by one: the patterns of UnitCube(203), 65 GB, take 13 s to allocate piecemeal). */
+SFEM_API int sfem_reserve_cached_memory(int64_t bytes, void* stream);
 /* Bytes the pool currently holds from the driver / bytes handed out to live buffers (diagnostics). */
 SFEM_API int sfem_cached_memory_info(int64_t* reserved_bytes, int64_t* used_bytes);
 

@@ -263,6 +263,17 @@ int sfem_release_cached_memory(void) {
   return 0;
 }
 
+int sfem_reserve_cached_memory(int64_t bytes, void* stream) {
+  SFEM_CHECK(bytes >= 0, "negative size");
+  if (bytes == 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  void* p = nullptr;
+  SFEM_CUDA(dev_malloc_bytes(&p, (size_t)bytes, st));   // grows the pool in one piece ...
+  dev_free(p, st);                                      // ... which stays cached (release threshold: never)
+  SFEM_CUDA(cudaStreamSynchronize(st));
+  return 0;
+}
+
 int sfem_cached_memory_info(int64_t* reserved_bytes, int64_t* used_bytes) {
   int dev = 0;
   SFEM_CUDA(cudaGetDevice(&dev));

@@ -28,6 +28,7 @@ def _load():
         'sfem_last_error': (C.c_char_p, []),
         'sfem_version': (C.c_char_p, []),
         'sfem_release_cached_memory': (i32, []),
+        'sfem_reserve_cached_memory': (i32, [C.c_int64, vp]),
         'sfem_cached_memory_info': (i32, [C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
         'sfem_mesh_create': (i32, [i32, i64, vp, i64, vp, vp, P(vp)]),
         'sfem_mesh_destroy': (i32, [vp]),
