@@ -216,6 +216,8 @@ int sfem_space_assemble_rows_to_host(sfem_space_t sp, int64_t ent_lo, int64_t en
   if (ent_hi < 0) ent_hi = sp->n_ent;
   SFEM_CHECK(0 <= ent_lo && ent_lo <= ent_hi && ent_hi <= sp->n_ent, "entity range out of bounds");
   SFEM_CHECK(h_S || h_T || h_S0 || h_cols, "nothing to do: pass at least one output array");
+  SFEM_CHECK(!sp->gid_e || ent_hi <= sp->E || ent_lo >= sp->E,
+             "partitioned mesh: a row range holds edge rows or face rows, not both");
   DeviceGuard dg(sp->device);
   cudaStream_t st = (cudaStream_t)stream;
   SFEM_TRY(sfem_space_count_nnz(sp, stream, nullptr));
@@ -294,6 +296,7 @@ int sfem_space_assemble_rows_to_host(sfem_space_t sp, int64_t ent_lo, int64_t en
     pat.device = sp->device;
     pat.stream = st;
     pat.ent_lo = lo;
+    if (sp->gid_e) pat.gshift = lo >= sp->E ? sp->gshift_f : sp->gshift_e;  // partitioned mesh: global row ids
     pat.ent_hi = hi;
     pat.n_rows_ent = hi - lo;
     rc = build_pattern_block(&pat, sp->rowptr_all, 0, nnz_ent, inc_lo, n_inc, sp->max_len_edges_all, sp->max_len_other_all, st);

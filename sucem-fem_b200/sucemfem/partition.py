@@ -172,6 +172,9 @@ def _all_gather_var(t, group=None):
     """Variable-length all-gather of a 1-D int64 tensor (concatenated in rank order)."""
     import torch.distributed as dist
     world = dist.get_world_size(group)
+    dev = t.device
+    if dist.get_backend(group) == 'gloo':       # CPU tests / single-GPU multi-process tests: gloo gathers host tensors
+        t = t.cpu()
     n = torch.tensor([t.numel()], dtype=torch.int64, device=t.device)
     sizes = [torch.zeros_like(n) for _ in range(world)]
     dist.all_gather(sizes, n, group=group)
@@ -181,7 +184,7 @@ def _all_gather_var(t, group=None):
     buf[:t.numel()] = t
     out = [torch.zeros_like(buf) for _ in range(world)]
     dist.all_gather(out, buf, group=group)
-    return torch.cat([o[:s] for o, s in zip(out, sizes)])
+    return torch.cat([o[:s] for o, s in zip(out, sizes)]).to(dev)
 
 
 def number_distributed(rn, group=None):
@@ -189,7 +192,7 @@ def number_distributed(rn, group=None):
     two integers per rank, then one variable-size all-gather of (key, id) per entity class."""
     import torch.distributed as dist
     world, rank = dist.get_world_size(group), dist.get_rank(group)
-    dev = rn.ce.device
+    dev = rn.ce.device if dist.get_backend(group) != 'gloo' else torch.device('cpu')
     c = torch.tensor(rn.counts(), dtype=torch.int64, device=dev)
     allc = [torch.zeros_like(c) for _ in range(world)]
     dist.all_gather(allc, c, group=group)

@@ -104,3 +104,56 @@ def test_rank_host_job_single_rank_group():
         assert torch.equal(torch.cat([oe[k], of[k]]), ref[k]), k
     assert torch.equal(oe['rowptr'], ref['rowptr'][:oe['rowptr'].numel()])
     assert torch.equal(of['rowptr'] + ne, ref['rowptr'][oe['rowptr'].numel() - 1:])
+
+
+def _host_job_worker(rank, world, port, ret):
+    import os
+    import sys
+    import torch
+    import torch.distributed as dist
+    from conftest import ROOT
+    sys.path.insert(0, os.path.join(ROOT, 'sucem-fem_b200'))
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)      # both ranks share cuda:0: gloo carries the exchange
+    from sucemfem import device as dev, partition as P
+    co, ce = meshes.unit_cube(6, 5, 4)
+    rng = np.random.default_rng(5)
+    eps, mu = rng.uniform(1, 16, len(ce)), rng.uniform(1, 2, len(ce))
+    ref = dev.assemble_host(co, ce, 2, eps, mu, pec='exterior', want=('cols', 'S', 'T', 'S0'))
+    lo, hi = P.cell_ranges(len(ce), world)[rank]
+    rc = P.RankCells(torch.from_numpy(ce).cuda(), lo, hi)
+    ids = rc.cell_ids.cpu().numpy()
+    job = P.RankHostJob(rc, co[rc.vertex_ids.cpu().numpy()], rc.cells_local.cpu().numpy(), 2, eps[ids], mu[ids], pec='exterior')
+    oe, of = job.run(want=('cols', 'S', 'T', 'S0'))
+    rn = job.numbering
+    job.close()
+    ok = True
+    E = rn.E_global
+    for out, row0 in ((oe, 2 * rn.e_off), (of, 2 * (E + rn.f_off))):
+        nrows = out['rowptr'].numel() - 1
+        a, b = int(ref['rowptr'][row0]), int(ref['rowptr'][row0 + nrows])
+        ok = ok and torch.equal(out['rowptr'] + a, ref['rowptr'][row0:row0 + nrows + 1])
+        for k in ('cols', 'S', 'T', 'S0'):
+            ok = ok and torch.equal(out[k], ref[k][a:b])
+    ret[rank] = int(ok)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_rank_host_jobs_two_processes_reproduce_the_serial_csr():
+    """Two PROCESSES (gloo for the numbering exchange, one GPU shared) each run partition.RankHostJob on their own cells +
+    halo: the rows they stream out -- pattern with global column ids, S, T and the full-pattern S_0, PEC unit rows included
+    -- are bit for bit the rows of the serial host job."""
+    import os
+    import torch.multiprocessing as mp
+    ctx = mp.get_context('spawn')
+    ret = ctx.Manager().dict()
+    port = 29750 + os.getpid() % 200
+    procs = [ctx.Process(target=_host_job_worker, args=(r, 2, port, ret)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(timeout=300)
+    assert all(p.exitcode == 0 for p in procs)
+    assert [ret.get(r) for r in range(2)] == [1, 1]
