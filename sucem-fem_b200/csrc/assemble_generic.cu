@@ -314,41 +314,59 @@ k_abc_rows(PatView pv, const double* __restrict__ coords, const int32_t* __restr
       out[rs0 + (int64_t)k * Q * len + idx] = (pecrow[k] && pv.ent_cols[a + s] == g + pv.gshift && kp == k) ? 1.0 : 0.0;
     }
   __syncwarp();
-  for (int64_t i = pv.inc_ptr[g]; i < pv.inc_ptr[g + 1]; ++i) {
-    const int64_t c = pv.inc_cell[i];
-    const unsigned m = cell_extmask[c];
-    if (!m) continue;
-    const int loc = pv.inc_loc[i];
-    unsigned on;  // local facets that contain the row entity (k_abc_row_flags)
-    if (DIM == 3) on = loc < 6 ? ((0xCA6953u >> (4 * loc)) & 15u) : (1u << (loc - 6));
-    else on = loc < 3 ? (1u << loc) : 0u;
-    const uint16_t* ps = pv.pos + (i - pv.inc_base) * pv.nec;
-    for (int lf = 0; lf < NFAC; ++lf) {
-      if (!(((m & on) >> lf) & 1u)) continue;
-      if (facet_mask && !facet_mask[cell_facets[c * NFAC + lf]]) continue;
-      double K[6];
-      facet_geometry<DIM>(coords, cells + c * (DIM + 1), lf, K);
-      // closure of the facet: tets -- its three edges (+ the face entity at order 2); triangles -- the edge itself
-      constexpr int NCL = DIM == 3 ? (ORDER == 2 ? 4 : 3) : 1;
-      if (lane < NCL * Q * Q) {
-        const int ci = lane / (Q * Q), k = (lane / Q) % Q, kp = lane % Q;
-        const int u = DIM == 3 ? (ci < 3 ? tet_face_edge(lf, ci) : 6 + lf) : lf;
-        // slot of local entity u of this cell in the row (the slot table of tets is in canonical column order)
-        int s = -1;
-        for (int uu = 0; uu < pv.nec; ++uu) {
-          const int ut = pv.canon ? (int)((kCanonDesc[loc] >> (8 + 4 * uu)) & 15ull) : uu;
-          if (ut == u) s = ps[uu];
-        }
-        if (s >= 0 && !pecrow[k]) {
-          const double* B = El::facet(lf, loc * Q + k, u * Q + kp);
-          double* o = out + rs0 + (int64_t)k * Q * len + (int64_t)Q * s + kp;
-          double acc = *o;
+  // the lanes look at the incident cells in PARALLEL (one dependent load chain for all of them instead of one per cell);
+  // the cells that do have an exterior facet containing the row entity are then visited in ascending order
+  const int64_t i_begin = pv.inc_ptr[g], i_end = pv.inc_ptr[g + 1];
+  for (int64_t ib = i_begin; ib < i_end; ib += 32) {
+    const int64_t il = ib + lane;
+    int64_t c_l = 0;
+    int loc_l = 0;
+    unsigned hit_l = 0u;  // exterior local facets of this lane's cell that contain the row entity
+    if (il < i_end) {
+      c_l = pv.inc_cell[il];
+      loc_l = pv.inc_loc[il];
+      const unsigned m = cell_extmask[c_l];
+      unsigned on;  // local facets that contain the row entity (k_abc_row_flags)
+      if (DIM == 3) on = loc_l < 6 ? ((0xCA6953u >> (4 * loc_l)) & 15u) : (1u << (loc_l - 6));
+      else on = loc_l < 3 ? (1u << loc_l) : 0u;
+      hit_l = m & on;
+    }
+    unsigned todo = __ballot_sync(0xffffffffu, hit_l != 0u);
+    while (todo) {
+      const int src = __ffs((int)todo) - 1;
+      todo &= todo - 1;
+      const int64_t c = __shfl_sync(0xffffffffu, c_l, src);
+      const int loc = __shfl_sync(0xffffffffu, loc_l, src);
+      const unsigned hit = __shfl_sync(0xffffffffu, hit_l, src);
+      const int64_t i = ib + src;
+      const uint16_t* ps = pv.pos + (i - pv.inc_base) * pv.nec;
+      for (int lf = 0; lf < NFAC; ++lf) {
+        if (!((hit >> lf) & 1u)) continue;
+        if (facet_mask && !facet_mask[cell_facets[c * NFAC + lf]]) continue;
+        double K[6];
+        facet_geometry<DIM>(coords, cells + c * (DIM + 1), lf, K);
+        // closure of the facet: tets -- its three edges (+ the face entity at order 2); triangles -- the edge itself
+        constexpr int NCL = DIM == 3 ? (ORDER == 2 ? 4 : 3) : 1;
+        if (lane < NCL * Q * Q) {
+          const int ci = lane / (Q * Q), k = (lane / Q) % Q, kp = lane % Q;
+          const int u = DIM == 3 ? (ci < 3 ? tet_face_edge(lf, ci) : 6 + lf) : lf;
+          // slot of local entity u of this cell in the row (the slot table of tets is in canonical column order)
+          int s = -1;
+          for (int uu = 0; uu < pv.nec; ++uu) {
+            const int ut = pv.canon ? (int)((kCanonDesc[loc] >> (8 + 4 * uu)) & 15ull) : uu;
+            if (ut == u) s = ps[uu];
+          }
+          if (s >= 0 && !pecrow[k]) {
+            const double* B = El::facet(lf, loc * Q + k, u * Q + kp);
+            double* o = out + rs0 + (int64_t)k * Q * len + (int64_t)Q * s + kp;
+            double acc = *o;
 #pragma unroll
-          for (int p = 0; p < NP; ++p) acc += K[p] * B[p];
-          *o = acc;
+            for (int p = 0; p < NP; ++p) acc += K[p] * B[p];
+            *o = acc;
+          }
         }
+        __syncwarp();  // the next facet may add to the same slot (the row entity's own block)
       }
-      __syncwarp();  // the next facet may add to the same slot (the row entity's own block)
     }
   }
 }
