@@ -3,6 +3,9 @@
 // /root/reference/sucemfem/SystemMatrices.py:54-55 for the forms of /root/reference/sucemfem/Forms.py:76,84.
 //
 // Work decomposition (row-owner gather, no atomics, bit-reproducible):
+//   * EDGES (k_canon_edges2, the default since round 2): one LANE per (edge, cell) item; a warp takes a batch of whole
+//     consecutive edges with at most 32 items (see the comment above that kernel).  The description below is the
+//     lane-PAIR layout, which the face kernel uses and which k_canon_edges keeps as the fallback for edges:
 //   * a PAIR of lanes owns one row entity (edge or face) = 2 CSR rows of S and 2 of T, and splits the entity's
 //     incident cells between its two lanes; a warp owns 16 consecutive entities, i.e. one contiguous span of the
 //     value arrays.  Warps are persistent over batches of 16 entities.
@@ -579,7 +582,11 @@ __device__ __forceinline__ void cp_async16(void* sdst, const void* gsrc) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(sdst)), "l"(gsrc) : "memory");
 }
 __device__ __forceinline__ void cp_async16_ca(void* sdst, const void* gsrc) {
+#ifdef SFEM_E2_COORDS_CG
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(sdst)), "l"(gsrc) : "memory");
+#else
   asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(sdst)), "l"(gsrc) : "memory");
+#endif
 }
 __device__ __forceinline__ void cp_async8_ca(void* sdst, const void* gsrc) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(sdst)), "l"(gsrc) : "memory");
@@ -594,12 +601,26 @@ __device__ __forceinline__ double2 shfl_down2(double2 v, int d) {
   return make_double2(__shfl_down_sync(0xffffffffu, v.x, d), __shfl_down_sync(0xffffffffu, v.y, d));
 }
 
-// records + aux words of batch b -> one ping-pong half of the warp's record stage (coalesced: 4 wavefronts per copy)
+// records + aux words of batch b -> one ping-pong half of the warp's record stage (coalesced: 4 wavefronts per copy).
+// They are read exactly once per step: L2 evict-first keeps the L2 for the gathered vertices and coefficients.
+__device__ __forceinline__ void cp_async16_stream(void* sdst, const void* gsrc, unsigned long long policy) {
+  asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"((unsigned)__cvta_generic_to_shared(sdst)),
+               "l"(gsrc), "l"(policy)
+               : "memory");
+}
 __device__ __forceinline__ void e2_issue_records(const Edge2Args& p, uint4* recst, int64_t b, int lane) {
   const uint4* r = p.rec + (b * 32 + lane) * 2;
+#ifdef SFEM_E2_NO_STREAM_HINT
   cp_async16(recst + lane, r);
   cp_async16(recst + 32 + lane, r + 1);
   cp_async16(recst + 64 + lane, p.aux + b * 32 + lane);
+#else
+  unsigned long long policy;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
+  cp_async16_stream(recst + lane, r, policy);
+  cp_async16_stream(recst + 32 + lane, r + 1, policy);
+  cp_async16_stream(recst + 64 + lane, p.aux + b * 32 + lane, policy);
+#endif
 }
 // Vertex data of the item whose record sits in `recst` -> the coordinate stage (cp.async).  A relabelled cell is
 // (a, b, entry, exit) with (a, b) the row edge, and consecutive cells of a ring share a face: the exit vertex of one is
