@@ -578,18 +578,17 @@ constexpr int kE2StageCoords = SFEM_E2_COORDS_SMEM ? 9 * 32 : 0;  // uint4 units
 constexpr int kE2StageRec = 3 * 32;                    // uint4 units per ping-pong half
 constexpr int kE2WarpSmem = (SFEM_E2_TILES * kE2TileChunks + kE2StageCoords + 2 * kE2StageRec) * 16;
 
+#ifdef SFEM_E2_NO_STREAM_HINT
 __device__ __forceinline__ void cp_async16(void* sdst, const void* gsrc) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(sdst)), "l"(gsrc) : "memory");
 }
+#endif
 __device__ __forceinline__ void cp_async16_ca(void* sdst, const void* gsrc) {
 #ifdef SFEM_E2_COORDS_CG
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(sdst)), "l"(gsrc) : "memory");
 #else
   asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(sdst)), "l"(gsrc) : "memory");
 #endif
-}
-__device__ __forceinline__ void cp_async8_ca(void* sdst, const void* gsrc) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(sdst)), "l"(gsrc) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
@@ -677,6 +676,7 @@ __device__ __forceinline__ void e2_read_coords(const uint4* cst, Item& it, int l
   it.cmu = c.x; it.ceps = c.y;
 }
 // ... or -> registers (consumed one batch later)
+#if !SFEM_E2_COORDS_SMEM
 __device__ __forceinline__ void e2_gather_coords(const Edge2Args& p, const uint4* recst, Item& it, int lane) {
   const uint4 ra = recst[lane];
   const int cell = (int)recst[32 + lane].x;
@@ -693,6 +693,7 @@ __device__ __forceinline__ void e2_gather_coords(const Edge2Args& p, const uint4
     it.ceps = p.eps[cell];
   }
 }
+#endif
 
 template <bool MASS>
 __device__ __forceinline__ void edge2_pass(double2* __restrict__ tile, int lane, bool active, const Slots& sl,

@@ -28,31 +28,33 @@ int edge_kernel_version() {
 }
 
 constexpr int kWarpsPerBlock = 4;
-constexpr int kCap = 1024;  // candidates per row entity (valence * entities per cell)
+constexpr int kCap = 1024;      // candidates per row entity (valence * entities per cell) in the normal launch
+constexpr int kCapBig = 24576;  // ... in the one-warp-per-block launch a mesh with a longer row falls back to (192 KB)
 
-template <bool FILL>
-__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+// WPB warps per block, each with two int32 arrays of `cap` candidates in dynamic shared memory
+template <bool FILL, int WPB>
+__global__ void __launch_bounds__(WPB * 32)
 k_pattern(SpaceView sv, const int32_t* __restrict__ cells, const int64_t* __restrict__ inc_ptr,
           const int32_t* __restrict__ inc_cell,
           const uint8_t* __restrict__ inc_loc, bool canon, int64_t ent_lo, int64_t n_rows, int64_t inc_base,
           int32_t* __restrict__ row_len,
           const int64_t* __restrict__ ent_rowptr, int32_t* __restrict__ ent_cols, uint16_t* __restrict__ pos,
-          uint8_t* __restrict__ rec, int* __restrict__ overflow) {
-  __shared__ int32_t s_cand[kWarpsPerBlock][kCap];
-  __shared__ int32_t s_sorted[kWarpsPerBlock][kCap];
+          uint8_t* __restrict__ rec, int* __restrict__ overflow, int cap) {
+  extern __shared__ int32_t s_pat[];
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int64_t r = blockIdx.x * (int64_t)kWarpsPerBlock + w;
+  const int64_t r = blockIdx.x * (int64_t)WPB + w;
   if (r >= n_rows) return;
   const int64_t g = ent_lo + r;
   const int64_t i0 = inc_ptr[g], i1 = inc_ptr[g + 1];
   const int nec = sv.n_ent_cell;
-  const int L = (int)(i1 - i0) * nec;
-  if (L > kCap) {
+  const int64_t L64 = (i1 - i0) * nec;
+  if (L64 > cap) {
     if (lane == 0) *overflow = 1;
     return;
   }
-  int32_t* cand = s_cand[w];
-  int32_t* sorted = s_sorted[w];
+  const int L = (int)L64;
+  int32_t* cand = s_pat + (size_t)w * 2 * cap;
+  int32_t* sorted = cand + cap;
   for (int idx = lane; idx < L; idx += 32) {
     int i = idx / nec, u = idx - i * nec;
     cand[idx] = sv.ent(inc_cell[i0 + i], u);
@@ -331,6 +333,29 @@ __global__ void k_rebase(const int64_t* __restrict__ src, int64_t* __restrict__ 
 
 }  // namespace
 
+// Launch of k_pattern: the normal configuration, or -- once a row of this space has overflowed it -- one warp per block
+// with the large candidate arrays (slow for the long rows: the rank sort is quadratic; a mesh with an edge in more than
+// 102 cells is the only way to get there).
+template <bool FILL>
+static int launch_pattern(const sfem_space_s* sp, SpaceView sv, bool canon, int64_t ent_lo, int64_t n, int64_t inc_base,
+                          int32_t* row_len, const int64_t* ent_rowptr, int32_t* ent_cols, uint16_t* pos, uint8_t* rec,
+                          int* overflow, cudaStream_t st) {
+  if (n <= 0) return 0;
+  if (!sp->pattern_big) {
+    const unsigned grid = (unsigned)((n + kWarpsPerBlock - 1) / kWarpsPerBlock);
+    k_pattern<FILL, kWarpsPerBlock><<<grid, kWarpsPerBlock * 32, (size_t)kWarpsPerBlock * 2 * kCap * 4, st>>>(
+        sv, sp->mesh->cells, sp->inc_ptr, sp->inc_cell, sp->inc_loc, canon, ent_lo, n, inc_base, row_len, ent_rowptr,
+        ent_cols, pos, rec, overflow, kCap);
+  } else {
+    SFEM_CUDA(cudaFuncSetAttribute(k_pattern<FILL, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * kCapBig * 4));
+    k_pattern<FILL, 1><<<(unsigned)n, 32, (size_t)2 * kCapBig * 4, st>>>(
+        sv, sp->mesh->cells, sp->inc_ptr, sp->inc_cell, sp->inc_loc, canon, ent_lo, n, inc_base, row_len, ent_rowptr,
+        ent_cols, pos, rec, overflow, kCapBig);
+  }
+  SFEM_CUDA(cudaGetLastError());
+  return 0;
+}
+
 // Count pass over the row entities [ent_lo, ent_hi): allocates *rowptr_out [n+1] (exclusive scan of the row lengths,
 // offsets relative to ent_lo) and returns the longest edge row / other row.  Synchronises `st`.
 int count_pattern_rows(const sfem_space_s* sp, int64_t ent_lo, int64_t ent_hi, cudaStream_t st, int64_t** rowptr_out,
@@ -347,10 +372,7 @@ int count_pattern_rows(const sfem_space_s* sp, int64_t ent_lo, int64_t ent_hi, c
   SFEM_CUDA(dev_malloc(&overflow, 4, st));
   SFEM_CUDA(cudaMemsetAsync(overflow, 0, 4, st));
   SFEM_CUDA(dev_malloc(&rowptr, (n + 1) * 8, st));
-  const unsigned grid = (unsigned)((n + kWarpsPerBlock - 1) / kWarpsPerBlock);
-  if (n > 0)
-    k_pattern<false><<<grid, kWarpsPerBlock * 32, 0, st>>>(sv, sp->mesh->cells, sp->inc_ptr, sp->inc_cell, sp->inc_loc, canon, ent_lo, n,
-                                                           0, row_len, nullptr, nullptr, nullptr, nullptr, overflow);
+  SFEM_TRY(launch_pattern<false>(sp, sv, canon, ent_lo, n, 0, row_len, nullptr, nullptr, nullptr, nullptr, overflow, st));
   k_len_to_i64<<<grid_for(n + 1), 256, 0, st>>>(row_len, len64, n);
   size_t tb = 0;
   SFEM_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tb, len64, rowptr, (int)(n + 1), st));
@@ -376,7 +398,11 @@ int count_pattern_rows(const sfem_space_s* sp, int64_t ent_lo, int64_t ent_hi, c
   dev_free(overflow, st);
   if (h_over) {
     dev_free(rowptr, st);
-    set_error("an entity has more incident cells than the pattern builder supports (valence*entities > 1024)");
+    if (!sp->pattern_big) {  // a row with more than 1024 candidates: redo the count with the large-row launch
+      const_cast<sfem_space_s*>(sp)->pattern_big = true;
+      return count_pattern_rows(sp, ent_lo, ent_hi, st, rowptr_out, nnz_ent, max_len_edges, max_len_other);
+    }
+    set_error("an entity has more incident cells than the pattern builder supports (valence * entities per cell > 24576)");
     return 3;
   }
   *rowptr_out = rowptr;
@@ -391,7 +417,6 @@ static int fill_pattern_impl(sfem_pattern_s* pat, cudaStream_t st, bool allow_e2
   const int64_t n = pat->n_rows_ent;
   SpaceView sv = make_view(sp);
   const bool canon = pos_is_canonical(sp);
-  const unsigned grid = (unsigned)((n + kWarpsPerBlock - 1) / kWarpsPerBlock);
   const int64_t n_edge_rows = std::max<int64_t>(0, std::min(pat->ent_hi, sp->E) - pat->ent_lo);
   // incidences of the block's edge rows: inc_ptr[E] = (cells) x (edges per cell), no read-back needed
   const int64_t inc_at_E = sp->mesh->C * sp->ne_loc;
@@ -417,10 +442,9 @@ static int fill_pattern_impl(sfem_pattern_s* pat, cudaStream_t st, bool allow_e2
     SFEM_CUDA(dev_malloc(&pat->rec_alloc, std::max<int64_t>(pat->n_inc_block - skip, 1) * 32, st));
     pat->rec = pat->rec_alloc - 2 * skip;
   }
-  if (n > 0)
-    k_pattern<true><<<grid, kWarpsPerBlock * 32, 0, st>>>(sv, sp->mesh->cells, sp->inc_ptr, sp->inc_cell, sp->inc_loc, canon, pat->ent_lo, n,
-                                                          pat->inc_base, nullptr, pat->ent_rowptr, pat->ent_cols,
-                                                          pat->pos, reinterpret_cast<uint8_t*>(pat->rec), overflow);
+  // (a row that overflows here has overflowed the count pass before: sp->pattern_big is already set)
+  SFEM_TRY(launch_pattern<true>(sp, sv, canon, pat->ent_lo, n, pat->inc_base, nullptr, pat->ent_rowptr, pat->ent_cols, pat->pos,
+                                reinterpret_cast<uint8_t*>(pat->rec), overflow, st));
   pat->ring_ok = false;
   int64_t* e2_slot0 = nullptr;
   uint32_t* e2_tileoff = nullptr;

@@ -120,6 +120,7 @@ struct sfem_space_s {
   uint8_t* facet_first_loc = nullptr; // [n_facets]
   uint8_t* cell_extmask = nullptr;    // [C] bit lf set <=> local facet lf is exterior
   double* coords4 = nullptr;          // [V][4] 32-byte padded copy of the coordinates (3-D; vector gathers)
+  bool pattern_big = false;           // a row has more than 1024 candidates: the pattern kernels use their large-row launch
   double* ones = nullptr;             // [C] 1.0, the default eps_r / mu_r (allocated on first use)
   double2* coef2 = nullptr;           // [C] (mu_r, eps_r) packed by every sfem_assemble_ST call (lane-per-item edge kernel)
   // count pass over ALL rows (lazily, sfem_space_count_nnz): entity-level row pointer, longest rows

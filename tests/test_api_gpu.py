@@ -270,6 +270,28 @@ def test_high_valence_edge_falls_back_to_generic_kernel():
     assert np.all(np.abs(T.cpu().numpy() - ref['M']) <= 1e-12 * np.abs(ref['M']) + 1e-15 * np.abs(ref['M']).max())
 
 
+def test_very_high_valence_edge_uses_the_large_row_pattern_launch():
+    """An edge shared by 150 cells: 1500 candidate column entities for its row, more than the pattern kernel's normal
+    launch holds in shared memory (1024).  The space switches to the one-warp-per-block launch with large arrays; pattern
+    bit-exact, values by the per-entity fallback (hub edge -> generic kernel), orders 2 and 1."""
+    import torch
+    from oracle import fem
+    from sucemfem import device, _native as N
+    m = 150
+    ang = 2 * np.pi * np.arange(m) / m
+    co = np.concatenate([[[0, 0, -1.0], [0, 0, 1.0]], np.stack([np.cos(ang), np.sin(ang), 0 * ang], 1)])
+    ce = np.sort(np.array([[0, 1, 2 + i, 2 + (i + 1) % m] for i in range(m)]), axis=1)
+    for order in (2, 1):
+        ref = fem.assemble_system(co, ce, order)
+        sp = device.DeviceSpace(device.DeviceMesh(co, ce), order)
+        pat = sp.pattern()
+        rp, cl = pat.csr()
+        assert np.array_equal(rp.cpu().numpy(), ref['rowptr']) and np.array_equal(cl.cpu().numpy(), ref['cols'])
+        S, T = pat.assemble_ST(kernel=N.KERNEL_AUTO)
+        assert np.all(np.abs(S.cpu().numpy() - ref['S']) <= 1e-12 * np.abs(ref['S']) + 1e-15 * np.abs(ref['S']).max())
+        assert np.all(np.abs(T.cpu().numpy() - ref['M']) <= 1e-12 * np.abs(ref['M']) + 1e-15 * np.abs(ref['M']).max())
+
+
 def _driven_problem(mesh, order, sources, freq):
     from sucemfem import dolfin_compat as dolfin
     from sucemfem.BoundaryConditions import ABCBoundaryCondition, BoundaryConditions
