@@ -390,6 +390,9 @@ __device__ __forceinline__ void tri_entity_rows(const PatView& pv, const double*
                                                 int64_t g, int64_t rs, int len, double* __restrict__ dS,
                                                 double* __restrict__ dT) {
   constexpr int Q = ORDER, NEC = ORDER == 1 ? 3 : 4, ND = Q * NEC;
+  // the tensors are stored per local row entity with a padded stride (kTriPad): lanes of a warp differ in `le` only, and the
+  // unpadded strides of order 2 (384 B / 128 B) put every le on the same banks (3-way conflicts on every operand read)
+  constexpr int SM_STRIDE = Q * ND * 3 + (ORDER == 2 ? 1 : 0), SC_STRIDE = Q * ND + (ORDER == 2 ? 1 : 0);
   const int64_t i0 = pv.inc_ptr[g], i1 = pv.inc_ptr[g + 1];
   bool pecrow[Q];
 #pragma unroll
@@ -414,9 +417,10 @@ __device__ __forceinline__ void tri_entity_rows(const PatView& pv, const double*
       for (int k = 0; k < Q; ++k)
 #pragma unroll
         for (int kp = 0; kp < Q; ++kp) {
-          const int ij = (le * Q + k) * ND + u * Q + kp;
-          vT[k][kp] = gT[0] * sM[3 * ij] + gT[1] * sM[3 * ij + 1] + gT[2] * sM[3 * ij + 2];
-          vS[k][kp] = gS[0] * sC[ij];
+          const int ij = k * ND + u * Q + kp;
+          const double* __restrict__ mh = sM + le * SM_STRIDE + 3 * ij;
+          vT[k][kp] = gT[0] * mh[0] + gT[1] * mh[1] + gT[2] * mh[2];
+          vS[k][kp] = gS[0] * sC[le * SC_STRIDE + ij];
         }
       if (u == le) {
         self_slot = s;
@@ -457,11 +461,13 @@ k_values_tri(PatView pv, const double* __restrict__ coords, const int32_t* __res
   using El = Elem<2, ORDER>;
   constexpr int Q = ORDER, NEC = ORDER == 1 ? 3 : 4, ND = Q * NEC;
   constexpr int CAP = 32 * Q * Q * (2 * NEC - 1);  // values per warp tile: 32 entities x q rows x q (2 NEC - 1) columns
-  __shared__ double sM[ND * ND * 3];
-  __shared__ double sC[ND * ND];
+  constexpr int SM_ROW = Q * ND * 3, SC_ROW = Q * ND;  // entries per local row entity; padded strides as in tri_entity_rows
+  constexpr int SM_STRIDE = SM_ROW + (ORDER == 2 ? 1 : 0), SC_STRIDE = SC_ROW + (ORDER == 2 ? 1 : 0);
+  __shared__ double sM[NEC * SM_STRIDE];
+  __shared__ double sC[NEC * SC_STRIDE];
   __shared__ __align__(16) double tiles[kTriThreads / 32][2][CAP];
-  for (int t = threadIdx.x; t < ND * ND * 3; t += blockDim.x) sM[t] = El::mass(0, 0)[t];
-  for (int t = threadIdx.x; t < ND * ND; t += blockDim.x) sC[t] = El::curl(0, 0)[t];
+  for (int t = threadIdx.x; t < ND * ND * 3; t += blockDim.x) sM[(t / SM_ROW) * SM_STRIDE + t % SM_ROW] = El::mass(0, 0)[t];
+  for (int t = threadIdx.x; t < ND * ND; t += blockDim.x) sC[(t / SC_ROW) * SC_STRIDE + t % SC_ROW] = El::curl(0, 0)[t];
   __syncthreads();
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
