@@ -432,10 +432,15 @@ __device__ __forceinline__ void tri_entity_rows(const PatView& pv, const double*
 #pragma unroll
         for (int k = 0; k < Q; ++k) {
           const int64_t o = rs + (int64_t)k * Q * len + Q * s;
+          if constexpr (Q == 2) {  // o is even and the arrays are 16-byte aligned: one 16-byte store per (row, column entity)
+            *reinterpret_cast<double2*>(dS + o) = pecrow[k] ? make_double2(0.0, 0.0) : make_double2(vS[k][0], vS[k][1]);
+            *reinterpret_cast<double2*>(dT + o) = pecrow[k] ? make_double2(0.0, 0.0) : make_double2(vT[k][0], vT[k][1]);
+          } else {
 #pragma unroll
-          for (int kp = 0; kp < Q; ++kp) {
-            dS[o + kp] = pecrow[k] ? 0.0 : vS[k][kp];
-            dT[o + kp] = pecrow[k] ? 0.0 : vT[k][kp];
+            for (int kp = 0; kp < Q; ++kp) {
+              dS[o + kp] = pecrow[k] ? 0.0 : vS[k][kp];
+              dT[o + kp] = pecrow[k] ? 0.0 : vT[k][kp];
+            }
           }
         }
       }
@@ -444,10 +449,16 @@ __device__ __forceinline__ void tri_entity_rows(const PatView& pv, const double*
 #pragma unroll
   for (int k = 0; k < Q; ++k) {
     const int64_t o = rs + (int64_t)k * Q * len + Q * self_slot;
+    if constexpr (Q == 2) {
+      const double2 unit = make_double2(k == 0 ? 1.0 : 0.0, k == 1 ? 1.0 : 0.0);
+      *reinterpret_cast<double2*>(dS + o) = pecrow[k] ? unit : make_double2(selfS[k][0], selfS[k][1]);
+      *reinterpret_cast<double2*>(dT + o) = pecrow[k] ? unit : make_double2(selfT[k][0], selfT[k][1]);
+    } else {
 #pragma unroll
-    for (int kp = 0; kp < Q; ++kp) {
-      dS[o + kp] = pecrow[k] ? (kp == k ? 1.0 : 0.0) : selfS[k][kp];
-      dT[o + kp] = pecrow[k] ? (kp == k ? 1.0 : 0.0) : selfT[k][kp];
+      for (int kp = 0; kp < Q; ++kp) {
+        dS[o + kp] = pecrow[k] ? (kp == k ? 1.0 : 0.0) : selfS[k][kp];
+        dT[o + kp] = pecrow[k] ? (kp == k ? 1.0 : 0.0) : selfT[k][kp];
+      }
     }
   }
 }
