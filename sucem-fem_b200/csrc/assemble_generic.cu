@@ -403,15 +403,44 @@ __device__ __forceinline__ void tri_entity_rows(const PatView& pv, const double*
 #pragma unroll
     for (int kp = 0; kp < Q; ++kp) selfS[k][kp] = selfT[k][kp] = 0.0;
   int self_slot = 0;
-  for (int64_t i = i0; i < i1; ++i) {
+  // An entity has at most two incident cells on a manifold mesh: everything the two cells need (incidence, slots, vertex
+  // ids, coordinates, coefficients) is loaded for BOTH before either is used, so the two dependent gather chains overlap.
+  struct CellIn {
+    int le;
+    int slot[NEC];
+    double x[3][2];
+    double ceps, cmu;
+  };
+  auto load_cell = [&](int64_t i, CellIn& ci) {
     const int64_t c = pv.inc_cell[i];
-    const int le = pv.inc_loc[i];
+    ci.le = pv.inc_loc[i];
     const uint16_t* __restrict__ ps = pv.pos + (i - pv.inc_base) * NEC;
+#pragma unroll
+    for (int u = 0; u < NEC; ++u) ci.slot[u] = ps[u];
+#pragma unroll
+    for (int v = 0; v < 3; ++v) {
+      const int64_t vid = cells[c * 3 + v];
+      ci.x[v][0] = coords[vid * 2];
+      ci.x[v][1] = coords[vid * 2 + 1];
+    }
+    ci.ceps = eps ? eps[c] : 1.0;
+    ci.cmu = mu ? mu[c] : 1.0;
+  };
+  auto add_cell = [&](const CellIn& ci) {
+    const int le = ci.le;
+    // 2 x 2 geometry of the cell (cell_geometry<2> on the gathered vertices)
+    const double J00 = ci.x[1][0] - ci.x[0][0], J01 = ci.x[2][0] - ci.x[0][0];
+    const double J10 = ci.x[1][1] - ci.x[0][1], J11 = ci.x[2][1] - ci.x[0][1];
+    const double det = J00 * J11 - J01 * J10, id = 1.0 / det, ad = fabs(det);
+    const double Ji00 = J11 * id, Ji01 = -J01 * id, Ji10 = -J10 * id, Ji11 = J00 * id;
     double gT[3], gS[1];
-    cell_geometry<2>(coords, cells + c * 3, eps ? eps[c] : 1.0, mu ? mu[c] : 1.0, gT, gS, nullptr);
+    gT[0] = (Ji00 * Ji00 + Ji01 * Ji01) * ad * ci.ceps;
+    gT[1] = (Ji10 * Ji10 + Ji11 * Ji11) * ad * ci.ceps;
+    gT[2] = (Ji00 * Ji10 + Ji01 * Ji11) * ad * ci.ceps;
+    gS[0] = 1.0 / (ad * ci.cmu);
 #pragma unroll
     for (int u = 0; u < NEC; ++u) {
-      const int s = ps[u];
+      const int s = ci.slot[u];
       double vS[Q][Q], vT[Q][Q];
 #pragma unroll
       for (int k = 0; k < Q; ++k)
@@ -444,6 +473,18 @@ __device__ __forceinline__ void tri_entity_rows(const PatView& pv, const double*
           }
         }
       }
+    }
+  };
+  const int64_t n_inc = i1 - i0;
+  if (n_inc >= 1) {
+    CellIn c0, c1;
+    load_cell(i0, c0);
+    if (n_inc >= 2) load_cell(i0 + 1, c1);
+    add_cell(c0);
+    if (n_inc >= 2) add_cell(c1);
+    for (int64_t i = i0 + 2; i < i1; ++i) {  // non-manifold edges
+      load_cell(i, c0);
+      add_cell(c0);
     }
   }
 #pragma unroll
