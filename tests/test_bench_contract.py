@@ -28,3 +28,22 @@ def test_reference_arm_other_ranks_exit_quietly():
     p = subprocess.run([sys.executable, os.path.join(ROOT, 'bench.py'), '--impl', 'reference', '--steps', '1', '--warmup', '0'],
                        capture_output=True, text=True, timeout=120, env=env)
     assert p.returncode == 0 and p.stdout.strip() == ''
+
+
+def test_closed_form_workload_sizes_match_the_oracle():
+    """bench.cube_counts (the `config` both arms print) against the oracle's numbering and pattern on small cubes."""
+    import importlib.util
+    import numpy as np
+    from oracle import fem, meshes
+    spec = importlib.util.spec_from_file_location('bench', os.path.join(ROOT, 'bench.py'))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    for n in (2, 3, 5):
+        co, ce = meshes.unit_cube(n)
+        num = fem.number_entities(ce)
+        cd, ndof = fem.cell_dofs(num, 2)
+        rowptr, cols = fem.pattern(cd, ndof)
+        c = bench.cube_counts(n)
+        assert (c["tets"], c["vertices"], c["ndof"], c["nnz"]) == (len(ce), len(co), ndof, len(cols))
+    assert bench.workload_config(119, 1) == bench.workload_config(119, 1)
+    assert bench.slab_layers(119, 700e3) == 8 and bench.slab_layers(203, 700e3) == 3
