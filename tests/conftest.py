@@ -31,3 +31,11 @@ def pytest_collection_modifyitems(config, items):
 
 
 GOLDEN = os.path.join(ROOT, 'tests', 'golden')
+
+
+def free_port():
+    """A TCP port that is free right now on 127.0.0.1 (rendezvous of the multi-process tests)."""
+    import socket
+    with socket.socket(socket.AF_INET, socket.SOCK_STREAM) as sk:
+        sk.bind(('127.0.0.1', 0))
+        return sk.getsockname()[1]

@@ -10,7 +10,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from conftest import ROOT
+from conftest import ROOT, free_port
 
 
 def _worker(rank, world, port, ret):
@@ -71,7 +71,7 @@ def _worker(rank, world, port, ret):
 def test_row_blocks_gather_to_full_matrix(world):
     ctx = mp.get_context('spawn')
     ret = ctx.Manager().dict()
-    port = 29600 + world + (os.getpid() % 200)
+    port = free_port()
     procs = [ctx.Process(target=_worker, args=(r, world, port, ret)) for r in range(world)]
     for p in procs:
         p.start()

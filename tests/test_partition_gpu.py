@@ -88,9 +88,8 @@ def test_rank_host_job_single_rank_group():
     rng = np.random.default_rng(2)
     eps, mu = rng.uniform(1, 16, len(ce)), rng.uniform(1, 2, len(ce))
     ref = dev.assemble_host(co, ce, 2, eps, mu, pec='exterior')
-    os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
-    os.environ.setdefault('MASTER_PORT', str(29700 + os.getpid() % 200))
-    dist.init_process_group('nccl', rank=0, world_size=1)
+    from conftest import free_port
+    dist.init_process_group('nccl', init_method='tcp://127.0.0.1:%d' % free_port(), rank=0, world_size=1)
     try:
         rc = P.RankCells(ce, 0, len(ce))
         assert len(rc.cell_ids) == len(ce) and rc.own_lo == 0
@@ -149,7 +148,8 @@ def test_rank_host_jobs_two_processes_reproduce_the_serial_csr():
     import torch.multiprocessing as mp
     ctx = mp.get_context('spawn')
     ret = ctx.Manager().dict()
-    port = 29750 + os.getpid() % 200
+    from conftest import free_port
+    port = free_port()
     procs = [ctx.Process(target=_host_job_worker, args=(r, 2, port, ret)) for r in range(2)]
     for p in procs:
         p.start()
